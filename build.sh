@@ -1,0 +1,17 @@
+#!/bin/bash
+# Builds libgpushare_b200.so (sm_100a only) in-tree, plus the oracle's C pieces.
+# Called by __graft_entry__.build(); safe to run on a GPU-less box (nvcc cross-compiles).
+set -euo pipefail
+cd "$(dirname "$0")"
+PKG=gpushare_device_plugin_b200
+SRC=$PKG/csrc
+OUT=$PKG/libgpushare_b200.so
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+mkdir -p build
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -cudart static"
+$NVCC $FLAGS -Xptxas -v -c $SRC/hbm_probe_sm100a.cu -o build/hbm_probe_sm100a.o 2> build/ptxas_hbm_probe.log || { cat build/ptxas_hbm_probe.log; exit 1; }
+$NVCC $FLAGS -c $SRC/gsb_device.cu -o build/gsb_device.o
+g++ -O2 -std=c++17 -fPIC -Wall -c $SRC/gsb_wire.cc -o build/gsb_wire.o
+$NVCC -shared -cudart static -o $OUT build/hbm_probe_sm100a.o build/gsb_device.o build/gsb_wire.o -ldl -lpthread -lrt
+echo "built $OUT"
+if [ -f oracle/Makefile ]; then make -s -C oracle; fi

@@ -1,0 +1,416 @@
+/*
+ * gsb_wire.cc — host-only half of libgpushare_b200.so: slice arithmetic, fake device IDs, the
+ * device-plugin v1beta1 wire encoders/decoder and the Allocate decision. No CUDA in this file.
+ *
+ * Mirrors (reference paths):
+ *   pkg/gpu/nvidia/nvidia.go:26-45                      IDs and MiB->slice arithmetic
+ *   vendor/k8s.io/kubernetes/pkg/kubelet/apis/deviceplugin/v1beta1/api.pb.go
+ *        :730-767  RegisterRequest.MarshalTo     :794-812  ListAndWatchResponse.MarshalTo
+ *        :824-843  Device.MarshalTo              :940-957  ContainerAllocateRequest.MarshalTo
+ *        :969-987  AllocateResponse.MarshalTo    :999-1062 ContainerAllocateResponse.MarshalTo
+ *   pkg/gpu/nvidia/allocate.go:24-198, podutils.go:27-35,78-119, podmanager.go:215-262
+ */
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/gpushare_b200.h"
+
+namespace {
+
+inline size_t varint_size(uint64_t v) {  // sovApi
+  size_t n = 1;
+  while (v >= 0x80) {
+    v >>= 7;
+    n++;
+  }
+  return n;
+}
+
+inline uint8_t *put_varint(uint8_t *p, uint64_t v) {  // encodeVarintApi
+  while (v >= 0x80) {
+    *p++ = (uint8_t)(v | 0x80);
+    v >>= 7;
+  }
+  *p++ = (uint8_t)v;
+  return p;
+}
+
+inline uint8_t *put_bytes(uint8_t *p, uint8_t tag, const char *s, size_t n) {
+  *p++ = tag;
+  p = put_varint(p, n);
+  memcpy(p, s, n);
+  return p + n;
+}
+
+inline size_t dec_len(uint32_t v) {
+  return v < 10 ? 1 : v < 100 ? 2 : v < 1000 ? 3 : v < 10000 ? 4 : v < 100000 ? 5 : v < 1000000 ? 6
+         : v < 10000000 ? 7 : v < 100000000 ? 8 : v < 1000000000 ? 9 : 10;
+}
+
+inline char *put_dec(char *p, uint64_t v) {
+  char tmp[24];
+  int n = 0;
+  do {
+    tmp[n++] = (char)('0' + v % 10);
+    v /= 10;
+  } while (v);
+  while (n) *p++ = tmp[--n];
+  return p;
+}
+
+std::string dec(uint64_t v) {
+  char b[24];
+  return std::string(b, put_dec(b, v));
+}
+
+const char kHealthy[] = "Healthy";      // pluginapi.Healthy   (v1beta1/constants.go)
+const char kUnhealthy[] = "Unhealthy";  // pluginapi.Unhealthy
+
+// ---- minimal proto3 reader -------------------------------------------------------------
+
+struct Reader {
+  const uint8_t *p, *end;
+  bool varint(uint64_t *v) {
+    uint64_t r = 0;
+    for (int shift = 0; shift < 64; shift += 7) {
+      if (p >= end) return false;
+      const uint8_t b = *p++;
+      r |= (uint64_t)(b & 0x7F) << shift;
+      if (!(b & 0x80)) {
+        *v = r;
+        return true;
+      }
+    }
+    return false;
+  }
+  bool skip(uint32_t wire) {
+    uint64_t n;
+    switch (wire) {
+      case 0: return varint(&n);
+      case 1: if (end - p < 8) return false; p += 8; return true;
+      case 2: if (!varint(&n) || (uint64_t)(end - p) < n) return false; p += n; return true;
+      case 5: if (end - p < 4) return false; p += 4; return true;
+      default: return false;
+    }
+  }
+};
+
+// AllocateRequest -> number of devicesIDs per container request
+bool decode_allocate_request(const uint8_t *req, size_t len, std::vector<uint64_t> *per_container) {
+  Reader r{req, req + len};
+  while (r.p < r.end) {
+    uint64_t key;
+    if (!r.varint(&key)) return false;
+    const uint32_t field = (uint32_t)(key >> 3), wire = (uint32_t)(key & 7);
+    if (field == 1 && wire == 2) {  // container_requests
+      uint64_t n;
+      if (!r.varint(&n) || (uint64_t)(r.end - r.p) < n) return false;
+      Reader c{r.p, r.p + n};
+      r.p += n;
+      uint64_t ids = 0;
+      while (c.p < c.end) {
+        uint64_t k2;
+        if (!c.varint(&k2)) return false;
+        if ((k2 >> 3) == 1 && (k2 & 7) == 2) {  // devicesIDs
+          uint64_t sl;
+          if (!c.varint(&sl) || (uint64_t)(c.end - c.p) < sl) return false;
+          c.p += sl;
+          ids++;
+        } else if (!c.skip((uint32_t)(k2 & 7))) {
+          return false;
+        }
+      }
+      per_container->push_back(ids);
+    } else if (!r.skip(wire)) {
+      return false;
+    }
+  }
+  return true;
+}
+
+struct Env {
+  const char *k;
+  std::string v;
+};
+
+// ContainerAllocateResponse with only envs set; keys must arrive sorted
+size_t container_response_size(const std::vector<Env> &envs) {
+  size_t n = 0;
+  for (const Env &e : envs) {
+    const size_t kl = strlen(e.k), vl = e.v.size();
+    const size_t map_size = 1 + kl + varint_size(kl) + 1 + vl + varint_size(vl);
+    n += 1 + varint_size(map_size) + map_size;
+  }
+  return n;
+}
+
+uint8_t *put_container_response(uint8_t *p, const std::vector<Env> &envs) {
+  for (const Env &e : envs) {
+    const size_t kl = strlen(e.k), vl = e.v.size();
+    const size_t map_size = 1 + kl + varint_size(kl) + 1 + vl + varint_size(vl);
+    *p++ = 0x0a;
+    p = put_varint(p, map_size);
+    p = put_bytes(p, 0x0a, e.k, kl);
+    p = put_bytes(p, 0x12, e.v.data(), vl);
+  }
+  return p;
+}
+
+int encode_allocate_response(const std::vector<std::vector<Env>> &containers, uint8_t *resp, size_t cap,
+                             size_t *resp_len) {
+  size_t total = 0;
+  for (const auto &c : containers) {
+    const size_t sz = container_response_size(c);
+    total += 1 + varint_size(sz) + sz;
+  }
+  *resp_len = total;
+  if (!resp || cap < total) return GSB_ERR_BUFFER_TOO_SMALL;
+  uint8_t *p = resp;
+  for (const auto &c : containers) {
+    *p++ = 0x0a;
+    p = put_varint(p, container_response_size(c));
+    p = put_container_response(p, c);
+  }
+  return GSB_OK;
+}
+
+// env keys (const.go:24-32), listed in sorted order
+const char kEnvContainer[] = "ALIYUN_COM_GPU_MEM_CONTAINER";
+const char kEnvDev[] = "ALIYUN_COM_GPU_MEM_DEV";
+const char kEnvIdx[] = "ALIYUN_COM_GPU_MEM_IDX";
+const char kEnvPod[] = "ALIYUN_COM_GPU_MEM_POD";
+const char kEnvCgpuDisable[] = "CGPU_DISABLE";
+const char kEnvNvGpu[] = "NVIDIA_VISIBLE_DEVICES";
+
+// buildErrResponse (allocate.go:24-39)
+std::vector<std::vector<Env>> err_envs(const gsb_allocate_ctx *ctx, const std::vector<uint64_t> &per_container,
+                                       uint64_t pod_req) {
+  std::vector<std::vector<Env>> out;
+  for (uint64_t n : per_container) {
+    std::vector<Env> e;
+    e.push_back({kEnvContainer, dec(n)});
+    e.push_back({kEnvDev, dec(ctx->slices)});
+    e.push_back({kEnvIdx, "-1"});
+    e.push_back({kEnvPod, dec(pod_req)});
+    e.push_back({kEnvNvGpu, "no-gpu-has-" + dec(pod_req) + (ctx->unit_gib ? "GiB" : "MiB") + "-to-run"});
+    out.push_back(std::move(e));
+  }
+  return out;
+}
+
+// allocate.go:113-128 (matched pod) and :160-175 (single-GPU shortcut)
+std::vector<std::vector<Env>> ok_envs(const gsb_allocate_ctx *ctx, const std::vector<uint64_t> &per_container,
+                                      uint64_t pod_req, const std::string &visible, uint64_t idx) {
+  std::vector<std::vector<Env>> out;
+  for (uint64_t n : per_container) {
+    std::vector<Env> e;
+    e.push_back({kEnvContainer, dec(n)});
+    e.push_back({kEnvDev, dec(ctx->slices)});
+    e.push_back({kEnvIdx, dec(idx)});
+    e.push_back({kEnvPod, dec(pod_req)});
+    if (ctx->disable_cgpu_isolation) e.push_back({kEnvCgpuDisable, "true"});
+    e.push_back({kEnvNvGpu, visible});
+    out.push_back(std::move(e));
+  }
+  return out;
+}
+
+// isGPUMemoryAssumedPod (podutils.go:78-119)
+inline bool is_assumed(const gsb_pod &p) {
+  if (p.gpu_mem_limit == 0) return false;
+  if (!p.has_assume_time) return false;
+  return p.has_assigned && p.assigned_is_false;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t gsb_slices(uint64_t total_mib, int unit_gib) {
+  // setGPUMemory: v := raw; if metric == GiBPrefix { v = raw / 1024 }   (nvidia.go:34-41)
+  return (uint32_t)(unit_gib ? total_mib / 1024ull : total_mib);
+}
+
+int gsb_fake_device_id(const char *uuid, uint32_t j, char *buf, size_t cap) {
+  if (!uuid || !buf) return GSB_ERR_INVALID_ARGUMENT;
+  const size_t ul = strlen(uuid), need = ul + 3 + dec_len(j);
+  if (cap < need + 1) return GSB_ERR_BUFFER_TOO_SMALL;
+  memcpy(buf, uuid, ul);
+  memcpy(buf + ul, "-_-", 3);
+  char *e = put_dec(buf + ul + 3, j);
+  *e = 0;
+  return (int)need;
+}
+
+int gsb_real_device_id(const char *fake_id, char *buf, size_t cap) {
+  if (!fake_id || !buf) return GSB_ERR_INVALID_ARGUMENT;
+  const char *sep = strstr(fake_id, "-_-");
+  const size_t n = sep ? (size_t)(sep - fake_id) : strlen(fake_id);
+  if (cap < n + 1) return GSB_ERR_BUFFER_TOO_SMALL;
+  memcpy(buf, fake_id, n);
+  buf[n] = 0;
+  return (int)n;
+}
+
+int64_t gsb_encode_list_and_watch(const char *const *uuids, uint32_t n_gpus, uint32_t slices,
+                                  const uint8_t *unhealthy_bits, uint8_t *buf, size_t cap) {
+  if (n_gpus && !uuids) return GSB_ERR_INVALID_ARGUMENT;
+  // pass 1: size
+  size_t total = 0;
+  for (uint32_t g = 0; g < n_gpus; g++) {
+    if (!uuids[g]) return GSB_ERR_INVALID_ARGUMENT;
+    const size_t ul = strlen(uuids[g]);
+    for (uint32_t j = 0; j < slices; j++) {
+      const size_t id_len = ul + 3 + dec_len(j);
+      const size_t bit = (size_t)g * slices + j;
+      const bool bad = unhealthy_bits && (unhealthy_bits[bit >> 3] >> (bit & 7) & 1);
+      const size_t hl = bad ? sizeof(kUnhealthy) - 1 : sizeof(kHealthy) - 1;
+      const size_t dev = 1 + varint_size(id_len) + id_len + 1 + 1 + hl;
+      total += 1 + varint_size(dev) + dev;
+    }
+  }
+  if (!buf) return (int64_t)total;
+  if (cap < total) return GSB_ERR_BUFFER_TOO_SMALL;
+  // pass 2: bytes
+  uint8_t *p = buf;
+  for (uint32_t g = 0; g < n_gpus; g++) {
+    const char *u = uuids[g];
+    const size_t ul = strlen(u);
+    for (uint32_t j = 0; j < slices; j++) {
+      const size_t id_len = ul + 3 + dec_len(j);
+      const size_t bit = (size_t)g * slices + j;
+      const bool bad = unhealthy_bits && (unhealthy_bits[bit >> 3] >> (bit & 7) & 1);
+      const char *h = bad ? kUnhealthy : kHealthy;
+      const size_t hl = bad ? sizeof(kUnhealthy) - 1 : sizeof(kHealthy) - 1;
+      const size_t dev = 1 + varint_size(id_len) + id_len + 1 + 1 + hl;
+      *p++ = 0x0a;  // ListAndWatchResponse.devices
+      p = put_varint(p, dev);
+      *p++ = 0x0a;  // Device.ID
+      p = put_varint(p, id_len);
+      memcpy(p, u, ul);
+      p += ul;
+      *p++ = '-';
+      *p++ = '_';
+      *p++ = '-';
+      p = (uint8_t *)put_dec((char *)p, j);
+      p = put_bytes(p, 0x12, h, hl);  // Device.health
+    }
+  }
+  return (int64_t)(p - buf);
+}
+
+int64_t gsb_encode_register_request(const char *version, const char *endpoint, const char *resource_name,
+                                    uint8_t *buf, size_t cap) {
+  const char *f[3] = {version ? version : "", endpoint ? endpoint : "", resource_name ? resource_name : ""};
+  const uint8_t tags[3] = {0x0a, 0x12, 0x1a};
+  size_t total = 0;
+  for (int i = 0; i < 3; i++) {
+    const size_t n = strlen(f[i]);
+    if (n) total += 1 + varint_size(n) + n;  // proto3: empty strings are omitted
+  }
+  if (!buf) return (int64_t)total;
+  if (cap < total) return GSB_ERR_BUFFER_TOO_SMALL;
+  uint8_t *p = buf;
+  for (int i = 0; i < 3; i++) {
+    const size_t n = strlen(f[i]);
+    if (n) p = put_bytes(p, tags[i], f[i], n);
+  }
+  return (int64_t)(p - buf);
+}
+
+int gsb_allocate(const gsb_allocate_ctx *ctx, const gsb_pod *pods, uint32_t n_pods, const uint8_t *req,
+                 size_t req_len, uint8_t *resp, size_t resp_cap, size_t *resp_len, int32_t *pod_index,
+                 uint32_t *pod_req_gpu) {
+  if (!ctx || (!pods && n_pods) || (!req && req_len) || !resp_len) return GSB_ERR_INVALID_ARGUMENT;
+  if (pod_index) *pod_index = -1;
+  std::vector<uint64_t> per_container;
+  if (!decode_allocate_request(req, req_len, &per_container)) return GSB_ERR_MALFORMED;
+  uint64_t pod_req = 0;  // allocate.go:54-56
+  for (uint64_t n : per_container) pod_req += n;
+  if (pod_req_gpu) *pod_req_gpu = (uint32_t)pod_req;
+
+  // getPendingPodsInNode's dedupe by UID (podmanager.go:162-212), then the candidate filter
+  std::vector<uint32_t> cand;
+  for (uint32_t i = 0; i < n_pods; i++) {
+    if (!pods[i].on_node) continue;
+    bool dup = false;
+    for (uint32_t k = 0; k < i && !dup; k++)
+      dup = pods[k].on_node && pods[k].uid && pods[i].uid && strcmp(pods[k].uid, pods[i].uid) == 0;
+    if (dup) continue;
+    if (is_assumed(pods[i])) cand.push_back(i);
+  }
+  // makePodOrderdByAge: sort.Sort with Less = (t[i] <= t[j])  (podmanager.go:241-262). Go 1.10's
+  // sort.Sort on <= 12 elements is one ShellSort pass with gap 6 followed by insertionSort; with the
+  // non-strict Less that is what decides the order of pods with EQUAL assume-times, so it is
+  // restated exactly. Beyond 12 elements Go's pivot code (standard library, not in the reference
+  // tree) decides tie order; the insertion rule alone is used there (deviations).
+  auto less = [&](size_t i, size_t j) { return pods[cand[i]].assume_time <= pods[cand[j]].assume_time; };
+  if (cand.size() > 1 && cand.size() <= 12)
+    for (size_t i = 6; i < cand.size(); i++)
+      if (less(i, i - 6)) std::swap(cand[i], cand[i - 6]);
+  for (size_t i = 1; i < cand.size(); i++)
+    for (size_t j = i; j > 0 && less(j, j - 1); j--) std::swap(cand[j], cand[j - 1]);
+
+  int32_t found = -1;
+  for (uint32_t c : cand) {  // allocate.go:78-88
+    if (pods[c].gpu_mem_limit == pod_req) {
+      found = (int32_t)c;
+      break;
+    }
+  }
+
+  int kind;
+  std::vector<std::vector<Env>> envs;
+  if (found >= 0) {
+    int64_t id = pods[found].gpu_idx;  // getGPUIDFromPodAnnotation (podutils.go:37-61)
+    const char *uuid = nullptr;
+    if (id >= 0) {  // GetDeviceNameByIndex: minor -> UUID (server.go:72-83)
+      for (uint32_t g = 0; g < ctx->n_gpus; g++)
+        if (ctx->minors[g] == (uint64_t)id) uuid = ctx->uuids[g];
+      if (!uuid) id = -1;
+    }
+    if (id < 0) {
+      kind = GSB_ALLOC_ERR_RESPONSE;  // allocate.go:108-110
+      envs = err_envs(ctx, per_container, pod_req);
+    } else {
+      kind = GSB_ALLOC_MATCHED;
+      envs = ok_envs(ctx, per_container, pod_req, dec((uint64_t)id), (uint64_t)id);  // %v of int
+      if (pod_index) *pod_index = found;
+    }
+  } else if (ctx->n_gpus == 1) {  // allocate.go:151-177
+    kind = GSB_ALLOC_SINGLE_GPU;
+    envs = ok_envs(ctx, per_container, pod_req, ctx->uuids[0], ctx->minors[0]);
+  } else {
+    kind = GSB_ALLOC_ERR_RESPONSE;  // allocate.go:179-184
+    envs = err_envs(ctx, per_container, pod_req);
+  }
+  const int rc = encode_allocate_response(envs, resp, resp_cap, resp_len);
+  return rc ? rc : kind;
+}
+
+int gsb_allocate_err_response(const gsb_allocate_ctx *ctx, const uint8_t *req, size_t req_len, uint8_t *resp,
+                              size_t resp_cap, size_t *resp_len) {
+  if (!ctx || (!req && req_len) || !resp_len) return GSB_ERR_INVALID_ARGUMENT;
+  std::vector<uint64_t> per_container;
+  if (!decode_allocate_request(req, req_len, &per_container)) return GSB_ERR_MALFORMED;
+  uint64_t pod_req = 0;
+  for (uint64_t n : per_container) pod_req += n;
+  return encode_allocate_response(err_envs(ctx, per_container, pod_req), resp, resp_cap, resp_len);
+}
+
+int gsb_patch_assigned_body(uint64_t now_unix_ns, char *buf, size_t cap) {
+  if (!buf) return GSB_ERR_INVALID_ARGUMENT;
+  // json.Marshal of the nested map: keys sorted, no whitespace (podutils.go:27-35)
+  const int n = snprintf(buf, cap,
+                         "{\"metadata\":{\"annotations\":{\"ALIYUN_COM_GPU_MEM_ASSIGNED\":\"true\","
+                         "\"ALIYUN_COM_GPU_MEM_ASSUME_TIME\":\"%llu\"}}}",
+                         (unsigned long long)now_unix_ns);
+  if (n < 0 || (size_t)n >= cap) return GSB_ERR_BUFFER_TOO_SMALL;
+  return n;
+}
+
+}  // extern "C"

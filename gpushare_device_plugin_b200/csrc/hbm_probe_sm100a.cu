@@ -1,0 +1,521 @@
+/*
+ * hbm_probe_sm100a.cu — the per-device HBM probe kernels (sm_100a only).
+ *
+ * Replaces the reference's passive health half — nvml.WaitForEvent in watchXIDs
+ * (pkg/gpu/nvidia/nvidia.go:100-152), which never touches HBM — with an active walk of the arena:
+ * every 16-byte word of the window is loaded once (compared with the pattern of the generation
+ * that last wrote it) and stored once (the next generation's pattern). Algorithmic traffic of a
+ * VERIFY_REFILL launch = 2 * window bytes; bound = HBM bandwidth. Integer only,
+ * no tensor cores (this is not a contraction).
+ *
+ * Three data paths, same results bit for bit (tests/test_probe_gpu.py):
+ *   DIRECT   ld.global.v4 -> registers -> st.global.v4          (control: no staging)
+ *   CPASYNC  cp.async 16 B (LDGSTS) -> shared ring -> ld.shared.v4 -> st.global.v4
+ *   BULK     cp.async.bulk (TMA 1-D, UBLKCP) + mbarrier -> shared ring -> ld.shared.v4 /
+ *            st.shared.v4 -> cp.async.bulk shared->global
+ * All are persistent grid-stride kernels over fixed-size tiles, grid = resident CTAs/SM x #SMs.
+ *
+ * Reduction: per-thread registers -> warp shuffles -> one gsb_partial slot per CTA (plain stores,
+ * no atomics on the data path) -> a self-resetting ticket elects the last CTA, which folds all
+ * slots into the pinned host-mapped gsb_kernel_out. Checksums are XOR / wrapping-add, so the
+ * result does not depend on CTA scheduling order.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gsb_internal.h"
+#include "gsb_pattern.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr unsigned long long kNoBad = ~0ull;
+
+struct Acc {
+  uint32_t mm_words = 0, mm_bits = 0, cxor = 0, csum = 0, words = 0;
+  unsigned long long first_bad = kNoBad;
+};
+
+// ---------------------------------------------------------------- memory-op helpers (PTX)
+
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
+  uint4 v;
+  asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_stream(uint4 *p, const uint4 v) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+// TMA 1-D bulk copy shared -> global, tracked by the thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---------------------------------------------------------------- pattern + compare
+
+__device__ __forceinline__ uint4 pattern_from_key(uint32_t m, uint32_t seed_key) {
+  uint4 p;
+  p.x = (m * GSB_PAT_K0 + GSB_PAT_C0) ^ seed_key;
+  p.y = (m * GSB_PAT_K1 + GSB_PAT_C1) ^ seed_key;
+  p.z = (m * GSB_PAT_K2 + GSB_PAT_C2) ^ seed_key;
+  p.w = (m * GSB_PAT_K3 + GSB_PAT_C3) ^ seed_key;
+  return p;
+}
+
+__device__ __forceinline__ void fold_checksum(const uint4 v, Acc &acc) {
+  acc.cxor ^= v.x ^ v.y ^ v.z ^ v.w;
+  acc.csum += v.x + v.y + v.z + v.w;
+}
+
+__device__ __forceinline__ void compare_word(const uint4 v, const uint4 e, unsigned long long w, Acc &acc) {
+  const uint32_t dx = v.x ^ e.x, dy = v.y ^ e.y, dz = v.z ^ e.z, dw = v.w ^ e.w;
+  if ((dx | dy | dz | dw) != 0u) {  // cold path: a healthy device never takes it
+    acc.mm_words += 1u;
+    acc.mm_bits += __popc(dx) + __popc(dy) + __popc(dz) + __popc(dw);
+    acc.first_bad = w < acc.first_bad ? w : acc.first_bad;
+  }
+}
+
+// expected-seed key of the tile starting at absolute word w (tiles never straddle a granule when a
+// table is in use: the shim enforces 64 KiB window alignment and granules are 64 MiB)
+__device__ __forceinline__ uint32_t expect_key_of(const gsb_kernel_args &a, unsigned long long w) {
+  const uint32_t s = a.seed_table ? __ldg(a.seed_table + (w >> a.granule_shift)) : a.seed_expect;
+  return gsb_seed_key(s);
+}
+
+// one word: OP is a compile-time GSB_OP_*; `v` is the loaded value (ignored for FILL); returns the
+// value to store (undefined for VERIFY)
+template <int OP>
+__device__ __forceinline__ uint4 process_word(const uint4 v, unsigned long long w, uint32_t key_expect,
+                                              uint32_t key_write, Acc &acc) {
+  const uint32_t m = gsb_word_key(w);
+  uint4 nw = make_uint4(0, 0, 0, 0);
+  if (OP != GSB_OP_FILL) {
+    fold_checksum(v, acc);
+    compare_word(v, pattern_from_key(m, key_expect), w, acc);
+  }
+  if (OP != GSB_OP_VERIFY) {
+    nw = pattern_from_key(m, key_write);
+    if (OP == GSB_OP_FILL) fold_checksum(nw, acc);
+  }
+  acc.words += 1u;
+  return nw;
+}
+
+// ---------------------------------------------------------------- CTA epilogue
+
+__device__ __forceinline__ void warp_fold(gsb_partial &p) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    p.mismatch_words += __shfl_xor_sync(0xffffffffu, p.mismatch_words, off);
+    p.mismatch_bits += __shfl_xor_sync(0xffffffffu, p.mismatch_bits, off);
+    p.words += __shfl_xor_sync(0xffffffffu, p.words, off);
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, p.first_bad_word, off);
+    p.first_bad_word = o < p.first_bad_word ? o : p.first_bad_word;
+    p.checksum_xor ^= __shfl_xor_sync(0xffffffffu, p.checksum_xor, off);
+    p.checksum_sum += __shfl_xor_sync(0xffffffffu, p.checksum_sum, off);
+  }
+}
+
+__device__ __forceinline__ void merge(gsb_partial &d, const gsb_partial &s) {
+  d.mismatch_words += s.mismatch_words;
+  d.mismatch_bits += s.mismatch_bits;
+  d.words += s.words;
+  d.first_bad_word = s.first_bad_word < d.first_bad_word ? s.first_bad_word : d.first_bad_word;
+  d.checksum_xor ^= s.checksum_xor;
+  d.checksum_sum += s.checksum_sum;
+}
+
+__device__ __forceinline__ gsb_partial block_fold(gsb_partial p, gsb_partial *wslots) {
+  warp_fold(p);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) wslots[warp] = p;
+  __syncthreads();
+  gsb_partial r = wslots[0];
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 1; i < kWarps; i++) merge(r, wslots[i]);
+  }
+  return r;  // valid in thread 0
+}
+
+__device__ __forceinline__ gsb_partial ld_partial_cg(const gsb_partial *p) {
+  gsb_partial r;
+  r.mismatch_words = __ldcg(&p->mismatch_words);
+  r.mismatch_bits = __ldcg(&p->mismatch_bits);
+  r.first_bad_word = __ldcg(&p->first_bad_word);
+  r.words = __ldcg(&p->words);
+  r.checksum_xor = __ldcg(&p->checksum_xor);
+  r.checksum_sum = __ldcg(&p->checksum_sum);
+  return r;
+}
+
+__device__ void finish(const gsb_kernel_args &a, const Acc &acc) {
+  __shared__ gsb_partial wslots[kWarps];
+  __shared__ int is_last;
+  gsb_partial p;
+  p.mismatch_words = acc.mm_words;
+  p.mismatch_bits = acc.mm_bits;
+  p.first_bad_word = acc.first_bad;
+  p.words = acc.words;
+  p.checksum_xor = acc.cxor;
+  p.checksum_sum = acc.csum;
+  gsb_partial cta = block_fold(p, wslots);
+  if (threadIdx.x == 0) {
+    a.partials[blockIdx.x] = cta;
+    __threadfence();
+    const unsigned prev = atomicAdd(a.ticket, 1u);
+    is_last = (prev == gridDim.x - 1u);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  gsb_partial t;
+  t.mismatch_words = 0;
+  t.mismatch_bits = 0;
+  t.first_bad_word = kNoBad;
+  t.words = 0;
+  t.checksum_xor = 0;
+  t.checksum_sum = 0;
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += kThreads) merge(t, ld_partial_cg(a.partials + i));
+  __syncthreads();  // wslots reuse
+  gsb_partial all = block_fold(t, wslots);
+  if (a.table_update) {
+    // every other CTA has finished: record the generation now held by each granule this window
+    // covered completely (plus the arena's ragged tail granule when the window reaches the end)
+    const unsigned long long gw = 1ull << a.granule_shift;
+    const unsigned long long end = a.first_word + a.n_words;
+    const unsigned long long g0 = (a.first_word + gw - 1) >> a.granule_shift;
+    unsigned long long g1 = end >> a.granule_shift;
+    if (end == a.arena_words && (a.arena_words & (gw - 1))) g1 += 1;
+    for (unsigned long long g = g0 + threadIdx.x; g < g1; g += kThreads) a.table_update[g] = a.seed_write;
+  }
+  if (threadIdx.x == 0) {
+    *a.ticket = 0u;  // self-reset: the next launch on this stream starts from 0
+    gsb_kernel_out *o = a.out;
+    o->mismatch_words = all.mismatch_words;
+    o->mismatch_bits = all.mismatch_bits;
+    o->first_bad_word = all.first_bad_word;
+    o->checksum_xor = all.checksum_xor;
+    o->checksum_sum = all.checksum_sum;
+    o->words_done = all.words;
+    __threadfence_system();
+    o->done_flag = a.launch_seq;
+  }
+}
+
+// ---------------------------------------------------------------- DIRECT
+
+template <int OP, int U>
+__global__ void __launch_bounds__(kThreads) probe_direct(const gsb_kernel_args a) {
+  constexpr unsigned long long TILE = (unsigned long long)kThreads * U;
+  const unsigned long long n_tiles = (a.n_words + TILE - 1) / TILE;
+  const uint32_t key_write = gsb_seed_key(a.seed_write);
+  uint4 *__restrict__ win = a.base + a.first_word;
+  Acc acc;
+  for (unsigned long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const unsigned long long l0 = t * TILE + threadIdx.x;
+    const uint32_t key_expect = (OP != GSB_OP_FILL) ? expect_key_of(a, a.first_word + t * TILE) : 0u;
+    uint4 v[U];
+    if ((t + 1) * TILE <= a.n_words) {
+      if (OP != GSB_OP_FILL) {
+#pragma unroll
+        for (int u = 0; u < U; u++) v[u] = ld_stream(win + l0 + (unsigned long long)u * kThreads);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const unsigned long long l = l0 + (unsigned long long)u * kThreads;
+        const uint4 nw = process_word<OP>(v[u], a.first_word + l, key_expect, key_write, acc);
+        if (OP != GSB_OP_VERIFY) st_stream(win + l, nw);
+      }
+    } else {  // ragged last tile
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const unsigned long long l = l0 + (unsigned long long)u * kThreads;
+        if (l < a.n_words) {
+          if (OP != GSB_OP_FILL) v[u] = ld_stream(win + l);
+          const uint4 nw = process_word<OP>(v[u], a.first_word + l, key_expect, key_write, acc);
+          if (OP != GSB_OP_VERIFY) st_stream(win + l, nw);
+        }
+      }
+    }
+  }
+  finish(a, acc);
+}
+
+// ---------------------------------------------------------------- CPASYNC (LDGSTS ring)
+
+template <int OP, int U, int S>
+__global__ void __launch_bounds__(kThreads) probe_cpasync(const gsb_kernel_args a) {
+  static_assert(OP != GSB_OP_FILL, "FILL has no loads to stage");
+  constexpr unsigned long long TILE = (unsigned long long)kThreads * U;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint4 *ring = reinterpret_cast<uint4 *>(smem_raw);  // [S][TILE]
+  const unsigned long long n_tiles = (a.n_words + TILE - 1) / TILE;
+  const unsigned long long my_n =
+      n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0ull;
+  const uint32_t key_write = gsb_seed_key(a.seed_write);
+  uint4 *__restrict__ win = a.base + a.first_word;
+  Acc acc;
+
+  auto issue = [&](unsigned long long k) {
+    if (k < my_n) {
+      const unsigned long long t = blockIdx.x + k * gridDim.x;
+      const int s = (int)(k % S);
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const unsigned long long l = t * TILE + (unsigned long long)u * kThreads + threadIdx.x;
+        if (l < a.n_words) cp_async16(smem_u32(ring + s * TILE + u * kThreads + threadIdx.x), win + l);
+      }
+    }
+    cp_async_commit();  // always commit: keeps the group count uniform
+  };
+
+#pragma unroll
+  for (int k = 0; k < S - 1; k++) issue(k);
+  for (unsigned long long k = 0; k < my_n; k++) {
+    issue(k + S - 1);
+    cp_async_wait<S - 1>();  // tile k's copies (this thread's own 16 B slots) have landed
+    const unsigned long long t = blockIdx.x + k * gridDim.x;
+    const int s = (int)(k % S);
+    const uint32_t key_expect = expect_key_of(a, a.first_word + t * TILE);
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const unsigned long long l = t * TILE + (unsigned long long)u * kThreads + threadIdx.x;
+      if (l < a.n_words) {
+        // each thread reads back only the slots it copied itself: no CTA barrier needed
+        const uint4 v = ring[s * TILE + u * kThreads + threadIdx.x];
+        const uint4 nw = process_word<OP>(v, a.first_word + l, key_expect, key_write, acc);
+        if (OP != GSB_OP_VERIFY) st_stream(win + l, nw);
+      }
+    }
+  }
+  cp_async_wait<0>();
+  finish(a, acc);
+}
+
+// ---------------------------------------------------------------- BULK (TMA 1-D ring)
+
+template <int OP, int U, int S>
+__global__ void __launch_bounds__(kThreads) probe_bulk(const gsb_kernel_args a) {
+  constexpr unsigned long long TILE = (unsigned long long)kThreads * U;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint4 *ring = reinterpret_cast<uint4 *>(smem_raw);  // [S][TILE]
+  __shared__ __align__(8) unsigned long long full_bar[S];
+  const unsigned long long n_tiles = (a.n_words + TILE - 1) / TILE;
+  const unsigned long long my_n =
+      n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0ull;
+  const uint32_t key_write = gsb_seed_key(a.seed_write);
+  uint4 *__restrict__ win = a.base + a.first_word;
+  const bool leader = threadIdx.x == 0;
+  Acc acc;
+
+  auto tile_words = [&](unsigned long long k) -> uint32_t {
+    const unsigned long long t = blockIdx.x + k * gridDim.x;
+    const unsigned long long left = a.n_words - t * TILE;
+    return (uint32_t)(left < TILE ? left : TILE);
+  };
+  auto load = [&](unsigned long long k) {  // leader only
+    const unsigned long long t = blockIdx.x + k * gridDim.x;
+    const int s = (int)(k % S);
+    const uint32_t bytes = tile_words(k) * 16u;
+    mbar_expect_tx(smem_u32(&full_bar[s]), bytes);
+    bulk_g2s(smem_u32(ring + s * TILE), win + t * TILE, bytes, smem_u32(&full_bar[s]));
+  };
+
+  if (leader) {
+#pragma unroll
+    for (int s = 0; s < S; s++) mbar_init(smem_u32(&full_bar[s]), 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // prologue: VERIFY can keep all S stages in flight (a consumed stage is refilled at once);
+  // VERIFY_REFILL keeps S-1 (a stage is refilled one iteration after its store was issued)
+  constexpr int kPrologue = (OP == GSB_OP_VERIFY) ? S : S - 1;
+  if (OP != GSB_OP_FILL && leader) {
+    for (int k = 0; k < kPrologue; k++)
+      if ((unsigned long long)k < my_n) load(k);
+  }
+
+  for (unsigned long long k = 0; k < my_n; k++) {
+    const unsigned long long t = blockIdx.x + k * gridDim.x;
+    const int s = (int)(k % S);
+    const uint32_t nw_tile = tile_words(k);
+    uint4 *stage = ring + s * TILE;
+    if (OP == GSB_OP_FILL) {
+      // the bulk store that last read this stage (tile k-S) must have drained it
+      if (leader) bulk_wait_read<S - 1>();
+      __syncthreads();
+    } else {
+      mbar_wait(smem_u32(&full_bar[s]), (uint32_t)((k / S) & 1ull));
+    }
+    const uint32_t key_expect = (OP != GSB_OP_FILL) ? expect_key_of(a, a.first_word + t * TILE) : 0u;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint32_t i = u * kThreads + threadIdx.x;
+      if (i < nw_tile) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (OP != GSB_OP_FILL) v = stage[i];
+        const uint4 nw = process_word<OP>(v, a.first_word + t * TILE + i, key_expect, key_write, acc);
+        if (OP != GSB_OP_VERIFY) stage[i] = nw;
+      }
+    }
+    if (OP != GSB_OP_VERIFY) fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk engine
+    __syncthreads();  // every thread is done with this stage (reads, and writes + proxy fence)
+    if (leader) {
+      if (OP == GSB_OP_VERIFY) {
+        if (k + S < my_n) load(k + S);  // same stage, just released by the barrier
+      } else {
+        bulk_s2g(win + t * TILE, smem_u32(stage), nw_tile * 16u);
+        bulk_commit();
+        if (OP == GSB_OP_VERIFY_REFILL && k + S - 1 < my_n) {
+          // refill stage (k-1)%S: its store (tile k-1) must have finished READING shared memory;
+          // one group (tile k's store, just committed) may stay in flight
+          if (k >= 1) bulk_wait_read<1>();
+          load(k + S - 1);
+        }
+      }
+    }
+  }
+  if (leader && OP != GSB_OP_VERIFY) bulk_wait_all<0>();  // shared memory must outlive the stores
+  finish(a, acc);
+}
+
+// ---------------------------------------------------------------- geometry + dispatch
+
+constexpr int kDirectU = 4;
+constexpr int kCpU = 4, kCpS = 4;      // 16 KiB tiles x 4 stages = 64 KiB / CTA
+constexpr int kBulkU = 4, kBulkS = 4;  // 16 KiB tiles x 4 stages = 64 KiB / CTA
+constexpr uint32_t kCpSmem = kCpU * kThreads * 16 * kCpS;
+constexpr uint32_t kBulkSmem = kBulkU * kThreads * 16 * kBulkS;
+constexpr int kMaxCtasPerSm = 8;
+
+template <typename K>
+int resident_ctas(K kernel, uint32_t smem) {
+  int n = 0;
+  if (smem > 48 * 1024) {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return -1;
+  }
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, smem) != cudaSuccess) return -1;
+  return n;
+}
+
+typedef void (*probe_fn)(const gsb_kernel_args);
+
+probe_fn pick(uint32_t op, uint32_t variant, uint32_t *smem) {
+  *smem = 0;
+  switch (variant) {
+    case GSB_VARIANT_DIRECT:
+      if (op == GSB_OP_FILL) return probe_direct<GSB_OP_FILL, kDirectU>;
+      if (op == GSB_OP_VERIFY) return probe_direct<GSB_OP_VERIFY, kDirectU>;
+      if (op == GSB_OP_VERIFY_REFILL) return probe_direct<GSB_OP_VERIFY_REFILL, kDirectU>;
+      return nullptr;
+    case GSB_VARIANT_CPASYNC:
+      // FILL issues no loads, so there is nothing to stage: it takes the direct store path
+      if (op == GSB_OP_FILL) return probe_direct<GSB_OP_FILL, kDirectU>;
+      *smem = kCpSmem;
+      if (op == GSB_OP_VERIFY) return probe_cpasync<GSB_OP_VERIFY, kCpU, kCpS>;
+      if (op == GSB_OP_VERIFY_REFILL) return probe_cpasync<GSB_OP_VERIFY_REFILL, kCpU, kCpS>;
+      return nullptr;
+    case GSB_VARIANT_BULK:
+      *smem = kBulkSmem;
+      if (op == GSB_OP_FILL) return probe_bulk<GSB_OP_FILL, kBulkU, kBulkS>;
+      if (op == GSB_OP_VERIFY) return probe_bulk<GSB_OP_VERIFY, kBulkU, kBulkS>;
+      if (op == GSB_OP_VERIFY_REFILL) return probe_bulk<GSB_OP_VERIFY_REFILL, kBulkU, kBulkS>;
+      return nullptr;
+    default:
+      return nullptr;
+  }
+}
+
+}  // namespace
+
+uint32_t gsb_kernel_max_grid(int sm_count) { return (uint32_t)(sm_count * kMaxCtasPerSm); }
+
+int gsb_kernel_geometry(uint32_t op, uint32_t variant, uint32_t grid_request, int sm_count,
+                        gsb_launch_geom *geom) {
+  if (variant == GSB_VARIANT_AUTO) variant = GSB_VARIANT_BULK;
+  uint32_t smem = 0;
+  probe_fn fn = pick(op, variant, &smem);
+  if (!fn) return (int)cudaErrorInvalidValue;
+  int per_sm = resident_ctas(fn, smem);
+  if (per_sm <= 0) return (int)cudaErrorInvalidDeviceFunction;
+  if (per_sm > kMaxCtasPerSm) per_sm = kMaxCtasPerSm;
+  uint32_t grid = (uint32_t)(per_sm * sm_count);  // one full wave of resident CTAs: persistent
+  if (grid_request) grid = grid_request < gsb_kernel_max_grid(sm_count) ? grid_request : gsb_kernel_max_grid(sm_count);
+  geom->variant = variant;
+  geom->grid = grid;
+  geom->block = kThreads;
+  geom->smem_bytes = smem;
+  return 0;
+}
+
+int gsb_kernel_launch(uint32_t op, const gsb_launch_geom *geom, const gsb_kernel_args *args,
+                      cudaStream_t stream) {
+  uint32_t smem = 0;
+  probe_fn fn = pick(op, geom->variant, &smem);
+  if (!fn) return (int)cudaErrorInvalidValue;
+  fn<<<geom->grid, geom->block, smem, stream>>>(*args);
+  return (int)cudaGetLastError();
+}

@@ -1,0 +1,445 @@
+"""CPU oracle of the host half of the path — TEST INFRASTRUCTURE ONLY.
+
+Line-by-line restatement, in plain Python, of what the reference's Go code computes for
+inventory -> fake devices -> wire bytes, the XID filter, and Allocate. Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import it; the
+product never does.
+
+Parity status: the reference has NO tests or golden vectors for this path (its only test,
+pkg/kubelet/client/client_test.go, asserts nothing — SURVEY.md §4), and its Go sources cannot be
+compiled here (no Go toolchain). The known-answer vectors in tests/golden/wire_kat.json are direct
+readings of the cited lines (SURVEY.md §8(c) ①-⑨); the byte-level encoders are additionally checked
+against google.protobuf's own encoder driven by a descriptor built from the reference's api.proto
+field numbers (tests/test_wire_oracle.py).
+
+Every function cites the reference lines it follows (paths relative to /root/reference).
+"""
+from __future__ import annotations
+
+import json
+from typing import Dict, Iterable, List, Optional, Tuple
+
+# ---------------------------------------------------------------- const.go:11-35
+
+resourceName = "aliyun.com/gpu-mem"
+resourceCount = "aliyun.com/gpu-count"
+serverSockName = "aliyungpushare.sock"
+OptimisticLockErrorMsg = ("the object has been modified; please apply your changes to the latest version and "
+                          "try again")
+envNVGPU = "NVIDIA_VISIBLE_DEVICES"
+EnvResourceIndex = "ALIYUN_COM_GPU_MEM_IDX"
+EnvResourceByPod = "ALIYUN_COM_GPU_MEM_POD"
+EnvResourceByContainer = "ALIYUN_COM_GPU_MEM_CONTAINER"
+EnvResourceByDev = "ALIYUN_COM_GPU_MEM_DEV"
+EnvAssignedFlag = "ALIYUN_COM_GPU_MEM_ASSIGNED"
+EnvResourceAssumeTime = "ALIYUN_COM_GPU_MEM_ASSUME_TIME"
+EnvNodeLabelForDisableCGPU = "cgpu.disable.isolation"
+GiBPrefix, MiBPrefix = "GiB", "MiB"
+Healthy, Unhealthy = "Healthy", "Unhealthy"  # vendor/.../deviceplugin/v1beta1/constants.go:19-22
+Version = "v1beta1"                          # constants.go:27
+
+# ---------------------------------------------------------------- nvidia.go:26-45, bindings.go:346-349
+
+
+def generateFakeDeviceID(realID: str, fakeCounter: int) -> str:  # nvidia.go:26-28
+    return "%s-_-%d" % (realID, fakeCounter)
+
+
+def extractRealDeviceID(fakeDeviceID: str) -> str:  # nvidia.go:30-32
+    return fakeDeviceID.split("-_-")[0]
+
+
+def mib_from_bytes(total_bytes: int) -> int:  # bindings.go:346-349: *totalMem /= 1024 * 1024
+    return total_bytes // (1024 * 1024)
+
+
+def setGPUMemory(raw_mib: int, metric: str) -> int:  # nvidia.go:34-41
+    v = raw_mib
+    if metric == GiBPrefix:
+        v = raw_mib // 1024
+    return v
+
+
+def getDevices(inventory: List[dict], metric: str = GiBPrefix) -> Tuple[List[List[str]], Dict[str, int], int]:
+    """nvidia.go:53-89. `inventory` = what nvml.NewDevice returned per index:
+    {"uuid", "path": "/dev/nvidia<minor>", "memory_mib"}. Returns ([ID, Health] list, uuid->minor,
+    gpuMemory). The process-global gpuMemory is set from the FIRST device only (nvidia.go:70-72)."""
+    devs: List[List[str]] = []
+    realDevNames: Dict[str, int] = {}
+    gpuMemory = 0
+    for d in inventory:
+        path = d["path"]
+        if not path.startswith("/dev/nvidia"):  # fmt.Sscanf(d.Path, "/dev/nvidia%d", &id)  nvidia.go:65
+            raise ValueError("input does not match format")
+        digits = ""
+        for ch in path[len("/dev/nvidia"):]:
+            if ch.isdigit():
+                digits += ch
+            else:
+                break
+        if not digits:
+            raise ValueError("expected integer")
+        realDevNames[d["uuid"]] = int(digits)
+        if gpuMemory == 0:
+            gpuMemory = setGPUMemory(int(d["memory_mib"]), metric)
+        for j in range(gpuMemory):
+            devs.append([generateFakeDeviceID(d["uuid"], j), Healthy])
+    return devs, realDevNames, gpuMemory
+
+
+# ---------------------------------------------------------------- gogo wire format (api.pb.go)
+
+
+def sovApi(x: int) -> int:  # api.pb.go sovApi
+    n = 1
+    while x >= 0x80:
+        x >>= 7
+        n += 1
+    return n
+
+
+def encodeVarintApi(v: int) -> bytes:
+    out = bytearray()
+    while v >= 0x80:
+        out.append((v & 0x7F) | 0x80)
+        v >>= 7
+    out.append(v)
+    return bytes(out)
+
+
+def _str_field(tag: int, s: str) -> bytes:
+    b = s.encode()
+    return bytes([tag]) + encodeVarintApi(len(b)) + b
+
+
+def marshal_Device(ID: str, health: str) -> bytes:  # api.pb.go:824-843
+    out = b""
+    if len(ID) > 0:
+        out += _str_field(0x0A, ID)
+    if len(health) > 0:
+        out += _str_field(0x12, health)
+    return out
+
+
+def marshal_ListAndWatchResponse(devs: Iterable[Iterable[str]]) -> bytes:  # api.pb.go:794-812
+    out = bytearray()
+    for ID, health in devs:
+        d = marshal_Device(ID, health)
+        out += b"\x0a" + encodeVarintApi(len(d)) + d
+    return bytes(out)
+
+
+def marshal_RegisterRequest(version: str, endpoint: str, resource_name: str) -> bytes:  # api.pb.go:730-767
+    out = b""
+    if version:
+        out += _str_field(0x0A, version)
+    if endpoint:
+        out += _str_field(0x12, endpoint)
+    if resource_name:
+        out += _str_field(0x1A, resource_name)
+    return out
+
+
+def marshal_AllocateRequest(container_requests: List[List[str]]) -> bytes:  # api.pb.go:900-957
+    out = bytearray()
+    for ids in container_requests:
+        c = b"".join(_str_field(0x0A, s) for s in ids)
+        out += b"\x0a" + encodeVarintApi(len(c)) + c
+    return bytes(out)
+
+
+def marshal_ContainerAllocateResponse(envs: Dict[str, str], key_order: Optional[List[str]] = None) -> bytes:
+    """api.pb.go:999-1062 with only Envs set. Go iterates the map in random order (`for k := range
+    m.Envs`), so the byte string is defined only up to entry order; key_order picks one."""
+    out = bytearray()
+    for k in (key_order if key_order is not None else sorted(envs)):
+        v = envs[k]
+        kb, vb = k.encode(), v.encode()
+        mapSize = 1 + len(kb) + sovApi(len(kb)) + 1 + len(vb) + sovApi(len(vb))
+        out += b"\x0a" + encodeVarintApi(mapSize) + b"\x0a" + encodeVarintApi(len(kb)) + kb
+        out += b"\x12" + encodeVarintApi(len(vb)) + vb
+    return bytes(out)
+
+
+def marshal_AllocateResponse(container_envs: List[Dict[str, str]]) -> bytes:  # api.pb.go:969-987
+    out = bytearray()
+    for envs in container_envs:
+        c = marshal_ContainerAllocateResponse(envs)
+        out += b"\x0a" + encodeVarintApi(len(c)) + c
+    return bytes(out)
+
+
+def _read_varint(b: bytes, i: int) -> Tuple[int, int]:
+    v = shift = 0
+    while True:
+        x = b[i]
+        i += 1
+        v |= (x & 0x7F) << shift
+        if not x & 0x80:
+            return v, i
+        shift += 7
+
+
+def _fields(b: bytes) -> List[Tuple[int, int, object]]:
+    out, i = [], 0
+    while i < len(b):
+        key, i = _read_varint(b, i)
+        f, w = key >> 3, key & 7
+        if w == 0:
+            v, i = _read_varint(b, i)
+        elif w == 2:
+            n, i = _read_varint(b, i)
+            v = b[i:i + n]
+            i += n
+        elif w == 1:
+            v = b[i:i + 8]
+            i += 8
+        elif w == 5:
+            v = b[i:i + 4]
+            i += 4
+        else:
+            raise ValueError("bad wire type")
+        out.append((f, w, v))
+    return out
+
+
+def unmarshal_ListAndWatchResponse(b: bytes) -> List[List[str]]:
+    devs = []
+    for f, w, v in _fields(b):
+        if f == 1 and w == 2:
+            d = {1: "", 2: ""}
+            for f2, w2, v2 in _fields(v):
+                if w2 == 2 and f2 in d:
+                    d[f2] = v2.decode()
+            devs.append([d[1], d[2]])
+    return devs
+
+
+def unmarshal_AllocateResponse(b: bytes) -> List[Dict[str, str]]:
+    """Decoded form: one envs dict per container (the only meaningful comparison — map order is free)."""
+    out = []
+    for f, w, v in _fields(b):
+        if f == 1 and w == 2:
+            envs: Dict[str, str] = {}
+            for f2, w2, v2 in _fields(v):
+                if f2 == 1 and w2 == 2:
+                    kv = {1: b"", 2: b""}
+                    for f3, w3, v3 in _fields(v2):
+                        kv[f3] = v3
+                    envs[kv[1].decode()] = kv[2].decode()
+                else:
+                    raise AssertionError("reference never sets mounts/devices/annotations")
+            out.append(envs)
+    return out
+
+
+# ---------------------------------------------------------------- health (nvidia.go:100-152, server.go:172-189)
+
+
+def xid_event_effects(dev_ids: List[str], etype: int, edata: int, uuid: Optional[str],
+                      wait_error: bool = False) -> List[int]:
+    """Indices of fake devices that watchXIDs pushes on the xids channel for one WaitForEvent result."""
+    XidCriticalError = 0x8  # nvml.h:1082
+    if wait_error and etype != XidCriticalError:  # nvidia.go:127-129
+        return []
+    if edata in (31, 43, 45):  # nvidia.go:134-136
+        return []
+    if uuid is None or len(uuid) == 0:  # nvidia.go:138-144
+        return list(range(len(dev_ids)))
+    return [i for i, d in enumerate(dev_ids) if extractRealDeviceID(d) == uuid]  # nvidia.go:146-150
+
+
+def list_and_watch_stream(devs: List[List[str]], unhealthy_events: List[int]) -> List[bytes]:
+    """server.go:172-185: the full list once, then the full list again after EVERY health event
+    (one event per fake device; Unhealthy is sticky)."""
+    devs = [list(d) for d in devs]
+    frames = [marshal_ListAndWatchResponse(devs)]
+    for i in unhealthy_events:
+        devs[i][1] = Unhealthy
+        frames.append(marshal_ListAndWatchResponse(devs))
+    return frames
+
+
+# ---------------------------------------------------------------- podutils.go / podmanager.go
+
+
+def quantity_value(q) -> int:
+    """resource.Quantity.Value() for the forms a gpu-mem limit takes: integers, optionally with a
+    decimal-SI or binary-SI suffix; fractional values round up (Value() rounds away from zero)."""
+    if isinstance(q, int):
+        return q
+    s = str(q).strip()
+    suffixes = {"Ki": 1 << 10, "Mi": 1 << 20, "Gi": 1 << 30, "Ti": 1 << 40, "Pi": 1 << 50, "Ei": 1 << 60,
+                "k": 10 ** 3, "M": 10 ** 6, "G": 10 ** 9, "T": 10 ** 12, "P": 10 ** 15, "E": 10 ** 18}
+    mult_num, mult_den = 1, 1
+    for suf, m in suffixes.items():
+        if s.endswith(suf):
+            s, mult_num = s[: -len(suf)], m
+            break
+    else:
+        if s.endswith("m"):
+            s, mult_den = s[:-1], 1000
+    from fractions import Fraction
+    import math
+    return math.ceil(Fraction(s) * mult_num / mult_den)
+
+
+def getGPUMemoryFromPodResource(pod: dict) -> int:  # podutils.go:122-131
+    total = 0
+    for c in pod.get("spec", {}).get("containers", []) or []:
+        limits = (c.get("resources") or {}).get("limits") or {}
+        if resourceName in limits:
+            total += quantity_value(limits[resourceName])
+    return total
+
+
+def _atoi(s: str) -> Optional[int]:  # strconv.Atoi
+    t = s[1:] if s[:1] in "+-" else s
+    if not t or not all("0" <= ch <= "9" for ch in t):
+        return None
+    v = int(s)
+    if not -(1 << 63) <= v < (1 << 63):
+        return None
+    return v
+
+
+def getGPUIDFromPodAnnotation(pod: dict) -> int:  # podutils.go:37-61
+    ann = (pod.get("metadata") or {}).get("annotations") or {}
+    id_ = -1
+    if len(ann) > 0 and EnvResourceIndex in ann:
+        v = _atoi(ann[EnvResourceIndex])
+        id_ = v if v is not None else -1
+    return id_
+
+
+def getAssumeTimeFromPodAnnotation(pod: dict) -> int:  # podutils.go:64-75
+    ann = (pod.get("metadata") or {}).get("annotations") or {}
+    s = ann.get(EnvResourceAssumeTime)
+    if s is not None and s != "" and all("0" <= ch <= "9" for ch in s) and int(s) < (1 << 64):
+        return int(s)
+    return 0
+
+
+def isGPUMemoryAssumedPod(pod: dict) -> bool:  # podutils.go:78-119
+    if getGPUMemoryFromPodResource(pod) <= 0:
+        return False
+    ann = (pod.get("metadata") or {}).get("annotations") or {}
+    if EnvResourceAssumeTime not in ann:
+        return False
+    return ann.get(EnvAssignedFlag) == "false" if EnvAssignedFlag in ann else False
+
+
+def go110_sort(keys: List[int], items: list) -> list:
+    """sort.Sort as Go 1.10 runs it on <= 12 elements (quickSort's small-slice tail: one ShellSort
+    pass with gap 6, then insertionSort), with the reference's non-strict Less (`<=`,
+    podmanager.go:256-258). For more than 12 elements Go's doPivot decides the order of TIED keys;
+    that code is in the Go standard library, not under /root/reference, so ties beyond 12 candidates
+    are resolved by the same insertion rule here and in the product (DESIGN.md "deliberate
+    deviations"). Distinct keys sort identically under any algorithm."""
+    idx = list(range(len(items)))
+
+    def less(i, j):
+        return keys[idx[i]] <= keys[idx[j]]
+
+    n = len(idx)
+    if 1 < n <= 12:
+        for i in range(6, n):
+            if less(i, i - 6):
+                idx[i], idx[i - 6] = idx[i - 6], idx[i]
+    for i in range(1, n):
+        j = i
+        while j > 0 and less(j, j - 1):
+            idx[j], idx[j - 1] = idx[j - 1], idx[j]
+            j -= 1
+    return [items[i] for i in idx]
+
+
+def getCandidatePods(pod_list: List[dict], nodeName: str) -> List[dict]:  # podmanager.go:162-262
+    pods, seen = [], set()
+    for pod in pod_list:
+        if (pod.get("spec") or {}).get("nodeName") != nodeName:
+            continue
+        uid = (pod.get("metadata") or {}).get("uid")
+        if uid not in seen:
+            pods.append(pod)
+            seen.add(uid)
+    cand = [p for p in pods if isGPUMemoryAssumedPod(p)]
+    return go110_sort([getAssumeTimeFromPodAnnotation(p) for p in cand], cand)
+
+
+def patchPodAnnotationSpecAssigned(now_unix_nano: int) -> bytes:  # podutils.go:27-35 (json.Marshal sorts keys)
+    return json.dumps({"metadata": {"annotations": {EnvAssignedFlag: "true",
+                                                    EnvResourceAssumeTime: "%d" % now_unix_nano}}},
+                      separators=(",", ":"), sort_keys=True).encode()
+
+
+# ---------------------------------------------------------------- allocate.go
+
+
+def buildErrResponse(container_requests: List[List[str]], podReqGPU: int, metric: str, gpuMemory: int):
+    return [{envNVGPU: "no-gpu-has-%d%s-to-run" % (podReqGPU, metric),  # allocate.go:24-39
+             EnvResourceIndex: "-1",
+             EnvResourceByPod: "%d" % podReqGPU,
+             EnvResourceByContainer: "%d" % len(req),
+             EnvResourceByDev: "%d" % gpuMemory} for req in container_requests]
+
+
+def Allocate(container_requests: List[List[str]], pending_pods: List[dict], nodeName: str,
+             devNameMap: Dict[str, int], gpuMemory: int, metric: str = GiBPrefix,
+             disableCGPUIsolation: bool = False, list_error: bool = False, patch=None):
+    """allocate.go:42-198. Returns (container env dicts, pod that was patched or None).
+    `patch(pod, body_bytes) -> Optional[str]` performs the annotation PATCH and returns an error
+    string or None; it is retried once iff the error equals OptimisticLockErrorMsg (:135-149)."""
+    podReqGPU = sum(len(r) for r in container_requests)  # :54-56
+    if list_error:  # :62-66
+        return buildErrResponse(container_requests, podReqGPU, metric, gpuMemory), None
+    pods = getCandidatePods(pending_pods, nodeName)
+    assumePod = None
+    for pod in pods:  # :78-88
+        if getGPUMemoryFromPodResource(pod) == podReqGPU:
+            assumePod = pod
+            break
+    if assumePod is not None:
+        id_ = getGPUIDFromPodAnnotation(assumePod)  # :91
+        if id_ >= 0:
+            devIndxMap = {v: k for k, v in devNameMap.items()}  # server.go:72-83
+            if id_ not in devIndxMap:
+                id_ = -1
+        if id_ < 0:
+            return buildErrResponse(container_requests, podReqGPU, metric, gpuMemory), None  # :108-110
+        responses = []
+        for req in container_requests:  # :113-128
+            envs = {envNVGPU: "%d" % id_,
+                    EnvResourceIndex: "%d" % id_,
+                    EnvResourceByPod: "%d" % podReqGPU,
+                    EnvResourceByContainer: "%d" % len(req),
+                    EnvResourceByDev: "%d" % gpuMemory}
+            if disableCGPUIsolation:
+                envs["CGPU_DISABLE"] = "true"
+            responses.append(envs)
+        if patch is not None:  # :130-149
+            import time
+            body = patchPodAnnotationSpecAssigned(time.time_ns())
+            err = patch(assumePod, body)
+            if err is not None:
+                if err == OptimisticLockErrorMsg:
+                    err = patch(assumePod, body)
+                    if err is not None:
+                        return buildErrResponse(container_requests, podReqGPU, metric, gpuMemory), None
+                else:
+                    return buildErrResponse(container_requests, podReqGPU, metric, gpuMemory), None
+        return responses, assumePod
+    if len(devNameMap) == 1:  # :151-177
+        (devName, devIndex), = devNameMap.items()
+        responses = []
+        for req in container_requests:
+            envs = {envNVGPU: devName,
+                    EnvResourceIndex: "%d" % devIndex,
+                    EnvResourceByPod: "%d" % podReqGPU,
+                    EnvResourceByContainer: "%d" % len(req),
+                    EnvResourceByDev: "%d" % gpuMemory}
+            if disableCGPUIsolation:
+                envs["CGPU_DISABLE"] = "true"
+            responses.append(envs)
+        return responses, None
+    return buildErrResponse(container_requests, podReqGPU, metric, gpuMemory), None  # :179-184
