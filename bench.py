@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py — inventory + health-probe cycles/s (BASELINE.json's metric) on N B200s of one node.
+
+One step = one cycle of ONE device through the C ABI call `gsb_cycle` (include/gpushare_b200.h):
+fresh NVML/driver identity + memory queries -> slice count -> S fake devices -> ListAndWatchResponse
+bytes -> VERIFY_REFILL launch of the sm_100a probe kernel over this cycle's window of the arena ->
+verdict folded into Health. The path does not shard: under torchrun every rank
+is an independent replica on its own GPU, no data-path collective; value = device-cycles all ranks
+completed / max-over-ranks time ("scaling": "weak").
+
+Headline workload (config.workload): steady-state rotating window, W = 1 GiB (= one advertised
+aliyun.com/gpu-mem slice) moving across an arena of ALL allocatable HBM (~177.7 GiB), so no window is
+ever L2-resident. The full-arena walk (W = whole arena, one launch) is measured in the same run and
+reported under "full_walk" with its own roofline.
+
+  value      cycles/s from CUDA-event time of the probe launches (arena resident in HBM)
+  e2e        cycles/s from host wall time around the gsb_cycle calls (NVML queries, encode, launch,
+             stream sync, result read-back from pinned host memory) — the number to hold against
+             `--impl reference`
+  roofline   algorithmic bytes 2*W per launch / mean CUDA-event duration, vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline / --impl reference: the reference's NVML call sequence (oracle/_ref/ref_inventory,
+             built with the reference's own nvml_dl.c) timed on this box's host cores, 1 thread —
+             the reference is sequential by construction (nvidia.go:59) and budgeted 1 CPU
+             (device-plugin-ds.yaml:34-40). It never touches HBM.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GiB = 1 << 30
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "ref_inventory")
+METRIC = "inventory+health-probe cycles/sec"
+UNIT = "cycles/s"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:
+            self.proc.kill()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus: int):
+    """torch.distributed is plumbing only: barrier + max-over-ranks of the timings."""
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(
+        os.environ.get("LOCAL_RANK", 0))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("gloo")
+    return rank, world, local, dist
+
+
+def barrier_sync(dist, local):
+    if dist is not None:
+        import torch
+        dist.barrier()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize(local)
+
+
+def allmax(dist, local, x: float) -> float:
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}" if torch.cuda.is_available() else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run_reference_cycles(iters: int, warmup: int) -> dict:
+    """oracle/_ref/ref_inventory bench: inventory (11 NVML getters/GPU + fan-out + marshal) +
+    health set-up (RegisterEventForDevice per fake device) + one WaitForEvent(0 ms), per cycle, on 1
+    pinned host thread."""
+    if not os.access(REF_BIN, os.X_OK):
+        raise RuntimeError("oracle/_ref/ref_inventory missing: run build.sh where /root/reference exists")
+    cmd = [REF_BIN, "bench", "--iters", str(iters + warmup), "--wait-ms", "0"]
+    if subprocess.run(["taskset", "-c", "0", "true"], capture_output=True).returncode == 0:
+        cmd = ["taskset", "-c", "0"] + cmd
+    out = subprocess.run(cmd, check=True, capture_output=True, text=True, timeout=600)
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def cpu_model() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def bench_reference(args) -> None:
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return  # rank 0 alone runs the (sequential, single-process) reference path
+    r = run_reference_cycles(args.steps, args.warmup)
+    n = r["n_gpus"]
+    mean_us = r["cycle_us"]["mean"]
+    value = n * 1e6 / mean_us  # one node cycle covers n devices sequentially
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean_us / 1e3 / max(n, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "reference NVML path: N x nvml.NewDevice (11 getters) + fan-out + gogo marshal, "
+                               "RegisterEventForDevice x S*N, one WaitForEvent(0 ms); no HBM traffic",
+                   "devices_seen": n, "fake_devices": r["n_devices"], "lw_bytes": r["lw_len"],
+                   "register_calls_per_cycle": r["register_calls_per_cycle"], "register_rc": r["register_rc"],
+                   "phases_us_p50": {"inventory": r["inventory_us"]["p50"], "health_setup": r["health_setup_us"]["p50"],
+                                     "health_poll": r["health_poll_us"]["p50"]}},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
+                         "sample": f"{args.steps} cycles of oracle/_ref/ref_inventory (reference's nvml_dl.c), "
+                                   f"taskset -c 0, {cpu_model()}, nproc={os.cpu_count()}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def timed_cycles(cyc, steps: int, warmup: int, dist, local):
+    for _ in range(warmup):
+        cyc.step()
+    barrier_sync(dist, local)
+    kernel_ns, inv_ns, launches = 0, 0, 0
+    t0 = time.perf_counter_ns()
+    for _ in range(steps):
+        r = cyc.step()
+        if not r.healthy:
+            raise RuntimeError(f"probe reported {r.probe.mismatch_words} mismatching words — unhealthy device")
+        kernel_ns += r.probe.kernel_ns
+        inv_ns += r.inventory_ns
+        launches += 1
+    barrier_sync(dist, local)
+    wall_ns = time.perf_counter_ns() - t0
+    return wall_ns, kernel_ns, inv_ns, launches, r
+
+
+def bench_ours(args) -> None:
+    rank, world, local, dist = dist_setup(args.gpus)
+    from gpushare_device_plugin_b200 import _abi, device
+    if dist is not None:  # make NCCL allocate its buffers BEFORE the arena takes all free HBM
+        barrier_sync(dist, local)
+        allmax(dist, local, 0.0)
+    device.init()
+    n_dev = device.device_count()
+    idx = local if world > 1 else 0
+    if idx >= n_dev:
+        raise RuntimeError(f"rank {rank}: device index {idx} but only {n_dev} GPUs visible")
+    keep_free = (2 * GiB) if dist is not None else 0
+    arena = device.arena_create(idx, keep_free_bytes=keep_free)
+    variant = {"auto": 0, "direct": 1, "cpasync": 2, "bulk": 3}[args.variant]
+    peak, peak_src = measured_peak()
+    window = args.window_gib * GiB
+
+    sampler = ClockSampler(idx)
+    sampler.start()
+    # ---- headline: steady-state rotating window ------------------------------------------------
+    cyc = device.Cycler(idx, window_bytes=window, variant=variant)
+    wall_ns, kernel_ns, inv_ns, launches, last = timed_cycles(cyc, args.steps, args.warmup, dist, local)
+    # ---- same run: full-arena walk ------------------------------------------------------------------
+    full = device.Cycler(idx, window_bytes=0, variant=variant)
+    f_wall, f_kernel, f_inv, f_launches, f_last = timed_cycles(full, args.full_steps, 3, dist, local)
+    clocks = sampler.stop()
+
+    wall_s = allmax(dist, local, wall_ns / 1e9)
+    kern_s = allmax(dist, local, kernel_ns / 1e9)
+    f_wall_s = allmax(dist, local, f_wall / 1e9)
+    f_kern_s = allmax(dist, local, f_kernel / 1e9)
+    if rank != 0:
+        device.shutdown()
+        return
+
+    units = args.steps * world
+    f_units = args.full_steps * world
+    achieved = 2 * window * args.steps / (kernel_ns / 1e9) / 1e9  # this rank's kernel, GB/s
+    f_achieved = 2 * arena * args.full_steps / (f_kernel / 1e9) / 1e9
+    prof = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            prof = json.load(f)
+    except Exception:
+        pass
+    kname = {0: "probe_bulk", 1: "probe_direct", 2: "probe_cpasync", 3: "probe_bulk"}[variant]
+    line = {
+        "metric": METRIC, "value": units / kern_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": kern_s * 1e3 / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": f"1xB200-per-rank ListAndWatch inventory ({last.slices} x 1-GiB aliyun.com/gpu-mem slices, "
+                               f"{last.lw_len} B) + VERIFY_REFILL HBM probe of a rotating {args.window_gib} GiB window",
+                   "window_bytes": window, "arena_bytes": arena, "variant": _abi.VARIANT_NAMES[last.probe.variant],
+                   "grid_ctas": last.probe.grid_ctas, "block_threads": last.probe.block_threads,
+                   "l2_policy": "inputs larger than L2: the window rotates over the whole arena, no flush needed",
+                   "value_timing": "CUDA events around each probe launch, on the launching stream (inside gsb_probe)",
+                   "replicas": "one independent replica per GPU, no collective (path does not shard)",
+                   "host": f"{cpu_model()}, nproc={os.cpu_count()}"},
+        "e2e": {"value": units / wall_s, "unit": UNIT, "ms_per_step": wall_s * 1e3 / args.steps,
+                "h2d_bytes_per_step": 120, "d2h_bytes_per_step": 56,
+                "note": "gsb_cycle through ctypes: NVML+driver queries, encode, launch, stream sync; h2d = kernel "
+                        "argument block, d2h = gsb_kernel_out written by the last CTA into pinned mapped host memory; "
+                        "the ListAndWatch bytes are produced on the host",
+                "inventory_us_per_step": inv_ns / 1e3 / args.steps},
+        "gpu_launches": launches + f_launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": prof.get("window_1gib_dram_bytes_per_launch"), "kernel": kname + "<VERIFY_REFILL>",
+                     "algorithmic_bytes_per_launch": 2 * window, "peak_source": peak_src},
+        "full_walk": {"value": f_units / f_kern_s, "unit": UNIT, "steps": args.full_steps,
+                      "ms_per_step": f_kern_s * 1e3 / args.full_steps,
+                      "e2e": {"value": f_units / f_wall_s, "unit": UNIT, "ms_per_step": f_wall_s * 1e3 / args.full_steps},
+                      "window_bytes": arena,
+                      "roofline": {"bound": "hbm", "achieved": f_achieved, "peak": peak, "unit": "GB/s",
+                                   "frac": f_achieved / peak, "traffic": prof.get("full_walk_dram_bytes_per_launch"),
+                                   "algorithmic_bytes_per_launch": 2 * arena}},
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            r = run_reference_cycles(args.cpu_iters, 3)
+            line["cpu_baseline"] = {
+                "value": r["n_gpus"] * 1e6 / r["cycle_us"]["mean"], "unit": UNIT, "cores": 1, "kind": "reference",
+                "sample": f"{args.cpu_iters} cycles of oracle/_ref/ref_inventory (built with the reference's nvml_dl.c): "
+                          f"inventory p50 {r['inventory_us']['p50']} us + health set-up p50 {r['health_setup_us']['p50']} us "
+                          f"({r['register_calls_per_cycle']} NVML calls) + poll p50 {r['health_poll_us']['p50']} us; "
+                          f"taskset -c 0; no HBM traffic"}
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"failed: {e}"}
+    print(json.dumps(line))
+    device.shutdown()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--window-gib", type=int, default=1)
+    ap.add_argument("--full-steps", type=int, default=10)
+    ap.add_argument("--variant", default="auto", choices=["auto", "direct", "cpasync", "bulk"])
+    ap.add_argument("--cpu-iters", type=int, default=200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        bench_reference(args)
+    else:
+        bench_ours(args)
+    if int(os.environ.get("WORLD_SIZE", 1)) > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -22,6 +22,7 @@
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "gsb_internal.h"
 #include "gsb_pattern.h"
@@ -51,6 +52,33 @@ __device__ __forceinline__ void st_stream(uint4 *p, const uint4 v) {
   asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
                "r"(v.w)
                : "memory");
+}
+// cache-operator flavours of the direct path (experiment knob GSB_DIRECT_FLAVOR):
+// 0 = ld.cs/st.cs (streaming both ways), 1 = default ld/st, 2 = ld.L1::no_allocate + default st,
+// 3 = ld.cg/st.cg (L2 only)
+template <int F>
+__device__ __forceinline__ uint4 ld_flavor(const uint4 *p) {
+  uint4 v;
+  if (F == 0) {
+    return ld_stream(p);
+  } else if (F == 1) {
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  } else if (F == 2) {
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  } else {
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  }
+  return v;
+}
+template <int F>
+__device__ __forceinline__ void st_flavor(uint4 *p, const uint4 v) {
+  if (F == 0) {
+    st_stream(p, v);
+  } else if (F == 3) {
+    asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  } else {
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  }
 }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -265,7 +293,7 @@ __device__ void finish(const gsb_kernel_args &a, const Acc &acc) {
 
 // ---------------------------------------------------------------- DIRECT
 
-template <int OP, int U>
+template <int OP, int U, int F>
 __global__ void __launch_bounds__(kThreads) probe_direct(const gsb_kernel_args a) {
   constexpr unsigned long long TILE = (unsigned long long)kThreads * U;
   const unsigned long long n_tiles = (a.n_words + TILE - 1) / TILE;
@@ -279,22 +307,22 @@ __global__ void __launch_bounds__(kThreads) probe_direct(const gsb_kernel_args a
     if ((t + 1) * TILE <= a.n_words) {
       if (OP != GSB_OP_FILL) {
 #pragma unroll
-        for (int u = 0; u < U; u++) v[u] = ld_stream(win + l0 + (unsigned long long)u * kThreads);
+        for (int u = 0; u < U; u++) v[u] = ld_flavor<F>(win + l0 + (unsigned long long)u * kThreads);
       }
 #pragma unroll
       for (int u = 0; u < U; u++) {
         const unsigned long long l = l0 + (unsigned long long)u * kThreads;
         const uint4 nw = process_word<OP>(v[u], a.first_word + l, key_expect, key_write, acc);
-        if (OP != GSB_OP_VERIFY) st_stream(win + l, nw);
+        if (OP != GSB_OP_VERIFY) st_flavor<F>(win + l, nw);
       }
     } else {  // ragged last tile
 #pragma unroll
       for (int u = 0; u < U; u++) {
         const unsigned long long l = l0 + (unsigned long long)u * kThreads;
         if (l < a.n_words) {
-          if (OP != GSB_OP_FILL) v[u] = ld_stream(win + l);
+          if (OP != GSB_OP_FILL) v[u] = ld_flavor<F>(win + l);
           const uint4 nw = process_word<OP>(v[u], a.first_word + l, key_expect, key_write, acc);
-          if (OP != GSB_OP_VERIFY) st_stream(win + l, nw);
+          if (OP != GSB_OP_VERIFY) st_flavor<F>(win + l, nw);
         }
       }
     }
@@ -447,7 +475,6 @@ constexpr int kDirectU = 4;
 constexpr int kCpU = 4, kCpS = 4;      // 16 KiB tiles x 4 stages = 64 KiB / CTA
 constexpr int kBulkU = 4, kBulkS = 4;  // 16 KiB tiles x 4 stages = 64 KiB / CTA
 constexpr uint32_t kCpSmem = kCpU * kThreads * 16 * kCpS;
-constexpr uint32_t kBulkSmem = kBulkU * kThreads * 16 * kBulkS;
 constexpr int kMaxCtasPerSm = 8;
 
 template <typename K>
@@ -463,26 +490,67 @@ int resident_ctas(K kernel, uint32_t smem) {
 
 typedef void (*probe_fn)(const gsb_kernel_args);
 
+// experiment knob GSB_BULK_CFG: tile size x ring depth of the TMA path (0 = shipped default)
+int bulk_cfg() {
+  static const int f = [] {
+    const char *e = getenv("GSB_BULK_CFG");
+    const int v = e ? atoi(e) : 0;
+    return v < 0 || v > 5 ? 0 : v;
+  }();
+  return f;
+}
+
+int direct_flavor() {
+  static const int f = [] {
+    const char *e = getenv("GSB_DIRECT_FLAVOR");
+    const int v = e ? atoi(e) : 0;
+    return v < 0 || v > 3 ? 0 : v;
+  }();
+  return f;
+}
+
 probe_fn pick(uint32_t op, uint32_t variant, uint32_t *smem) {
   *smem = 0;
   switch (variant) {
     case GSB_VARIANT_DIRECT:
-      if (op == GSB_OP_FILL) return probe_direct<GSB_OP_FILL, kDirectU>;
-      if (op == GSB_OP_VERIFY) return probe_direct<GSB_OP_VERIFY, kDirectU>;
-      if (op == GSB_OP_VERIFY_REFILL) return probe_direct<GSB_OP_VERIFY_REFILL, kDirectU>;
+      switch (direct_flavor()) {
+#define GSB_DIRECT_CASE(F)                                                                   \
+  case F:                                                                                    \
+    if (op == GSB_OP_FILL) return probe_direct<GSB_OP_FILL, kDirectU, F>;                    \
+    if (op == GSB_OP_VERIFY) return probe_direct<GSB_OP_VERIFY, kDirectU, F>;                \
+    if (op == GSB_OP_VERIFY_REFILL) return probe_direct<GSB_OP_VERIFY_REFILL, kDirectU, F>;  \
+    return nullptr;
+        GSB_DIRECT_CASE(0)
+        GSB_DIRECT_CASE(1)
+        GSB_DIRECT_CASE(2)
+        GSB_DIRECT_CASE(3)
+#undef GSB_DIRECT_CASE
+      }
       return nullptr;
     case GSB_VARIANT_CPASYNC:
       // FILL issues no loads, so there is nothing to stage: it takes the direct store path
-      if (op == GSB_OP_FILL) return probe_direct<GSB_OP_FILL, kDirectU>;
+      if (op == GSB_OP_FILL) return probe_direct<GSB_OP_FILL, kDirectU, 0>;
       *smem = kCpSmem;
       if (op == GSB_OP_VERIFY) return probe_cpasync<GSB_OP_VERIFY, kCpU, kCpS>;
       if (op == GSB_OP_VERIFY_REFILL) return probe_cpasync<GSB_OP_VERIFY_REFILL, kCpU, kCpS>;
       return nullptr;
     case GSB_VARIANT_BULK:
-      *smem = kBulkSmem;
-      if (op == GSB_OP_FILL) return probe_bulk<GSB_OP_FILL, kBulkU, kBulkS>;
-      if (op == GSB_OP_VERIFY) return probe_bulk<GSB_OP_VERIFY, kBulkU, kBulkS>;
-      if (op == GSB_OP_VERIFY_REFILL) return probe_bulk<GSB_OP_VERIFY_REFILL, kBulkU, kBulkS>;
+      switch (bulk_cfg()) {
+#define GSB_BULK_CASE(ID, U, S)                                                              \
+  case ID:                                                                                   \
+    *smem = U * kThreads * 16 * S;                                                           \
+    if (op == GSB_OP_FILL) return probe_bulk<GSB_OP_FILL, U, S>;                             \
+    if (op == GSB_OP_VERIFY) return probe_bulk<GSB_OP_VERIFY, U, S>;                         \
+    if (op == GSB_OP_VERIFY_REFILL) return probe_bulk<GSB_OP_VERIFY_REFILL, U, S>;           \
+    return nullptr;
+        GSB_BULK_CASE(0, kBulkU, kBulkS)  // 16 KiB x 4 stages = 64 KiB/CTA (3 CTAs/SM)
+        GSB_BULK_CASE(1, 8, 3)            // 32 KiB x 3 = 96 KiB (2 CTAs/SM)
+        GSB_BULK_CASE(2, 4, 6)            // 16 KiB x 6 = 96 KiB (2 CTAs/SM)
+        GSB_BULK_CASE(3, 2, 8)            //  8 KiB x 8 = 64 KiB (3 CTAs/SM)
+        GSB_BULK_CASE(4, 4, 3)            // 16 KiB x 3 = 48 KiB (4 CTAs/SM)
+        GSB_BULK_CASE(5, 8, 6)            // 32 KiB x 6 = 192 KiB (1 CTA/SM)
+#undef GSB_BULK_CASE
+      }
       return nullptr;
     default:
       return nullptr;

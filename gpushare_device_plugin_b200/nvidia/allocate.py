@@ -1,0 +1,106 @@
+"""Allocate — mirror of pkg/gpu/nvidia/allocate.go. The decision (request decode, candidate filter,
+assume-time order, first pod whose limit equals the request, env synthesis, response encode) runs in
+the C ABI (gsb_allocate: wire bytes in, wire bytes out); this module does the control-plane I/O
+around it: list the node's pending pods, PATCH the matched pod's annotations."""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+from typing import List, Optional, Sequence
+
+from .. import _abi
+from .._abi import AllocateCtx, Pod, check, lib
+from . import const, nvidia, podmanager
+from .podutils import (getAssumeTimeFromPodAnnotation, getGPUIDFromPodAnnotation, getGPUMemoryFromPodResource,
+                       patchPodAnnotationSpecAssigned)
+
+log = logging.getLogger("gpushare.nvidia")
+
+_RESP_CAP = 1 << 16
+
+
+class AllocateContext:
+    """Immutable per-plugin inputs of gsb_allocate (devNameMap, getGPUMemory(), metric, CGPU flag)."""
+
+    def __init__(self, devNameMap: dict, slices: int, unit_gib: bool, disableCGPUIsolation: bool):
+        self._uuids_b = [u.encode() for u in devNameMap]
+        self._uuids = (C.c_char_p * len(self._uuids_b))(*self._uuids_b)
+        self._minors = (C.c_uint32 * len(self._uuids_b))(*devNameMap.values())
+        self.ctx = AllocateCtx(self._uuids, self._minors, len(self._uuids_b), slices, 1 if unit_gib else 0,
+                               1 if disableCGPUIsolation else 0)
+
+
+def pod_table(pods: Sequence[dict], nodeName: str):
+    """v1.Pod JSON -> gsb_pod[]: the fields the reference reads (podutils.go:37-131, podmanager.go:187-201)."""
+    arr = (Pod * len(pods))()
+    keep = []  # keep the bytes alive while C reads them
+    for i, p in enumerate(pods):
+        md = p.get("metadata") or {}
+        ann = md.get("annotations") or {}
+        name, ns, uid = (md.get("name") or "").encode(), (md.get("namespace") or "").encode(), (md.get("uid") or "").encode()
+        keep.append((name, ns, uid))
+        e = arr[i]
+        e.name, e.ns, e.uid = name, ns, uid
+        e.gpu_mem_limit = getGPUMemoryFromPodResource(p)
+        e.assume_time = getAssumeTimeFromPodAnnotation(p)
+        e.gpu_idx = max(-1, min(getGPUIDFromPodAnnotation(p), 0x7FFFFFFF))
+        e.has_assume_time = 1 if const.EnvResourceAssumeTime in ann else 0
+        e.has_assigned = 1 if const.EnvAssignedFlag in ann else 0
+        e.assigned_is_false = 1 if ann.get(const.EnvAssignedFlag) == "false" else 0
+        e.on_node = 1 if (p.get("spec") or {}).get("nodeName") == nodeName else 0
+    return arr, keep
+
+
+def buildErrResponse(actx: AllocateContext, req: bytes) -> bytes:  # allocate.go:24-39
+    buf = C.create_string_buffer(_RESP_CAP)
+    n = C.c_size_t(0)
+    check(lib.gsb_allocate_err_response(C.byref(actx.ctx), req, len(req), buf, _RESP_CAP, C.byref(n)),
+          "gsb_allocate_err_response")
+    return buf.raw[: n.value]
+
+
+def allocate(plugin, req: bytes) -> bytes:
+    """NvidiaDevicePlugin.Allocate (allocate.go:42-198). Never raises: every failure is encoded in the
+    response envs, exactly like the reference (gRPC status stays OK)."""
+    log.info("----Allocating GPU for gpu mem is started----")
+    actx: AllocateContext = plugin.allocate_ctx
+    with plugin.lock:  # allocate.go:59-60: one Allocate at a time
+        log.info("checking...")
+        try:
+            pods = podmanager.getPendingPodsInNode(plugin.queryKubelet, plugin.kubeletClient)
+        except Exception as e:  # noqa: BLE001  allocate.go:62-66
+            log.info("invalid allocation requst: Failed to find candidate pods due to %s", e)
+            return buildErrResponse(actx, req)
+        table, _keep = pod_table(pods, podmanager.nodeName)
+        buf = C.create_string_buffer(_RESP_CAP)
+        n, pod_index, pod_req = C.c_size_t(0), C.c_int32(-1), C.c_uint32(0)
+        kind = lib.gsb_allocate(C.byref(actx.ctx), table, len(pods), req, len(req), buf, _RESP_CAP, C.byref(n),
+                                C.byref(pod_index), C.byref(pod_req))
+        if kind < 0:
+            log.warning("Allocate: %s", _abi.last_error() or lib.gsb_strerror(kind).decode())
+            return b""  # undecodable request: nothing to answer for
+        log.info("RequestPodGPUs: %d", pod_req.value)
+        if kind == _abi.GSB_ALLOC_MATCHED:
+            pod = pods[pod_index.value]
+            md = pod["metadata"]
+            log.info("Found Assumed GPU shared Pod %s in ns %s with GPU Memory %d", md.get("name"),
+                     md.get("namespace"), pod_req.value)
+            body = patchPodAnnotationSpecAssigned()  # allocate.go:131
+            try:
+                podmanager.clientset.patch_pod(md.get("namespace"), md.get("name"), body)
+            except Exception as e:  # noqa: BLE001
+                if str(e) == const.OptimisticLockErrorMsg:  # allocate.go:138-144: one retry
+                    try:
+                        podmanager.clientset.patch_pod(md.get("namespace"), md.get("name"), body)
+                    except Exception as e2:  # noqa: BLE001
+                        log.warning("Failed due to %s", e2)
+                        return buildErrResponse(actx, req)
+                else:
+                    log.warning("Failed due to %s", e)
+                    return buildErrResponse(actx, req)
+            log.info("----Allocating GPU for gpu mem for %s is ended----", md.get("name"))
+        elif kind == _abi.GSB_ALLOC_SINGLE_GPU:
+            log.info("this node has only one gpu device,skip to search pod and directly specify the device")
+        else:
+            log.warning("invalid allocation requst: request GPU memory %d can't be satisfied.", pod_req.value)
+        return buf.raw[: n.value]

@@ -1,0 +1,190 @@
+"""Device-plugin gRPC server — mirror of pkg/gpu/nvidia/server.go.
+
+Wire surface unchanged: service v1beta1.DevicePlugin (GetDevicePluginOptions, ListAndWatch, Allocate,
+PreStartContainer) on a unix socket, and a v1beta1.Registration/Register call to the kubelet with
+{version "v1beta1", endpoint "aliyungpushare.sock", resource_name "aliyun.com/gpu-mem"}
+(server.go:150-169). All message bytes are produced/consumed by the C ABI (gsb_encode_*,
+gsb_allocate); grpcio is the HTTP/2 transport only (identity (de)serialisers, generic handlers — the
+image has no protoc and no Go toolchain).
+"""
+from __future__ import annotations
+
+import logging
+import os
+import threading
+from concurrent import futures
+from typing import Dict, List, Optional
+
+import grpc
+
+from .. import device
+from . import allocate as _allocate
+from . import const, nvidia, podmanager
+
+log = logging.getLogger("gpushare.nvidia")
+
+_SERVICE = "v1beta1.DevicePlugin"
+
+
+class NvidiaDevicePlugin:
+    """server.go:19-35. `coalesce_health=False` reproduces the reference's stream exactly (one full
+    resend per fake-device health event, server.go:179-182); True (default) folds the events that
+    are already queued into one resend — same final list, 1 frame instead of S per GPU."""
+
+    def __init__(self, mps: bool, healthCheck: bool, queryKubelet: bool, client, socket: str = const.serverSock,
+                 coalesce_health: bool = True, probe_period_ms: int = 1000, window_bytes: int = device.GiB,
+                 max_workers: int = 16):
+        self.devs, self.devNameMap = nvidia.getDevices()  # server.go:39
+        devList = list(self.devNameMap)
+        log.info("Device Map: %s", self.devNameMap)
+        log.info("Device List: %s", devList)
+        podmanager.patchGPUCount(len(devList))  # server.go:49-52
+        self.disableCGPUIsolation = podmanager.disableCGPUIsolationOrNot()  # server.go:53-56
+        self.realDevNames = devList
+        self.devIndxMap: Dict[int, str] = {}
+        self.socket = socket
+        self.mps, self.healthCheck, self.queryKubelet, self.kubeletClient = mps, healthCheck, queryKubelet, client
+        self.coalesce_health = coalesce_health
+        self.probe_period_ms, self.window_bytes = probe_period_ms, window_bytes
+        self.max_workers = max_workers
+        self.stop = threading.Event()
+        self.lock = threading.RLock()  # sync.RWMutex of server.go:34; Allocate takes it exclusively
+        self.server: Optional[grpc.Server] = None
+        # health state: bitset over self.devs + a version counter instead of the reference's unbuffered
+        # channel, so a health event never blocks when no ListAndWatch stream is attached
+        self._uuids = list(self.devNameMap)  # NVML order == insertion order of getDevices
+        self._slices = nvidia.getGPUMemory()
+        self._index = {d.ID: i for i, d in enumerate(self.devs)}
+        self._bits = bytearray((len(self.devs) + 7) // 8)
+        self._cv = threading.Condition()
+        self._pending: List[int] = []
+        self.allocate_ctx = _allocate.AllocateContext(self.devNameMap, self._slices,
+                                                      nvidia.metric == const.GiBPrefix, self.disableCGPUIsolation)
+        self._health_thread: Optional[threading.Thread] = None
+
+    # ---- helpers -------------------------------------------------------------------------
+    def GetDeviceNameByIndex(self, index: int):  # server.go:72-83
+        if len(self.devIndxMap) == 0:
+            self.devIndxMap = {v: k for k, v in self.devNameMap.items()}
+            log.info("Get devIndexMap: %s", self.devIndxMap)
+        name = self.devIndxMap.get(index)
+        return name, name is not None
+
+    def _list_bytes(self) -> bytes:
+        bits = bytes(self._bits) if any(self._bits) else None
+        return device.encode_list_and_watch(self._uuids, self._slices, bits)
+
+    # ---- RPC handlers (raw bytes in/out) ---------------------------------------------------
+    def GetDevicePluginOptions(self, request: bytes, context) -> bytes:  # server.go:85-87
+        return b""
+
+    def PreStartContainer(self, request: bytes, context) -> bytes:  # server.go:191-193
+        return b""
+
+    def ListAndWatch(self, request: bytes, context):  # server.go:172-185
+        with self._cv:
+            first = self._list_bytes()
+            cursor = len(self._pending)
+        yield first  # never yield while holding the condition's lock
+        while True:
+            with self._cv:
+                while cursor >= len(self._pending) and not self.stop.is_set() and context.is_active():
+                    self._cv.wait(0.25)
+                if self.stop.is_set() or not context.is_active():
+                    return
+                if self.coalesce_health:
+                    for i in self._pending[cursor:]:
+                        self._bits[i >> 3] |= 1 << (i & 7)
+                        self.devs[i].Health = const.Unhealthy
+                    cursor = len(self._pending)
+                    frames = [self._list_bytes()]
+                else:
+                    frames = []
+                    for i in self._pending[cursor:]:
+                        self._bits[i >> 3] |= 1 << (i & 7)  # d.Health = Unhealthy; never recovers (:180)
+                        self.devs[i].Health = const.Unhealthy
+                        frames.append(self._list_bytes())
+                    cursor = len(self._pending)
+            for f in frames:
+                yield f
+
+    def Allocate(self, request: bytes, context) -> bytes:
+        return _allocate.allocate(self, request)
+
+    # ---- health plumbing (server.go:187-189, 203-221) ----------------------------------------
+    def unhealthy(self, dev: nvidia.Device) -> None:
+        with self._cv:
+            self._pending.append(self._index[dev.ID])
+            self._cv.notify_all()
+
+    def healthcheck(self) -> None:
+        if self.healthCheck:
+            nvidia.watchXIDs(self.stop, self.devs, self.unhealthy, self.probe_period_ms, self.window_bytes)
+        else:
+            self.stop.wait()
+
+    # ---- lifecycle ---------------------------------------------------------------------------
+    def cleanup(self) -> None:  # server.go:195-201
+        try:
+            os.remove(self.socket)
+        except FileNotFoundError:
+            pass
+
+    def Start(self) -> None:  # server.go:106-134
+        self.cleanup()
+        handlers = {
+            "GetDevicePluginOptions": grpc.unary_unary_rpc_method_handler(self.GetDevicePluginOptions),
+            "ListAndWatch": grpc.unary_stream_rpc_method_handler(self.ListAndWatch),
+            "Allocate": grpc.unary_unary_rpc_method_handler(self.Allocate),
+            "PreStartContainer": grpc.unary_unary_rpc_method_handler(self.PreStartContainer),
+        }
+        self.server = grpc.server(futures.ThreadPoolExecutor(max_workers=self.max_workers))
+        self.server.add_generic_rpc_handlers((grpc.method_handlers_generic_handler(_SERVICE, handlers),))
+        self.server.add_insecure_port("unix://" + self.socket)
+        self.server.start()
+        # wait for the server to come up with a blocking self-dial, 5 s (server.go:122-127)
+        ch = grpc.insecure_channel("unix://" + self.socket)
+        try:
+            grpc.channel_ready_future(ch).result(timeout=5)
+        finally:
+            ch.close()
+        self._health_thread = threading.Thread(target=self.healthcheck, name="healthcheck", daemon=True)
+        self._health_thread.start()
+
+    def Stop(self) -> None:  # server.go:137-147
+        if self.server is None:
+            return
+        self.stop.set()
+        with self._cv:
+            self._cv.notify_all()
+        self.server.stop(0)
+        self.server = None
+        self.cleanup()
+
+    def Register(self, kubeletEndpoint: str, resourceName: str) -> None:  # server.go:150-169
+        ch = grpc.insecure_channel("unix://" + kubeletEndpoint)
+        try:
+            grpc.channel_ready_future(ch).result(timeout=5)
+            req = device.encode_register_request(const.Version, os.path.basename(self.socket), resourceName)
+            ch.unary_unary("/v1beta1.Registration/Register")(req, timeout=5)
+        finally:
+            ch.close()
+
+    def Serve(self, kubeletSocket: str = const.KubeletSocket) -> None:  # server.go:224-241
+        try:
+            self.Start()
+        except Exception as e:  # noqa: BLE001
+            log.info("Could not start device plugin: %s", e)
+            raise
+        log.info("Starting to serve on %s", self.socket)
+        try:
+            self.Register(kubeletSocket, const.resourceName)
+        except Exception as e:  # noqa: BLE001
+            log.info("Could not register device plugin: %s", e)
+            self.Stop()
+            raise
+        log.info("Registered device plugin with Kubelet")
+
+
+def NewNvidiaDevicePlugin(mps: bool, healthCheck: bool, queryKubelet: bool, client, **kw) -> NvidiaDevicePlugin:
+    return NvidiaDevicePlugin(mps, healthCheck, queryKubelet, client, **kw)

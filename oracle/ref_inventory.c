@@ -252,7 +252,8 @@ static double pct(double *v, int n, double q) {
   return v[i < 0 ? 0 : i >= n ? n - 1 : i];
 }
 
-int main(int argc, char **argv) {
+/* entry point of libref_inventory.so; oracle/ref_launcher.c dlopen()s it (see Makefile for why) */
+int ref_main(int argc, char **argv) {
   const char *mode = argc > 1 ? argv[1] : "inventory";
   int unit_gib = 1, iters = 30;
   unsigned wait_ms = 0;
