@@ -12,6 +12,6 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 $NVCC $FLAGS -Xptxas -v -c $SRC/hbm_probe_sm100a.cu -o build/hbm_probe_sm100a.o 2> build/ptxas_hbm_probe.log || { cat build/ptxas_hbm_probe.log; exit 1; }
 $NVCC $FLAGS -c $SRC/gsb_device.cu -o build/gsb_device.o
 g++ -O2 -std=c++17 -fPIC -Wall -c $SRC/gsb_wire.cc -o build/gsb_wire.o
-$NVCC -shared -cudart static -o $OUT build/hbm_probe_sm100a.o build/gsb_device.o build/gsb_wire.o -ldl -lpthread -lrt
+$NVCC -shared -gencode arch=compute_100a,code=sm_100a -cudart static -o $OUT build/hbm_probe_sm100a.o build/gsb_device.o build/gsb_wire.o -ldl -lpthread -lrt
 echo "built $OUT"
 if [ -f oracle/Makefile ]; then make -s -C oracle; fi

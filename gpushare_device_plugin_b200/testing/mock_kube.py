@@ -1,0 +1,159 @@
+"""Stateful loopback mock of the kube-apiserver calls the path makes, plus the kubelet's /pods/.
+
+  GET   /api/v1/nodes/<name>
+  PATCH /api/v1/nodes/<name>/status            (strategic merge of status.capacity / allocatable)
+  GET   /api/v1/pods?fieldSelector=spec.nodeName=<n>,status.phase=<p>
+  PATCH /api/v1/namespaces/<ns>/pods/<name>    (strategic merge of metadata.annotations)
+  GET   /pods/                                 (kubelet: every pod bound to the node)
+
+The PATCH is applied, so an assigned pod stops matching the next Allocate (config 4's requirement).
+`fail_next_patch(msg, times)` injects apiserver errors (OptimisticLock retry path).
+"""
+from __future__ import annotations
+
+import copy
+import json
+import threading
+import urllib.parse
+from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
+from typing import Dict, List, Optional
+
+
+def make_node(name: str, gpu_count: Optional[int] = None, labels: Optional[dict] = None) -> dict:
+    cap = {"cpu": "128", "memory": "2113929216Ki"}
+    if gpu_count is not None:
+        cap["aliyun.com/gpu-count"] = str(gpu_count)
+    return {"kind": "Node", "apiVersion": "v1", "metadata": {"name": name, "labels": dict(labels or {})},
+            "status": {"capacity": dict(cap), "allocatable": dict(cap)}}
+
+
+def make_pod(i: int, node: str, gpu_mem: int = 4, idx: Optional[int] = 0, assume_time: Optional[int] = None,
+             assigned: Optional[str] = "false", phase: str = "Pending", namespace: str = "default",
+             containers: int = 1) -> dict:
+    ann = {}
+    if idx is not None:
+        ann["ALIYUN_COM_GPU_MEM_IDX"] = str(idx)
+    if assume_time is not None:
+        ann["ALIYUN_COM_GPU_MEM_ASSUME_TIME"] = str(assume_time)
+    if assigned is not None:
+        ann["ALIYUN_COM_GPU_MEM_ASSIGNED"] = assigned
+    per = gpu_mem // containers
+    cs = [{"name": f"c{k}", "image": "busybox",
+           "resources": {"limits": {"aliyun.com/gpu-mem": str(per if k else gpu_mem - per * (containers - 1))}}}
+          for k in range(containers)]
+    return {"kind": "Pod", "apiVersion": "v1",
+            "metadata": {"name": f"pod-{i:02d}", "namespace": namespace, "uid": f"uid-{namespace}-{i:05d}",
+                         "annotations": ann},
+            "spec": {"nodeName": node, "containers": cs},
+            "status": {"phase": phase}}
+
+
+def config4_pods(node: str = "b200-0", n: int = 64, per_gpu: int = 8, mod: bool = False) -> List[dict]:
+    """SURVEY.md §8(d) config 4 (IDX = i div 8) / config 5 (mod=True: IDX = i mod 8)."""
+    return [make_pod(i, node, gpu_mem=4, idx=(i % 8 if mod else i // per_gpu),
+                     assume_time=1_700_000_000_000_000_000 + i) for i in range(n)]
+
+
+class MockKube:
+    def __init__(self, node: dict, pods: List[dict]):
+        self.lock = threading.Lock()
+        self.nodes: Dict[str, dict] = {node["metadata"]["name"]: node}
+        self.pods: Dict[tuple, dict] = {(p["metadata"]["namespace"], p["metadata"]["name"]): p for p in pods}
+        self.order = [(p["metadata"]["namespace"], p["metadata"]["name"]) for p in pods]
+        self.requests: List[tuple] = []
+        self._fail_patch: List[str] = []
+        self.fail_lists = 0
+        mock = self
+
+        class H(BaseHTTPRequestHandler):
+            protocol_version = "HTTP/1.1"
+
+            def log_message(self, *a):
+                pass
+
+            def _send(self, code: int, obj):
+                body = json.dumps(obj, separators=(",", ":")).encode()
+                self.send_response(code)
+                self.send_header("Content-Type", "application/json")
+                self.send_header("Content-Length", str(len(body)))
+                self.end_headers()
+                self.wfile.write(body)
+
+            def _status(self, code: int, message: str):
+                self._send(code, {"kind": "Status", "apiVersion": "v1", "status": "Failure", "message": message,
+                                  "code": code})
+
+            def do_GET(self):
+                u = urllib.parse.urlparse(self.path)
+                parts = [p for p in u.path.split("/") if p]
+                with mock.lock:
+                    mock.requests.append(("GET", self.path))
+                    if u.path == "/pods/" or u.path == "/pods":
+                        return self._send(200, {"kind": "PodList", "apiVersion": "v1",
+                                                "items": [copy.deepcopy(mock.pods[k]) for k in mock.order]})
+                    if parts[:3] == ["api", "v1", "nodes"] and len(parts) == 4:
+                        n = mock.nodes.get(parts[3])
+                        return self._send(200, n) if n else self._status(404, f'nodes "{parts[3]}" not found')
+                    if parts[:3] == ["api", "v1", "pods"]:
+                        if mock.fail_lists > 0:
+                            mock.fail_lists -= 1
+                            return self._status(500, "etcdserver: request timed out")
+                        sel = dict(kv.split("=", 1) for kv in
+                                   urllib.parse.parse_qs(u.query).get("fieldSelector", [""])[0].split(",") if "=" in kv)
+                        items = []
+                        for k in mock.order:
+                            p = mock.pods[k]
+                            if "spec.nodeName" in sel and p["spec"].get("nodeName") != sel["spec.nodeName"]:
+                                continue
+                            if "status.phase" in sel and p["status"].get("phase") != sel["status.phase"]:
+                                continue
+                            items.append(copy.deepcopy(p))
+                        return self._send(200, {"kind": "PodList", "apiVersion": "v1", "items": items})
+                self._status(404, "not found")
+
+            def do_PATCH(self):
+                u = urllib.parse.urlparse(self.path)
+                parts = [p for p in u.path.split("/") if p]
+                body = self.rfile.read(int(self.headers.get("Content-Length", "0")))
+                with mock.lock:
+                    mock.requests.append(("PATCH", self.path, body, self.headers.get("Content-Type")))
+                    try:
+                        patch = json.loads(body)
+                    except ValueError:
+                        return self._status(400, "invalid JSON patch")
+                    if parts[:3] == ["api", "v1", "nodes"] and len(parts) == 5 and parts[4] == "status":
+                        n = mock.nodes.get(parts[3])
+                        if not n:
+                            return self._status(404, f'nodes "{parts[3]}" not found')
+                        for k in ("capacity", "allocatable"):
+                            n["status"].setdefault(k, {}).update((patch.get("status") or {}).get(k) or {})
+                        return self._send(200, n)
+                    if parts[:3] == ["api", "v1", "namespaces"] and len(parts) == 6 and parts[4] == "pods":
+                        if mock._fail_patch:
+                            return self._status(409, mock._fail_patch.pop(0))
+                        p = mock.pods.get((parts[3], parts[5]))
+                        if not p:
+                            return self._status(404, f'pods "{parts[5]}" not found')
+                        p["metadata"].setdefault("annotations", {}).update(
+                            (patch.get("metadata") or {}).get("annotations") or {})
+                        return self._send(200, p)
+                self._status(404, "not found")
+
+        self.httpd = ThreadingHTTPServer(("127.0.0.1", 0), H)
+        self.httpd.daemon_threads = True
+        self.port = self.httpd.server_address[1]
+        self.url = f"http://127.0.0.1:{self.port}"
+        self.thread = threading.Thread(target=self.httpd.serve_forever, name="mock-kube", daemon=True)
+        self.thread.start()
+
+    def fail_next_patch(self, message: str, times: int = 1):
+        with self.lock:
+            self._fail_patch.extend([message] * times)
+
+    def pod(self, name: str, namespace: str = "default") -> dict:
+        with self.lock:
+            return copy.deepcopy(self.pods[(namespace, name)])
+
+    def close(self):
+        self.httpd.shutdown()
+        self.httpd.server_close()

@@ -1,0 +1,94 @@
+"""The C-ABI library loads on a GPU-less box, exports every symbol include/gpushare_b200.h declares,
+its structs have the layout the ctypes binding assumes, and device entry points FAIL LOUDLY (negative
+status, never a CPU fallback) when there is no driver."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from gpushare_device_plugin_b200 import _abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "gpushare_b200.h")
+
+
+def header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gsb_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_binding_and_library_agree():
+    declared = header_functions()
+    assert declared == sorted(_abi.SYMBOLS)
+    out = subprocess.run(["nm", "-D", "--defined-only", _abi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = sorted(set(re.findall(r" T (gsb_[a-z_0-9]+)", out)))
+    assert exported == declared
+    assert _abi.lib.gsb_abi_version() == 1
+
+
+def test_no_hard_dependency_on_cuda_or_nvml_libraries():
+    out = subprocess.run(["readelf", "-d", _abi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    needed = re.findall(r"NEEDED.*\[(.*?)\]", out)
+    assert not any("libcuda" in n or "nvidia-ml" in n or "cudart" in n for n in needed), needed
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    prog = tmp_path / "layout.c"
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "gpushare_b200.h"\n'
+                    "int main(void){\n"
+                    'printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(gsb_device_info), sizeof(gsb_probe_cfg), '
+                    "sizeof(gsb_probe_result), sizeof(gsb_cycle_result), sizeof(gsb_event), sizeof(gsb_pod), "
+                    "sizeof(gsb_allocate_ctx));\n"
+                    'printf("%zu %zu %zu %zu %zu\\n", offsetof(gsb_device_info,total_bytes), offsetof(gsb_probe_result,kernel_ns), '
+                    "offsetof(gsb_cycle_result,probe), offsetof(gsb_pod,gpu_idx), offsetof(gsb_allocate_ctx,slices));\n"
+                    "return 0;}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(prog)], check=True)
+    a, b = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()
+    assert [int(x) for x in a.split()] == [C.sizeof(t) for t in (_abi.DeviceInfo, _abi.ProbeCfg, _abi.ProbeResult,
+                                                                  _abi.CycleResult, _abi.Event, _abi.Pod,
+                                                                  _abi.AllocateCtx)]
+    assert [int(x) for x in b.split()] == [_abi.DeviceInfo.total_bytes.offset, _abi.ProbeResult.kernel_ns.offset,
+                                           _abi.CycleResult.probe.offset, _abi.Pod.gpu_idx.offset,
+                                           _abi.AllocateCtx.slices.offset]
+
+
+def test_library_carries_sm100a_code_only():
+    out = subprocess.run(["cuobjdump", "-lelf", _abi.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_\d+a?", out.stdout))
+    assert archs == {"sm_100a"}, archs
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidiactl"), reason="this box has a GPU")
+def test_device_entry_points_fail_loudly_without_a_driver():
+    rc = _abi.lib.gsb_init()
+    assert rc == _abi.GSB_ERR_LIBRARY_NOT_FOUND
+    assert "could not load" in _abi.last_error()
+    n = C.c_uint32(7)
+    assert _abi.lib.gsb_device_count(C.byref(n)) == _abi.GSB_ERR_NOT_INITIALIZED
+    info = _abi.DeviceInfo()
+    assert _abi.lib.gsb_device_info_get(0, C.byref(info)) == _abi.GSB_ERR_NOT_INITIALIZED
+    res, cfg = _abi.ProbeResult(), _abi.ProbeCfg(op=_abi.GSB_OP_VERIFY)
+    assert _abi.lib.gsb_probe(0, C.byref(cfg), C.byref(res)) == _abi.GSB_ERR_NOT_INITIALIZED
+    assert res.status == _abi.GSB_ERR_NOT_INITIALIZED
+    arena = C.c_uint64(0)
+    assert _abi.lib.gsb_arena_create(0, 0, 0, C.byref(arena)) == _abi.GSB_ERR_NOT_INITIALIZED
+    cyc = _abi.CycleResult()
+    assert _abi.lib.gsb_cycle(0, 0, 0, 1, 0, None, 0, C.byref(cyc)) == _abi.GSB_ERR_NOT_INITIALIZED
+    assert _abi.lib.gsb_health_start(0, 0) == _abi.GSB_ERR_NOT_INITIALIZED
+    with pytest.raises(_abi.GsbError):
+        _abi.check(rc, "gsb_init")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "gpushare_device_plugin_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cc", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and '"oracle/' not in text, f
