@@ -413,8 +413,20 @@ int arena_create_locked(Device *d, uint64_t max_bytes, uint64_t keep_free, uint6
   return GSB_OK;
 }
 
-int run_probe_locked(Device *d, const gsb_probe_cfg *cfg, gsb_probe_result *out) {
-  const uint64_t t_begin = now_ns();
+struct ProbeFlight {
+  gsb_probe_cfg cfg;
+  gsb_launch_geom geom;
+  gsb_kernel_args args;
+  uint64_t bytes = 0;
+  uint64_t t_begin = 0;
+  bool timed = false;
+  bool launched = false;
+};
+
+// validate + enqueue (does not wait)
+int probe_begin_locked(Device *d, const gsb_probe_cfg *cfg, gsb_probe_result *out, ProbeFlight *fl) {
+  fl->t_begin = now_ns();
+  fl->cfg = *cfg;
   memset(out, 0, sizeof *out);
   out->first_bad_offset = UINT64_MAX;
   int rc = ensure_ready(d);
@@ -429,7 +441,7 @@ int run_probe_locked(Device *d, const gsb_probe_cfg *cfg, gsb_probe_result *out)
               (unsigned long long)cfg->window_offset, (unsigned long long)cfg->window_bytes);
     return out->status = GSB_ERR_INVALID_ARGUMENT;
   }
-  uint64_t bytes = cfg->window_bytes ? cfg->window_bytes : d->arena_bytes - cfg->window_offset;
+  const uint64_t bytes = cfg->window_bytes ? cfg->window_bytes : d->arena_bytes - cfg->window_offset;
   if (cfg->window_offset + bytes > d->arena_bytes) {
     set_error("probe window [%llu, +%llu) exceeds arena of %llu bytes", (unsigned long long)cfg->window_offset,
               (unsigned long long)bytes, (unsigned long long)d->arena_bytes);
@@ -440,16 +452,14 @@ int run_probe_locked(Device *d, const gsb_probe_cfg *cfg, gsb_probe_result *out)
     set_error("seed-table probes need a 64 KiB aligned window offset");
     return out->status = GSB_ERR_INVALID_ARGUMENT;
   }
-
-  gsb_launch_geom geom;
-  int e = gsb_kernel_geometry(cfg->op, cfg->variant, cfg->grid_ctas, (int)d->sm_count, &geom);
+  int e = gsb_kernel_geometry(cfg->op, cfg->variant, cfg->grid_ctas, (int)d->sm_count, &fl->geom);
   if (e) {
     set_error("kernel geometry: %s", cudaGetErrorString((cudaError_t)e));
     return out->status = (e == (int)cudaErrorInvalidDeviceFunction || e == (int)cudaErrorNoKernelImageForDevice)
                              ? GSB_ERR_UNSUPPORTED_ARCH
                              : GSB_ERR_DRIVER;
   }
-  gsb_kernel_args a;
+  gsb_kernel_args &a = fl->args;
   memset(&a, 0, sizeof a);
   a.base = reinterpret_cast<uint4 *>(d->va);
   a.first_word = cfg->window_offset >> 4;
@@ -464,16 +474,26 @@ int run_probe_locked(Device *d, const gsb_probe_cfg *cfg, gsb_probe_result *out)
   a.partials = d->partials;
   a.ticket = d->ticket;
   a.out = d->out_dev;
-
-  const bool timed = (cfg->flags & GSB_PROBE_TIMED) != 0;
+  fl->bytes = bytes;
+  fl->timed = (cfg->flags & GSB_PROBE_TIMED) != 0;
   if (bytes > 0) {
-    if (timed) RT_TRY(cudaEventRecord(d->ev0, d->stream));
-    e = gsb_kernel_launch(cfg->op, &geom, &a, d->stream);
+    if (fl->timed) RT_TRY(cudaEventRecord(d->ev0, d->stream));
+    e = gsb_kernel_launch(cfg->op, &fl->geom, &a, d->stream);
     if (e) {
       set_error("kernel launch: %s", cudaGetErrorString((cudaError_t)e));
       return out->status = GSB_ERR_DRIVER;
     }
-    if (timed) RT_TRY(cudaEventRecord(d->ev1, d->stream));
+    if (fl->timed) RT_TRY(cudaEventRecord(d->ev1, d->stream));
+    fl->launched = true;
+  }
+  return GSB_OK;
+}
+
+// wait for the launch and collect what the last CTA wrote into pinned host memory
+int probe_end_locked(Device *d, ProbeFlight *fl, gsb_probe_result *out) {
+  const gsb_probe_cfg *cfg = &fl->cfg;
+  const gsb_kernel_args &a = fl->args;
+  if (fl->launched) {
     cudaError_t se = cudaStreamSynchronize(d->stream);
     if (se != cudaSuccess) {
       set_error("probe kernel failed: %s", cudaGetErrorString(se));
@@ -491,26 +511,33 @@ int run_probe_locked(Device *d, const gsb_probe_cfg *cfg, gsb_probe_result *out)
     out->first_bad_offset = ko.first_bad_word == ~0ull ? UINT64_MAX : ko.first_bad_word << 4;
     out->checksum_xor = ko.checksum_xor;
     out->checksum_sum = ko.checksum_sum;
-    if (timed) {
+    if (fl->timed) {
       float ms = 0.f;
       RT_TRY(cudaEventElapsedTime(&ms, d->ev0, d->ev1));
       out->kernel_ns = (uint64_t)((double)ms * 1e6);
     }
     if (a.table_update) {  // host mirror of what the kernel's last CTA wrote
       const uint64_t g0 = (cfg->window_offset + kGranuleBytes - 1) / kGranuleBytes;
-      const uint64_t g1 = (cfg->window_offset + bytes) / kGranuleBytes;
-      const bool tail = cfg->window_offset + bytes == d->arena_bytes && (d->arena_bytes % kGranuleBytes);
+      const uint64_t g1 = (cfg->window_offset + fl->bytes) / kGranuleBytes;
+      const bool tail = cfg->window_offset + fl->bytes == d->arena_bytes && (d->arena_bytes % kGranuleBytes);
       for (uint64_t g = g0; g < g1 + (tail ? 1 : 0) && g < d->gen.size(); g++) d->gen[g] = cfg->seed_write;
     }
   }
-  out->variant = geom.variant;
-  out->grid_ctas = geom.grid;
-  out->block_threads = geom.block;
-  out->bytes_walked = bytes;
-  out->bytes_read = cfg->op == GSB_OP_FILL ? 0 : bytes;
-  out->bytes_written = cfg->op == GSB_OP_VERIFY ? 0 : bytes;
-  out->wall_ns = now_ns() - t_begin;
+  out->variant = fl->geom.variant;
+  out->grid_ctas = fl->geom.grid;
+  out->block_threads = fl->geom.block;
+  out->bytes_walked = fl->bytes;
+  out->bytes_read = cfg->op == GSB_OP_FILL ? 0 : fl->bytes;
+  out->bytes_written = cfg->op == GSB_OP_VERIFY ? 0 : fl->bytes;
+  out->wall_ns = now_ns() - fl->t_begin;
   return out->status = GSB_OK;
+}
+
+int run_probe_locked(Device *d, const gsb_probe_cfg *cfg, gsb_probe_result *out) {
+  ProbeFlight fl;
+  int rc = probe_begin_locked(d, cfg, out, &fl);
+  if (rc) return rc;
+  return probe_end_locked(d, &fl, out);
 }
 
 int query_info(Device *d, gsb_device_info *out) {
@@ -774,36 +801,12 @@ int gsb_cycle(uint32_t idx, uint64_t cycle_no, uint64_t window_bytes, int unit_g
     set_error("cycle window must be a multiple of 64 MiB (or 0 = whole arena)");
     return GSB_ERR_INVALID_ARGUMENT;
   }
-  // 1. inventory: fresh identity + memory info, slices, S fake devices, wire bytes
-  const uint64_t t0 = now_ns();
-  int rc = query_info(d, &out->info);
-  if (rc) return rc;
-  out->info.index = idx;
-  out->slices = gsb_slices(out->info.total_mib, unit_gib);
-  const char *uuids[1] = {out->info.uuid};
   std::lock_guard<std::mutex> lk(d->mu);
-  uint8_t bits_stack[64];
-  std::vector<uint8_t> bits_heap;
-  uint8_t *bits = nullptr;
-  if (d->faulted) {  // sticky: every fake device of a faulted GPU is Unhealthy (nvidia.go:146-150)
-    const size_t nb = (out->slices + 7) / 8;
-    if (nb <= sizeof bits_stack) {
-      bits = bits_stack;
-    } else {
-      bits_heap.resize(nb);
-      bits = bits_heap.data();
-    }
-    memset(bits, 0xFF, nb);
-  }
-  out->lw_len = gsb_encode_list_and_watch(uuids, 1, out->slices, bits, lw_buf, lw_cap);
-  if (out->lw_len < 0) return (int)out->lw_len;
-  out->inventory_ns = now_ns() - t0;
-
-  // 2. health: VERIFY_REFILL of this cycle's window
   if (!d->va) {
     set_error("no arena on %s: call gsb_arena_create first", d->uuid);
     return GSB_ERR_NO_ARENA;
   }
+  // 1. health: enqueue the VERIFY_REFILL of this cycle's window (asynchronous)
   gsb_probe_cfg cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.op = GSB_OP_VERIFY_REFILL;
@@ -816,17 +819,37 @@ int gsb_cycle(uint32_t idx, uint64_t cycle_no, uint64_t window_bytes, int unit_g
   }
   cfg.seed_write = d->next_gen++;
   if (d->next_gen == 0) d->next_gen = 1;
-  rc = run_probe_locked(d, &cfg, &out->probe);
-  out->healthy = (rc == GSB_OK && out->probe.mismatch_words == 0) ? 1u : 0u;
+  ProbeFlight fl;
+  int prc = probe_begin_locked(d, &cfg, &out->probe, &fl);
+
+  // 2. inventory while the kernel walks HBM: fresh identity + memory info, slices, S fake devices,
+  //    wire bytes (optimistically with the health this device had going into the cycle)
+  const uint64_t t0 = now_ns();
+  int rc = query_info(d, &out->info);
+  if (rc == GSB_OK) {
+    out->info.index = idx;
+    out->slices = gsb_slices(out->info.total_mib, unit_gib);
+  }
+  const char *uuids[1] = {out->info.uuid};
+  std::vector<uint8_t> bits;
+  auto encode = [&](bool unhealthy) -> int64_t {
+    if (unhealthy) bits.assign((out->slices + 7) / 8, 0xFF);  // every fake device of a faulted GPU (nvidia.go:146-150)
+    return gsb_encode_list_and_watch(uuids, 1, out->slices, unhealthy ? bits.data() : nullptr, lw_buf, lw_cap);
+  };
+  if (rc == GSB_OK) out->lw_len = encode(d->faulted);
+  out->inventory_ns = now_ns() - t0;
+
+  // 3. verdict
+  if (prc == GSB_OK) prc = probe_end_locked(d, &fl, &out->probe);
+  if (rc) return rc;
+  if (out->lw_len < 0) return (int)out->lw_len;
+  out->healthy = (prc == GSB_OK && out->probe.mismatch_words == 0) ? 1u : 0u;
   if (!out->healthy && !d->faulted) {
-    d->faulted = true;
-    // 3. verdict changed: the list this cycle reports must already carry it
-    const size_t nb = (out->slices + 7) / 8;
-    std::vector<uint8_t> all(nb, 0xFF);
-    out->lw_len = gsb_encode_list_and_watch(uuids, 1, out->slices, all.data(), lw_buf, lw_cap);
+    d->faulted = true;  // sticky (server.go:180 FIXME): the list this cycle reports already carries it
+    out->lw_len = encode(true);
     if (out->lw_len < 0) return (int)out->lw_len;
   }
-  return rc;
+  return prc;
 }
 
 // ---------------------------------------------------------------------- health

@@ -31,6 +31,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
+constexpr int kMaxWarps = 16;
 constexpr unsigned long long kNoBad = ~0ull;
 
 struct Acc {
@@ -69,6 +70,14 @@ __device__ __forceinline__ uint4 ld_flavor(const uint4 *p) {
     asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   }
   return v;
+}
+// A refill stores to the address it has just loaded from, and the stored value does not depend on
+// the loaded one. Left alone, the store issues while the load is still in flight and the memory
+// system serialises the pair: measured 0.12 of HBM peak (profiles/sweep_r01_variants.json, "direct"
+// "refill"). Naming the loaded register as an (unused) asm input makes the store wait for the data.
+__device__ __forceinline__ uint4 after_load(uint4 nw, uint32_t loaded) {
+  asm volatile("// order after load %1" : "+r"(nw.x) : "r"(loaded));
+  return nw;
 }
 template <int F>
 __device__ __forceinline__ void st_flavor(uint4 *p, const uint4 v) {
@@ -216,12 +225,12 @@ __device__ __forceinline__ void merge(gsb_partial &d, const gsb_partial &s) {
 __device__ __forceinline__ gsb_partial block_fold(gsb_partial p, gsb_partial *wslots) {
   warp_fold(p);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_warps = (int)(blockDim.x >> 5);
   if (lane == 0) wslots[warp] = p;
   __syncthreads();
   gsb_partial r = wslots[0];
   if (threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 1; i < kWarps; i++) merge(r, wslots[i]);
+    for (int i = 1; i < n_warps; i++) merge(r, wslots[i]);
   }
   return r;  // valid in thread 0
 }
@@ -238,7 +247,7 @@ __device__ __forceinline__ gsb_partial ld_partial_cg(const gsb_partial *p) {
 }
 
 __device__ void finish(const gsb_kernel_args &a, const Acc &acc) {
-  __shared__ gsb_partial wslots[kWarps];
+  __shared__ gsb_partial wslots[kMaxWarps];
   __shared__ int is_last;
   gsb_partial p;
   p.mismatch_words = acc.mm_words;
@@ -264,7 +273,7 @@ __device__ void finish(const gsb_kernel_args &a, const Acc &acc) {
   t.words = 0;
   t.checksum_xor = 0;
   t.checksum_sum = 0;
-  for (unsigned i = threadIdx.x; i < gridDim.x; i += kThreads) merge(t, ld_partial_cg(a.partials + i));
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) merge(t, ld_partial_cg(a.partials + i));
   __syncthreads();  // wslots reuse
   gsb_partial all = block_fold(t, wslots);
   if (a.table_update) {
@@ -275,7 +284,7 @@ __device__ void finish(const gsb_kernel_args &a, const Acc &acc) {
     const unsigned long long g0 = (a.first_word + gw - 1) >> a.granule_shift;
     unsigned long long g1 = end >> a.granule_shift;
     if (end == a.arena_words && (a.arena_words & (gw - 1))) g1 += 1;
-    for (unsigned long long g = g0 + threadIdx.x; g < g1; g += kThreads) a.table_update[g] = a.seed_write;
+    for (unsigned long long g = g0 + threadIdx.x; g < g1; g += blockDim.x) a.table_update[g] = a.seed_write;
   }
   if (threadIdx.x == 0) {
     *a.ticket = 0u;  // self-reset: the next launch on this stream starts from 0
@@ -312,7 +321,8 @@ __global__ void __launch_bounds__(kThreads) probe_direct(const gsb_kernel_args a
 #pragma unroll
       for (int u = 0; u < U; u++) {
         const unsigned long long l = l0 + (unsigned long long)u * kThreads;
-        const uint4 nw = process_word<OP>(v[u], a.first_word + l, key_expect, key_write, acc);
+        uint4 nw = process_word<OP>(v[u], a.first_word + l, key_expect, key_write, acc);
+        if (OP == GSB_OP_VERIFY_REFILL) nw = after_load(nw, v[u].x ^ v[u].y ^ v[u].z ^ v[u].w);
         if (OP != GSB_OP_VERIFY) st_flavor<F>(win + l, nw);
       }
     } else {  // ragged last tile
@@ -321,7 +331,8 @@ __global__ void __launch_bounds__(kThreads) probe_direct(const gsb_kernel_args a
         const unsigned long long l = l0 + (unsigned long long)u * kThreads;
         if (l < a.n_words) {
           if (OP != GSB_OP_FILL) v[u] = ld_flavor<F>(win + l);
-          const uint4 nw = process_word<OP>(v[u], a.first_word + l, key_expect, key_write, acc);
+          uint4 nw = process_word<OP>(v[u], a.first_word + l, key_expect, key_write, acc);
+          if (OP == GSB_OP_VERIFY_REFILL) nw = after_load(nw, v[u].x ^ v[u].y ^ v[u].z ^ v[u].w);
           if (OP != GSB_OP_VERIFY) st_flavor<F>(win + l, nw);
         }
       }
@@ -469,6 +480,110 @@ __global__ void __launch_bounds__(kThreads) probe_bulk(const gsb_kernel_args a) 
   finish(a, acc);
 }
 
+// ---------------------------------------------------------------- BULKW (per-warp TMA rings)
+//
+// Same data path as BULK, but every warp owns a private ring of S stages of WPL*512 bytes and its own
+// mbarriers; lane 0 issues that warp's bulk loads/stores. Nothing on the data path synchronises the
+// CTA (only __syncwarp), so a warp waiting on HBM never holds the other warps at a barrier. The warps
+// of a CTA take adjacent chunks of one contiguous super-tile, which keeps DRAM pages hot.
+template <int OP, int WPL, int S, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) probe_bulk_warp(const gsb_kernel_args a) {
+  constexpr unsigned long long TILE = (unsigned long long)WPL * 32;  // words per warp-tile
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint4 *ring = reinterpret_cast<uint4 *>(smem_raw) + (size_t)warp * S * TILE;  // [S][TILE]
+  __shared__ __align__(8) unsigned long long full_bar[WARPS][S];
+  const unsigned long long n_tiles = (a.n_words + TILE - 1) / TILE;
+  // k-th tile of this warp: warps of one CTA sit side by side inside a WARPS*TILE super-tile
+  auto tile_of = [&](unsigned long long k) -> unsigned long long {
+    return (blockIdx.x + k * gridDim.x) * WARPS + warp;
+  };
+  const unsigned long long first = tile_of(0);
+  const unsigned long long stride = (unsigned long long)gridDim.x * WARPS;
+  const unsigned long long my_n = n_tiles > first ? (n_tiles - first + stride - 1) / stride : 0ull;
+  const uint32_t key_write = gsb_seed_key(a.seed_write);
+  uint4 *__restrict__ win = a.base + a.first_word;
+  const bool leader = lane == 0;
+  Acc acc;
+
+  auto tile_words = [&](unsigned long long k) -> uint32_t {
+    const unsigned long long left = a.n_words - tile_of(k) * TILE;
+    return (uint32_t)(left < TILE ? left : TILE);
+  };
+  auto load = [&](unsigned long long k) {  // leader only
+    const int s = (int)(k % S);
+    const uint32_t bytes = tile_words(k) * 16u;
+    mbar_expect_tx(smem_u32(&full_bar[warp][s]), bytes);
+    bulk_g2s(smem_u32(ring + s * TILE), win + tile_of(k) * TILE, bytes, smem_u32(&full_bar[warp][s]));
+  };
+
+  if (leader) {
+#pragma unroll
+    for (int s = 0; s < S; s++) mbar_init(smem_u32(&full_bar[warp][s]), 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  constexpr int kPrologue = (OP == GSB_OP_VERIFY) ? S : S - 1;
+  if (OP != GSB_OP_FILL && leader) {
+    for (int k = 0; k < kPrologue; k++)
+      if ((unsigned long long)k < my_n) load(k);
+  }
+
+  for (unsigned long long k = 0; k < my_n; k++) {
+    const unsigned long long t = tile_of(k);
+    const int s = (int)(k % S);
+    const uint32_t nw_tile = tile_words(k);
+    uint4 *stage = ring + s * TILE;
+    if (OP == GSB_OP_FILL) {
+      if (leader) bulk_wait_read<S - 1>();  // the store that last read this stage has drained it
+      __syncwarp();
+    } else {
+      mbar_wait(smem_u32(&full_bar[warp][s]), (uint32_t)((k / S) & 1ull));
+    }
+    const uint32_t key_expect = (OP != GSB_OP_FILL) ? expect_key_of(a, a.first_word + t * TILE) : 0u;
+    if (nw_tile == TILE) {
+      uint4 v[WPL];
+      if (OP != GSB_OP_FILL) {
+#pragma unroll
+        for (int u = 0; u < WPL; u++) v[u] = stage[u * 32 + lane];
+      }
+#pragma unroll
+      for (int u = 0; u < WPL; u++) {
+        const uint4 nw = process_word<OP>(v[u], a.first_word + t * TILE + u * 32 + lane, key_expect, key_write, acc);
+        if (OP != GSB_OP_VERIFY) stage[u * 32 + lane] = nw;
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < WPL; u++) {
+        const uint32_t i = u * 32 + lane;
+        if (i < nw_tile) {
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (OP != GSB_OP_FILL) v = stage[i];
+          const uint4 nw = process_word<OP>(v, a.first_word + t * TILE + i, key_expect, key_write, acc);
+          if (OP != GSB_OP_VERIFY) stage[i] = nw;
+        }
+      }
+    }
+    if (OP != GSB_OP_VERIFY) fence_proxy_async_smem();
+    __syncwarp();  // the whole warp is done with this stage
+    if (leader) {
+      if (OP == GSB_OP_VERIFY) {
+        if (k + S < my_n) load(k + S);
+      } else {
+        bulk_s2g(win + t * TILE, smem_u32(stage), nw_tile * 16u);
+        bulk_commit();
+        if (OP == GSB_OP_VERIFY_REFILL && k + S - 1 < my_n) {
+          if (k >= 1) bulk_wait_read<1>();
+          load(k + S - 1);
+        }
+      }
+    }
+  }
+  if (leader && OP != GSB_OP_VERIFY) bulk_wait_all<0>();
+  finish(a, acc);
+}
+
 // ---------------------------------------------------------------- geometry + dispatch
 
 constexpr int kDirectU = 4;
@@ -478,17 +593,27 @@ constexpr uint32_t kCpSmem = kCpU * kThreads * 16 * kCpS;
 constexpr int kMaxCtasPerSm = 8;
 
 template <typename K>
-int resident_ctas(K kernel, uint32_t smem) {
+int resident_ctas(K kernel, uint32_t smem, int threads) {
   int n = 0;
-  if (smem > 48 * 1024) {
+  if (smem > 32 * 1024) {  // dynamic + the kernel's static shared memory may cross the 48 KiB default
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return -1;
   }
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, smem) != cudaSuccess) return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess) return -1;
   return n;
 }
 
 typedef void (*probe_fn)(const gsb_kernel_args);
+
+// experiment knob GSB_BULKW_CFG: warp-tile size x ring depth x warps per CTA of the per-warp TMA path
+int bulkw_cfg() {
+  static const int f = [] {
+    const char *e = getenv("GSB_BULKW_CFG");
+    const int v = e ? atoi(e) : 0;
+    return v < 0 || v > 7 ? 0 : v;
+  }();
+  return f;
+}
 
 // experiment knob GSB_BULK_CFG: tile size x ring depth of the TMA path (0 = shipped default)
 int bulk_cfg() {
@@ -509,8 +634,9 @@ int direct_flavor() {
   return f;
 }
 
-probe_fn pick(uint32_t op, uint32_t variant, uint32_t *smem) {
+probe_fn pick(uint32_t op, uint32_t variant, uint32_t *smem, uint32_t *threads) {
   *smem = 0;
+  *threads = kThreads;
   switch (variant) {
     case GSB_VARIANT_DIRECT:
       switch (direct_flavor()) {
@@ -552,6 +678,27 @@ probe_fn pick(uint32_t op, uint32_t variant, uint32_t *smem) {
 #undef GSB_BULK_CASE
       }
       return nullptr;
+    case GSB_VARIANT_BULKW:
+      switch (bulkw_cfg()) {
+#define GSB_BULKW_CASE(ID, WPL, S, WARPS)                                                    \
+  case ID:                                                                                   \
+    *smem = WPL * 512 * S * WARPS;                                                           \
+    *threads = WARPS * 32;                                                                   \
+    if (op == GSB_OP_FILL) return probe_bulk_warp<GSB_OP_FILL, WPL, S, WARPS>;               \
+    if (op == GSB_OP_VERIFY) return probe_bulk_warp<GSB_OP_VERIFY, WPL, S, WARPS>;           \
+    if (op == GSB_OP_VERIFY_REFILL) return probe_bulk_warp<GSB_OP_VERIFY_REFILL, WPL, S, WARPS>; \
+    return nullptr;
+        GSB_BULKW_CASE(0, 8, 3, 8)    //  4 KiB x 3 x 8 warps =  96 KiB/CTA (2 CTAs/SM, 16 warps/SM)
+        GSB_BULKW_CASE(1, 8, 6, 4)    //  4 KiB x 6 x 4 warps =  96 KiB     (2 CTAs/SM,  8 warps/SM)
+        GSB_BULKW_CASE(2, 16, 3, 4)   //  8 KiB x 3 x 4 warps =  96 KiB     (2 CTAs/SM,  8 warps/SM)
+        GSB_BULKW_CASE(3, 4, 6, 8)    //  2 KiB x 6 x 8 warps =  96 KiB     (2 CTAs/SM, 16 warps/SM)
+        GSB_BULKW_CASE(4, 8, 4, 4)    //  4 KiB x 4 x 4 warps =  64 KiB     (3 CTAs/SM, 12 warps/SM)
+        GSB_BULKW_CASE(5, 16, 3, 8)   //  8 KiB x 3 x 8 warps = 192 KiB     (1 CTA/SM,   8 warps/SM)
+        GSB_BULKW_CASE(6, 8, 3, 16)   //  4 KiB x 3 x 16 warps = 192 KiB    (1 CTA/SM,  16 warps/SM)
+        GSB_BULKW_CASE(7, 8, 2, 8)    //  4 KiB x 2 x 8 warps =  64 KiB     (3 CTAs/SM, 24 warps/SM)
+#undef GSB_BULKW_CASE
+      }
+      return nullptr;
     default:
       return nullptr;
   }
@@ -564,26 +711,26 @@ uint32_t gsb_kernel_max_grid(int sm_count) { return (uint32_t)(sm_count * kMaxCt
 int gsb_kernel_geometry(uint32_t op, uint32_t variant, uint32_t grid_request, int sm_count,
                         gsb_launch_geom *geom) {
   if (variant == GSB_VARIANT_AUTO) variant = GSB_VARIANT_BULK;
-  uint32_t smem = 0;
-  probe_fn fn = pick(op, variant, &smem);
+  uint32_t smem = 0, threads = 0;
+  probe_fn fn = pick(op, variant, &smem, &threads);
   if (!fn) return (int)cudaErrorInvalidValue;
-  int per_sm = resident_ctas(fn, smem);
+  int per_sm = resident_ctas(fn, smem, (int)threads);
   if (per_sm <= 0) return (int)cudaErrorInvalidDeviceFunction;
   if (per_sm > kMaxCtasPerSm) per_sm = kMaxCtasPerSm;
   uint32_t grid = (uint32_t)(per_sm * sm_count);  // one full wave of resident CTAs: persistent
   if (grid_request) grid = grid_request < gsb_kernel_max_grid(sm_count) ? grid_request : gsb_kernel_max_grid(sm_count);
   geom->variant = variant;
   geom->grid = grid;
-  geom->block = kThreads;
+  geom->block = threads;
   geom->smem_bytes = smem;
   return 0;
 }
 
 int gsb_kernel_launch(uint32_t op, const gsb_launch_geom *geom, const gsb_kernel_args *args,
                       cudaStream_t stream) {
-  uint32_t smem = 0;
-  probe_fn fn = pick(op, geom->variant, &smem);
+  uint32_t smem = 0, threads = 0;
+  probe_fn fn = pick(op, geom->variant, &smem, &threads);
   if (!fn) return (int)cudaErrorInvalidValue;
-  fn<<<geom->grid, geom->block, smem, stream>>>(*args);
+  fn<<<geom->grid, threads, smem, stream>>>(*args);
   return (int)cudaGetLastError();
 }

@@ -126,8 +126,9 @@ enum {
   GSB_VARIANT_AUTO = 0,
   GSB_VARIANT_DIRECT = 1,   /* ld.global.v4 -> registers -> st.global.v4 (control: no staging) */
   GSB_VARIANT_CPASYNC = 2,  /* cp.async 16 B -> shared ring -> ld.shared.v4 -> st.global.v4 */
-  GSB_VARIANT_BULK = 3      /* cp.async.bulk (TMA 1-D) -> shared ring -> ld.shared.v4 / st.shared.v4
-                               -> cp.async.bulk shared->global */
+  GSB_VARIANT_BULK = 3,     /* cp.async.bulk (TMA 1-D) -> shared ring -> ld.shared.v4 / st.shared.v4
+                               -> cp.async.bulk shared->global; one ring per CTA, CTA barrier per tile */
+  GSB_VARIANT_BULKW = 4     /* same data path, one private ring + mbarriers per WARP: no CTA barrier */
 };
 enum {
   GSB_PROBE_TIMED = 1u,       /* bracket the launch with CUDA events, fill kernel_ns */

@@ -1,0 +1,22 @@
+"""Small, short target for `ncu --set full` (ncu replays each launch ~40x and saves/restores device
+memory around every pass, which it cannot do for the 178 GiB arena): a 2 GiB arena, 1 GiB windows.
+usage: profile_target.py <variant 1..4> [n_launches]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gpushare_device_plugin_b200 import _abi, device  # noqa: E402
+
+variant = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 6
+device.init()
+device.arena_create(0, max_bytes=2 << 30)
+device.probe(0, _abi.GSB_OP_FILL, variant=1, seed_write=1)
+seed = 1
+for i in range(n):
+    r = device.probe(0, _abi.GSB_OP_VERIFY_REFILL, variant=variant, offset=(i % 2) << 30, nbytes=1 << 30,
+                     seed_expect=seed if i < 2 else seed - 1, seed_write=seed + 1 if i < 2 else seed)
+    if i % 2 == 1:
+        seed += 1
+print("done", r.kernel_ns)
+device.shutdown()

@@ -8,7 +8,7 @@ from gpushare_device_plugin_b200 import _abi, device
 GiB = 1 << 30
 variant, sizes = int(sys.argv[1]), [int(x) for x in sys.argv[2].split(",")]
 device.init()
-arena = device.arena_create(0, max_bytes=max(sizes) if max(sizes) else 0)
+arena = device.arena_create(0)
 rows = []
 for w in sizes:
     wb = w or arena
@@ -33,11 +33,19 @@ def run(env, variant, sizes):
     return json.loads(out.stdout.strip().splitlines()[-1])
 res = {}
 GiB = 1 << 30
-for f in range(4):
-    res[f"direct_flavor{f}"] = run({"GSB_DIRECT_FLAVOR": str(f)}, 1, [GiB, 16 * GiB])
-    print(f"direct_flavor{f}", json.dumps(res[f"direct_flavor{f}"]), flush=True)
-for c in range(6):
-    res[f"bulk_cfg{c}"] = run({"GSB_BULK_CFG": str(c)}, 3, [64 << 20, GiB, 0])
-    print(f"bulk_cfg{c}", json.dumps(res[f"bulk_cfg{c}"]), flush=True)
+def show(name, rows):
+    res[name] = rows
+    if isinstance(rows, dict):
+        print(name, rows, flush=True)
+        return
+    print(name, " | ".join(f"{r['bytes'] >> 20}MiB {r['op']} {r['median_us']:.0f}us {r['frac']:.3f}" for r in rows), flush=True)
+sizes = [64 << 20, GiB, 0]
+show("direct_flavor0", run({"GSB_DIRECT_FLAVOR": "0"}, 1, sizes))
+show("direct_flavor3", run({"GSB_DIRECT_FLAVOR": "3"}, 1, sizes))
+show("cpasync", run({}, 2, sizes))
+for c in (0, 1, 4, 5):
+    show(f"bulk_cfg{c}", run({"GSB_BULK_CFG": str(c)}, 3, sizes))
+for c in range(8):
+    show(f"bulkw_cfg{c}", run({"GSB_BULKW_CFG": str(c)}, 4, sizes))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/sweep2.json", "w"), indent=1)
