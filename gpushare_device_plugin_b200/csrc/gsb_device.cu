@@ -158,6 +158,7 @@ struct Global {
   std::deque<gsb_event> events;
   bool health_running = false;
   std::atomic<bool> health_stop{false};
+  uint64_t stop_gen = 0;  // bumped by every gsb_health_stop: wakes all gsb_health_wait callers
   std::vector<std::thread> health_threads;
   nvmlEventSet_t event_set{};
   bool have_event_set = false;
@@ -865,14 +866,14 @@ int gsb_health_inject(const gsb_event *ev) {
 int gsb_health_wait(uint32_t timeout_ms, gsb_event *ev) {
   if (!ev) return GSB_ERR_INVALID_ARGUMENT;
   std::unique_lock<std::mutex> lk(G.hmu);
-  if (!G.hcv.wait_for(lk, std::chrono::milliseconds(timeout_ms),
-                      [] { return !G.events.empty() || G.health_stop.load(); })) {
-    return GSB_ERR_TIMEOUT;
+  const uint64_t gen = G.stop_gen;
+  G.hcv.wait_for(lk, std::chrono::milliseconds(timeout_ms), [&] { return !G.events.empty() || G.stop_gen != gen; });
+  if (!G.events.empty()) {
+    *ev = G.events.front();
+    G.events.pop_front();
+    return GSB_OK;
   }
-  if (G.events.empty()) return GSB_ERR_STOPPED;
-  *ev = G.events.front();
-  G.events.pop_front();
-  return GSB_OK;
+  return G.stop_gen != gen ? GSB_ERR_STOPPED : GSB_ERR_TIMEOUT;
 }
 
 int gsb_health_start(uint32_t probe_period_ms, uint64_t window_bytes) {
@@ -945,6 +946,11 @@ int gsb_health_start(uint32_t probe_period_ms, uint64_t window_bytes) {
 }
 
 int gsb_health_stop(void) {
+  {  // wake every waiter, whether or not the internal threads are running
+    std::lock_guard<std::mutex> lk(G.hmu);
+    G.stop_gen++;
+  }
+  G.hcv.notify_all();
   std::vector<std::thread> ts;
   {
     std::lock_guard<std::mutex> lk(G.mu);
@@ -953,7 +959,6 @@ int gsb_health_stop(void) {
     ts.swap(G.health_threads);
     G.health_running = false;
   }
-  G.hcv.notify_all();
   for (auto &t : ts) t.join();
   if (G.have_event_set) {
     G.ml.eventSetFree(G.event_set);

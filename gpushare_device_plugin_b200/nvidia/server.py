@@ -155,6 +155,8 @@ class NvidiaDevicePlugin:
         if self.server is None:
             return
         self.stop.set()
+        if self.healthCheck:
+            device.health_stop()  # wakes watchXIDs out of its 5 s wait (the reference's ctx cancel)
         with self._cv:
             self._cv.notify_all()
         self.server.stop(0)

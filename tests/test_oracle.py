@@ -1,0 +1,110 @@
+"""Pins the oracle itself (CPU): the numpy and C restatements of the probe spec against the committed
+golden vectors and against each other; the C restatement of the reference's NVML path (linked with
+the reference's own nvml_dl.c) against a fake libnvidia-ml with 8 synthetic B200s and against the
+pure-Python restatement of getDevices + gogo marshal."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import probe_oracle as po
+from oracle import wire_oracle as wo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "probe_pattern.json")))
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "ref_inventory")
+FAKE = os.path.join(ROOT, "oracle", "_fake")
+
+
+def test_mix32_is_murmur3_finaliser():
+    got = po.mix32(np.array([0, 1, 0xFFFFFFFF], dtype=np.uint32))
+    assert [int(v) for v in got] == [GOLD["mix32"]["0"], GOLD["mix32"]["1"], GOLD["mix32"]["4294967295"]]
+    assert GOLD["mix32"]["1"] == 0x514E28B7 and GOLD["mix32"]["4294967295"] == 0x81F16F39  # published values
+
+
+@pytest.mark.parametrize("v", GOLD["words"], ids=lambda v: f"w{v['first_word']}-s{v['seed']}")
+def test_pattern_words_golden(v, c_oracle):
+    want = np.array(v["lanes"], dtype=np.uint32)
+    assert np.array_equal(po.pattern(v["first_word"], 4, v["seed"]), want)
+    out = np.empty((4, 4), dtype=np.uint32)
+    c_oracle.po_pattern(C.c_uint64(v["first_word"]), C.c_uint64(4), C.c_uint32(v["seed"]), out.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(out, want)
+
+
+@pytest.mark.parametrize("v", GOLD["windows"], ids=lambda v: f"w{v['first_word']}+{v['n_words']}")
+def test_window_checksums_golden(v, c_oracle):
+    p = po.pattern(v["first_word"], v["n_words"], v["seed"])
+    assert po.checksums(p) == (v["checksum_xor"], v["checksum_sum"])
+    res = (C.c_uint32 * 2)()
+    c_oracle.po_pattern_checksums(C.c_uint64(v["first_word"]), C.c_uint64(v["n_words"]), C.c_uint32(v["seed"]), res)
+    assert (res[0], res[1]) == (v["checksum_xor"], v["checksum_sum"])
+    # verify() on clean data reports exactly the checksums and no mismatch; a flipped bit is found
+    r = po.verify(p, v["first_word"], v["seed"])
+    assert (r["mismatch_words"], r["checksum_xor"]) == (0, v["checksum_xor"])
+    q = p.copy()
+    q[v["n_words"] // 2, 1] ^= np.uint32(1 << 7)
+    r = po.verify(q, v["first_word"], v["seed"])
+    assert (r["mismatch_words"], r["mismatch_bits"]) == (1, 1)
+    assert r["first_bad_offset"] == (v["first_word"] + v["n_words"] // 2) * 16
+    res4 = (C.c_uint64 * 4)()
+    c_oracle.po_verify.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]
+    first = c_oracle.po_verify(q.ctypes.data_as(C.c_void_p), v["first_word"], v["n_words"], v["seed"], res4)
+    assert (first, res4[2], res4[3]) == (v["first_word"] + v["n_words"] // 2, 1, 1)
+    assert (res4[0], res4[1]) == (r["checksum_xor"], r["checksum_sum"])
+
+
+def test_checksums_are_linear_over_disjoint_windows():
+    whole = po.checksums(po.pattern(1000, 5000, 3))
+    parts = [po.checksums(po.pattern(a, b - a, 3)) for a, b in ((1000, 1001), (1001, 3333), (3333, 6000))]
+    assert po.fold(parts) == whole
+    assert po.checksums(po.pattern(5, 0, 1)) == (0, 0)
+
+
+def test_seeds_never_collide_and_addresses_are_unique():
+    a, b = po.pattern(0, 4096, 1), po.pattern(0, 4096, 2)
+    assert (a != b).all()  # a word that kept an old generation always mismatches
+    assert len({tuple(r) for r in po.pattern((1 << 32) - 2048, 4096, 9)}) == 4096  # across the 2^32 word boundary
+
+
+def run_ref(args, env_extra):
+    env = dict(os.environ, LD_LIBRARY_PATH=FAKE, **env_extra)
+    out = subprocess.run([REF_BIN] + args, env=env, capture_output=True, text=True)
+    return out
+
+
+@pytest.mark.skipif(not os.access(REF_BIN, os.X_OK), reason="oracle/_ref not built (no /root/reference here)")
+class TestReferenceRestatement:
+    def test_without_nvml_it_reports_the_reference_error(self):
+        if os.path.exists("/usr/lib/x86_64-linux-gnu/libnvidia-ml.so.1"):
+            pytest.skip("real NVML present")
+        out = subprocess.run([REF_BIN, "inventory"], capture_output=True, text=True)
+        assert out.returncode == 12 and "could not load NVML library" in out.stderr  # bindings.go:60-66
+
+    @pytest.mark.parametrize("n", [1, 2, 8])
+    def test_inventory_matches_python_restatement(self, n, tmp_path):
+        lw = tmp_path / "lw.bin"
+        out = run_ref(["inventory", "--lw-out", str(lw)], {"FAKE_NVML_GPUS": str(n)})
+        assert out.returncode == 0, out.stderr
+        j = json.loads(out.stdout)
+        assert (j["n_gpus"], j["gpu_memory"], j["n_devices"]) == (n, 179, 179 * n)
+        devs, names, mem = wo.getDevices([{"uuid": d["uuid"], "path": d["path"], "memory_mib": d["memory_mib"]}
+                                          for d in j["devices"]])
+        assert mem == 179 and lw.read_bytes() == wo.marshal_ListAndWatchResponse(devs)
+        assert len(lw.read_bytes()) == {1: 10451, 2: 20902, 8: 83608}[n]
+        assert names == {d["uuid"]: d["minor"] for d in j["devices"]}
+        assert all(d["memory_mib"] == 183359 and d["total_bytes"] == 192265846784 for d in j["devices"])
+
+    def test_mib_unit(self):
+        out = run_ref(["inventory", "--unit", "MiB"], {"FAKE_NVML_GPUS": "1"})
+        j = json.loads(out.stdout)
+        assert j["gpu_memory"] == 183359 and j["n_devices"] == 183359
+
+    def test_health_setup_is_quadratic_like_the_reference(self):
+        out = run_ref(["bench", "--iters", "2"], {"FAKE_NVML_GPUS": "8"})
+        j = json.loads(out.stdout)
+        # per fake device: GetCount + (HandleByIndex + GetUUID) x (gpu index + 1) + RegisterEvents
+        want = sum(179 * (1 + 2 * (g + 1) + 1) for g in range(8))
+        assert j["register_calls_per_cycle"] == want == 15752

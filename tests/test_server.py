@@ -1,0 +1,243 @@
+"""The device-plugin gRPC surface end to end on CPU: real grpc over unix sockets, a fake kubelet
+(Registration server + device-manager client), a stateful mock apiserver; inventory injected
+(tests/fakes.py). Wire bytes are checked against the oracle's restatement of the reference."""
+import json
+import os
+import queue
+import re
+import threading
+import time
+
+import grpc
+import pytest
+
+from gpushare_device_plugin_b200 import device
+from gpushare_device_plugin_b200.kubelet.client import KubeletClientConfig, NewKubeletClient
+from gpushare_device_plugin_b200.nvidia import const, kubeclient, podmanager, server
+from gpushare_device_plugin_b200.testing.fake_kubelet import FakeKubelet
+from gpushare_device_plugin_b200.testing.mock_kube import MockKube, config4_pods, make_node, make_pod
+from oracle import wire_oracle as wo
+
+from . import fakes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KAT = json.load(open(os.path.join(ROOT, "tests", "golden", "wire_kat.json")))
+NODE = "b200-0"
+
+
+@pytest.fixture
+def world(tmp_path, monkeypatch):
+    fakes.install(monkeypatch)
+    monkeypatch.setattr(time, "sleep", lambda s: None)  # the retry back-offs of podmanager.go
+    kube = MockKube(make_node(NODE, labels={}), config4_pods(NODE))
+    podmanager.kubeInit(kubeclient.Clientset(kube.url), NODE)
+    kubelet = FakeKubelet(str(tmp_path))
+    made = []
+
+    def make(**kw):
+        p = server.NewNvidiaDevicePlugin(False, kw.pop("healthCheck", True), kw.pop("queryKubelet", False),
+                                         kw.pop("client", None), socket=str(tmp_path / "aliyungpushare.sock"), **kw)
+        made.append(p)
+        return p
+    yield type("W", (), {"kube": kube, "kubelet": kubelet, "make": staticmethod(make), "dir": tmp_path})
+    for p in made:
+        p.Stop()
+    kubelet.stop()
+    kube.close()
+
+
+def all_devs(unhealthy=()):
+    return [[wo.generateFakeDeviceID(u, j), wo.Unhealthy if (g, j) in unhealthy or g in unhealthy else wo.Healthy]
+            for g, u in enumerate(fakes.UUIDS) for j in range(179)]
+
+
+class Frames:
+    """One pump thread per stream: frames land in a queue (a timed-out next() must not be abandoned
+    mid-call, it would swallow the following frame)."""
+
+    def __init__(self, call):
+        self.q = queue.Queue()
+
+        def pump():
+            try:
+                for f in call:
+                    self.q.put(f)
+            except grpc.RpcError:
+                pass
+            self.q.put(None)
+        threading.Thread(target=pump, daemon=True).start()
+
+    def __iter__(self):
+        return self
+
+
+def next_frame(frames, timeout=5.0):
+    try:
+        return frames.q.get(timeout=timeout)
+    except queue.Empty:
+        return "timeout"
+
+
+def test_register_and_node_capacity(world):
+    p = world.make()
+    p.Serve(world.kubelet.socket)
+    req = world.kubelet.register_requests.get(timeout=5)
+    assert req.hex() == KAT["register_request_hex"]
+    node = world.kube.nodes[NODE]
+    assert node["status"]["capacity"]["aliyun.com/gpu-count"] == "8" == node["status"]["allocatable"]["aliyun.com/gpu-count"]
+    patches = [r for r in world.kube.requests if r[0] == "PATCH"]
+    assert patches[0][1] == f"/api/v1/nodes/{NODE}/status" and patches[0][3] == "application/strategic-merge-patch+json"
+    ch = world.kubelet.channel("aliyungpushare.sock")
+    assert world.kubelet.get_options(ch) == b"" and world.kubelet.pre_start(ch) == b""
+    ch.close()
+    # second plugin on the same node: capacity already right -> no PATCH (podmanager.go:80-85)
+    n_before = len([r for r in world.kube.requests if r[0] == "PATCH"])
+    p.Stop()
+    assert not os.path.exists(p.socket)  # stale socket removed (server.go:195-201)
+    world.make()
+    assert len([r for r in world.kube.requests if r[0] == "PATCH"]) == n_before
+
+
+@pytest.mark.parametrize("coalesce", [True, False], ids=["coalesced", "reference-stream"])
+def test_list_and_watch_stream(world, coalesce):
+    p = world.make(coalesce_health=coalesce)
+    p.Serve(world.kubelet.socket)
+    ch = world.kubelet.channel("aliyungpushare.sock")
+    it = Frames(world.kubelet.list_and_watch(ch))
+    first = next_frame(it)
+    assert first == wo.marshal_ListAndWatchResponse(all_devs()) and len(first) == 83608
+    # application-error XIDs leave the GPU healthy (nvidia.go:134)
+    device.health_inject(fakes.UUIDS[5], 8, 31)
+    assert next_frame(it, 0.7) == "timeout"
+    # a critical XID flips every fake device of that GPU
+    device.health_inject(fakes.UUIDS[5], 8, 79)
+    ids = [d[0] for d in all_devs()]
+    hits = wo.xid_event_effects(ids, 8, 79, fakes.UUIDS[5])
+    want = wo.list_and_watch_stream(all_devs(), hits)
+    if coalesce:
+        frames = [next_frame(it)]
+        while wo.unmarshal_ListAndWatchResponse(frames[-1]) != wo.unmarshal_ListAndWatchResponse(want[-1]):
+            frames.append(next_frame(it))  # events may straddle a wake-up; the end state is what counts
+        assert frames[-1] == want[-1] and len(frames) < 20
+    else:
+        got = [next_frame(it) for _ in range(179)]
+        assert got == want[1:]  # the reference's exact stream: one full list per fake device
+    # Unhealthy is sticky and an event without UUID takes every device down (nvidia.go:138-144)
+    device.health_inject("", 8, 48)
+    last = None
+    deadline = time.monotonic() + 10
+    while time.monotonic() < deadline:
+        f = next_frame(it, 2)
+        if f == "timeout":
+            break
+        last = f
+    assert all(h == wo.Unhealthy for _, h in wo.unmarshal_ListAndWatchResponse(last))
+    p.Stop()
+    assert next_frame(it, 5) is None  # the stream ends with the server (ListAndWatch returns nil on stop)
+    ch.close()
+
+
+def test_probe_events_mark_the_gpu_unhealthy(world):
+    p = world.make()
+    p.Serve(world.kubelet.socket)
+    ch = world.kubelet.channel("aliyungpushare.sock")
+    it = Frames(world.kubelet.list_and_watch(ch))
+    next_frame(it)
+    device.health_inject(fakes.UUIDS[2], 0x100, 1)  # GSB_EVENT_PROBE / mismatch
+    f = next_frame(it)
+    devs = wo.unmarshal_ListAndWatchResponse(f)
+    bad = {wo.extractRealDeviceID(i) for i, h in devs if h == wo.Unhealthy}
+    assert bad == {fakes.UUIDS[2]}
+    ch.close()
+
+
+def test_allocate_config4_end_to_end(world):
+    p = world.make()
+    p.Serve(world.kubelet.socket)
+    ch = world.kubelet.channel("aliyungpushare.sock")
+    minor_of = dict(zip(range(8), fakes.MINORS))
+    t0 = time.time_ns()
+    for i in range(64):
+        req = wo.marshal_AllocateRequest([[wo.generateFakeDeviceID(fakes.UUIDS[(i * 3) % 8], j) for j in range(4)]])
+        envs = wo.unmarshal_AllocateResponse(world.kubelet.allocate(ch, req))
+        idx = i // 8  # the pod's ALIYUN_COM_GPU_MEM_IDX annotation; must be a /dev/nvidia MINOR on this node
+        assert idx in minor_of.values()
+        assert envs == [{"NVIDIA_VISIBLE_DEVICES": str(idx), "ALIYUN_COM_GPU_MEM_IDX": str(idx),
+                         "ALIYUN_COM_GPU_MEM_POD": "4", "ALIYUN_COM_GPU_MEM_CONTAINER": "4",
+                         "ALIYUN_COM_GPU_MEM_DEV": "179"}]
+        ann = world.kube.pod(f"pod-{i:02d}")["metadata"]["annotations"]
+        assert ann["ALIYUN_COM_GPU_MEM_ASSIGNED"] == "true" and int(ann["ALIYUN_COM_GPU_MEM_ASSUME_TIME"]) >= t0
+    # every pod is assigned now: the 65th request gets the poison envs, gRPC status still OK
+    envs = wo.unmarshal_AllocateResponse(world.kubelet.allocate(ch, wo.marshal_AllocateRequest([["a", "b", "c", "d"]])))
+    assert envs == [KAT["err_response"]["envs"]]
+    pod_patches = [r for r in world.kube.requests if r[0] == "PATCH" and "/pods/" in r[1]]
+    assert len(pod_patches) == 64 and pod_patches[0][3] == "application/strategic-merge-patch+json"
+    assert re.fullmatch(rb'\{"metadata":\{"annotations":\{"ALIYUN_COM_GPU_MEM_ASSIGNED":"true",'
+                        rb'"ALIYUN_COM_GPU_MEM_ASSUME_TIME":"\d{19}"\}\}\}', pod_patches[0][2])
+    lists = [r for r in world.kube.requests if r[0] == "GET" and r[1].startswith("/api/v1/pods?")]
+    assert "spec.nodeName%3Db200-0%2Cstatus.phase%3DPending" in lists[0][1]
+    ch.close()
+
+
+def test_allocate_failure_paths_never_raise(world):
+    p = world.make()
+    p.Serve(world.kubelet.socket)
+    ch = world.kubelet.channel("aliyungpushare.sock")
+    req = wo.marshal_AllocateRequest([["a", "b", "c", "d"]])
+    err = [KAT["err_response"]["envs"]]
+
+    def n_patches():
+        return len([r for r in world.kube.requests if r[0] == "PATCH" and "/pods/" in r[1]])
+    # optimistic-lock conflict: exactly one retry, then success (allocate.go:138-144)
+    world.kube.fail_next_patch(const.OptimisticLockErrorMsg, 1)
+    before = n_patches()
+    envs = wo.unmarshal_AllocateResponse(world.kubelet.allocate(ch, req))
+    assert envs[0]["ALIYUN_COM_GPU_MEM_IDX"] == "0" and n_patches() == before + 2
+    # two conflicts in a row: error envs
+    world.kube.fail_next_patch(const.OptimisticLockErrorMsg, 2)
+    before = n_patches()
+    assert wo.unmarshal_AllocateResponse(world.kubelet.allocate(ch, req)) == err and n_patches() == before + 2
+    # any other PATCH error: no retry
+    world.kube.fail_next_patch("pods is forbidden", 1)
+    before = n_patches()
+    assert wo.unmarshal_AllocateResponse(world.kubelet.allocate(ch, req)) == err and n_patches() == before + 1
+    # LIST keeps failing (1 try + 3 retries): error envs (allocate.go:62-66)
+    world.kube.fail_lists = 4
+    assert wo.unmarshal_AllocateResponse(world.kubelet.allocate(ch, req)) == err
+    # LIST fails three times then works: the request is served
+    world.kube.fail_lists = 3
+    assert wo.unmarshal_AllocateResponse(world.kubelet.allocate(ch, req))[0]["ALIYUN_COM_GPU_MEM_IDX"] == "0"
+    ch.close()
+
+
+def test_query_kubelet_path_and_cgpu_label(world):
+    world.kube.nodes[NODE]["metadata"]["labels"]["cgpu.disable.isolation"] = "true"
+    kc = NewKubeletClient(KubeletClientConfig(Address="127.0.0.1", Port=world.kube.port, BearerToken="t", Scheme="http"))
+    p = world.make(queryKubelet=True, client=kc)
+    p.Serve(world.kubelet.socket)
+    ch = world.kubelet.channel("aliyungpushare.sock")
+    envs = wo.unmarshal_AllocateResponse(world.kubelet.allocate(ch, wo.marshal_AllocateRequest([["a", "b", "c", "d"]])))
+    assert envs[0]["CGPU_DISABLE"] == "true" and envs[0]["ALIYUN_COM_GPU_MEM_IDX"] == "0"
+    assert any(r[:2] == ("GET", "/pods/") for r in world.kube.requests)
+    ch.close()
+
+
+def test_single_gpu_shortcut_over_grpc(world, monkeypatch):
+    fakes.install(monkeypatch, n_gpus=1)
+    for k in list(world.kube.pods):
+        world.kube.pods[k]["status"]["phase"] = "Running"  # no pending candidates
+    p = world.make()
+    p.Serve(world.kubelet.socket)
+    ch = world.kubelet.channel("aliyungpushare.sock")
+    envs = wo.unmarshal_AllocateResponse(world.kubelet.allocate(ch, wo.marshal_AllocateRequest([["a", "b"]])))
+    assert envs == [{"NVIDIA_VISIBLE_DEVICES": fakes.UUIDS[0], "ALIYUN_COM_GPU_MEM_IDX": str(fakes.MINORS[0]),
+                     "ALIYUN_COM_GPU_MEM_POD": "2", "ALIYUN_COM_GPU_MEM_CONTAINER": "2", "ALIYUN_COM_GPU_MEM_DEV": "179"}]
+    ch.close()
+
+
+def test_register_fails_without_kubelet(world):
+    world.kubelet.stop()
+    p = world.make()
+    with pytest.raises(Exception):
+        p.Serve(world.kubelet.socket)
+    assert p.server is None and not os.path.exists(p.socket)  # Serve -> Stop on register failure (server.go:233-237)
