@@ -134,6 +134,25 @@ __device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src_smem, uint32_t 
                "r"(bytes)
                : "memory");
 }
+// same, carrying an L2 cache policy (createpolicy ... evict_first: streamed once, do not keep)
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar,
+                                              uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          dst_smem),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_hint(void *dst, uint32_t src_smem, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst),
+               "r"(src_smem), "r"(bytes), "l"(policy)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
@@ -406,6 +425,7 @@ __global__ void __launch_bounds__(kThreads) probe_bulk(const gsb_kernel_args a) 
   const uint32_t key_write = gsb_seed_key(a.seed_write);
   uint4 *__restrict__ win = a.base + a.first_word;
   const bool leader = threadIdx.x == 0;
+  const uint64_t policy = a.l2_hint ? l2_evict_first_policy() : 0ull;
   Acc acc;
 
   auto tile_words = [&](unsigned long long k) -> uint32_t {
@@ -418,7 +438,10 @@ __global__ void __launch_bounds__(kThreads) probe_bulk(const gsb_kernel_args a) 
     const int s = (int)(k % S);
     const uint32_t bytes = tile_words(k) * 16u;
     mbar_expect_tx(smem_u32(&full_bar[s]), bytes);
-    bulk_g2s(smem_u32(ring + s * TILE), win + t * TILE, bytes, smem_u32(&full_bar[s]));
+    if (a.l2_hint & 1u)
+      bulk_g2s_hint(smem_u32(ring + s * TILE), win + t * TILE, bytes, smem_u32(&full_bar[s]), policy);
+    else
+      bulk_g2s(smem_u32(ring + s * TILE), win + t * TILE, bytes, smem_u32(&full_bar[s]));
   };
 
   if (leader) {
@@ -465,7 +488,10 @@ __global__ void __launch_bounds__(kThreads) probe_bulk(const gsb_kernel_args a) 
       if (OP == GSB_OP_VERIFY) {
         if (k + S < my_n) load(k + S);  // same stage, just released by the barrier
       } else {
-        bulk_s2g(win + t * TILE, smem_u32(stage), nw_tile * 16u);
+        if (a.l2_hint & 2u)
+          bulk_s2g_hint(win + t * TILE, smem_u32(stage), nw_tile * 16u, policy);
+        else
+          bulk_s2g(win + t * TILE, smem_u32(stage), nw_tile * 16u);
         bulk_commit();
         if (OP == GSB_OP_VERIFY_REFILL && k + S - 1 < my_n) {
           // refill stage (k-1)%S: its store (tile k-1) must have finished READING shared memory;
@@ -504,6 +530,7 @@ __global__ void __launch_bounds__(WARPS * 32) probe_bulk_warp(const gsb_kernel_a
   const uint32_t key_write = gsb_seed_key(a.seed_write);
   uint4 *__restrict__ win = a.base + a.first_word;
   const bool leader = lane == 0;
+  const uint64_t policy = a.l2_hint ? l2_evict_first_policy() : 0ull;
   Acc acc;
 
   auto tile_words = [&](unsigned long long k) -> uint32_t {
@@ -514,7 +541,10 @@ __global__ void __launch_bounds__(WARPS * 32) probe_bulk_warp(const gsb_kernel_a
     const int s = (int)(k % S);
     const uint32_t bytes = tile_words(k) * 16u;
     mbar_expect_tx(smem_u32(&full_bar[warp][s]), bytes);
-    bulk_g2s(smem_u32(ring + s * TILE), win + tile_of(k) * TILE, bytes, smem_u32(&full_bar[warp][s]));
+    if (a.l2_hint & 1u)
+      bulk_g2s_hint(smem_u32(ring + s * TILE), win + tile_of(k) * TILE, bytes, smem_u32(&full_bar[warp][s]), policy);
+    else
+      bulk_g2s(smem_u32(ring + s * TILE), win + tile_of(k) * TILE, bytes, smem_u32(&full_bar[warp][s]));
   };
 
   if (leader) {
@@ -571,7 +601,10 @@ __global__ void __launch_bounds__(WARPS * 32) probe_bulk_warp(const gsb_kernel_a
       if (OP == GSB_OP_VERIFY) {
         if (k + S < my_n) load(k + S);
       } else {
-        bulk_s2g(win + t * TILE, smem_u32(stage), nw_tile * 16u);
+        if (a.l2_hint & 2u)
+          bulk_s2g_hint(win + t * TILE, smem_u32(stage), nw_tile * 16u, policy);
+        else
+          bulk_s2g(win + t * TILE, smem_u32(stage), nw_tile * 16u);
         bulk_commit();
         if (OP == GSB_OP_VERIFY_REFILL && k + S - 1 < my_n) {
           if (k >= 1) bulk_wait_read<1>();
@@ -615,12 +648,21 @@ int bulkw_cfg() {
   return f;
 }
 
-// experiment knob GSB_BULK_CFG: tile size x ring depth of the TMA path (0 = shipped default)
+// experiment knob GSB_BULK_CFG: tile size x ring depth of the TMA path (unset = per-op default)
 int bulk_cfg() {
   static const int f = [] {
     const char *e = getenv("GSB_BULK_CFG");
-    const int v = e ? atoi(e) : 0;
-    return v < 0 || v > 5 ? 0 : v;
+    const int v = e ? atoi(e) : -1;
+    return v < 0 || v > 5 ? -1 : v;
+  }();
+  return f;
+}
+
+// experiment knob GSB_L2_HINT: bit0 loads / bit1 stores of the TMA paths carry L2::evict_first
+uint32_t l2_hint_knob() {
+  static const uint32_t f = [] {
+    const char *e = getenv("GSB_L2_HINT");
+    return e ? (uint32_t)atoi(e) & 3u : 0u;
   }();
   return f;
 }
@@ -661,7 +703,9 @@ probe_fn pick(uint32_t op, uint32_t variant, uint32_t *smem, uint32_t *threads) 
       if (op == GSB_OP_VERIFY_REFILL) return probe_cpasync<GSB_OP_VERIFY_REFILL, kCpU, kCpS>;
       return nullptr;
     case GSB_VARIANT_BULK:
-      switch (bulk_cfg()) {
+      // shipped defaults (profiles/sweep_r01_knobs2.json): 32 KiB tiles; a pure-store FILL wants one fat
+      // CTA per SM with a deep ring, the loading ops want 2 CTAs/SM x 3 stages
+      switch (bulk_cfg() >= 0 ? bulk_cfg() : (op == GSB_OP_FILL ? 5 : 1)) {
 #define GSB_BULK_CASE(ID, U, S)                                                              \
   case ID:                                                                                   \
     *smem = U * kThreads * 16 * S;                                                           \
@@ -731,6 +775,8 @@ int gsb_kernel_launch(uint32_t op, const gsb_launch_geom *geom, const gsb_kernel
   uint32_t smem = 0, threads = 0;
   probe_fn fn = pick(op, geom->variant, &smem, &threads);
   if (!fn) return (int)cudaErrorInvalidValue;
-  fn<<<geom->grid, threads, smem, stream>>>(*args);
+  gsb_kernel_args a = *args;
+  a.l2_hint = l2_hint_knob();
+  fn<<<geom->grid, threads, smem, stream>>>(a);
   return (int)cudaGetLastError();
 }

@@ -39,13 +39,11 @@ def show(name, rows):
         print(name, rows, flush=True)
         return
     print(name, " | ".join(f"{r['bytes'] >> 20}MiB {r['op']} {r['median_us']:.0f}us {r['frac']:.3f}" for r in rows), flush=True)
-sizes = [64 << 20, GiB, 0]
-show("direct_flavor0", run({"GSB_DIRECT_FLAVOR": "0"}, 1, sizes))
-show("direct_flavor3", run({"GSB_DIRECT_FLAVOR": "3"}, 1, sizes))
-show("cpasync", run({}, 2, sizes))
-for c in (0, 1, 4, 5):
-    show(f"bulk_cfg{c}", run({"GSB_BULK_CFG": str(c)}, 3, sizes))
-for c in range(8):
-    show(f"bulkw_cfg{c}", run({"GSB_BULKW_CFG": str(c)}, 4, sizes))
+sizes = [GiB, 0]
+for h in range(4):
+    show(f"bulk_default_hint{h}", run({"GSB_L2_HINT": str(h)}, 3, sizes))
+for h in (0, 3):
+    show(f"bulkw_cfg7_hint{h}", run({"GSB_L2_HINT": str(h), "GSB_BULKW_CFG": "7"}, 4, sizes))
+    show(f"bulkw_cfg5_hint{h}", run({"GSB_L2_HINT": str(h), "GSB_BULKW_CFG": "5"}, 4, sizes))
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(res, open("gpurun_out/sweep2.json", "w"), indent=1)
+json.dump(res, open("gpurun_out/sweep4.json", "w"), indent=1)
