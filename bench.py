@@ -156,6 +156,77 @@ def cpu_model() -> str:
     return "unknown"
 
 
+UUIDS8 = ["GPU-%08x-4820-abfc-e83e-9431819757%02x" % (0xfef80890 + i, i) for i in range(8)]
+
+
+def bench_allocate(impl: str, quick: bool = False) -> dict:
+    """p50 Allocate() (BASELINE.json's second metric), SURVEY.md §8(d) configs 4-5, host-only: real grpc over
+    a unix socket, a stateful loopback mock apiserver that applies the PATCH, synthetic 8-GPU inventory
+    (the RPC never touches a GPU in either implementation). `ours` = nvidia/server.py over the C ABI
+    (gsb_allocate) with the pending-pod cache; `reference` = oracle/ref_plugin.py (global lock across I/O,
+    LIST per call, Python codec, synchronous log lines)."""
+    import logging
+    import shutil
+    import tempfile
+    logging.getLogger("gpushare").setLevel(logging.WARNING)
+    logging.getLogger("gpushare.nvidia").setLevel(logging.WARNING)
+    node = "b200-0"
+    out = {"impl": impl, "transport": "grpcio over unix socket (both arms)", "mock": "loopback Python apiserver (own process), clients in a third process",
+           "sweep": []}
+
+    def start(n_pods, mod):
+        tmp = tempfile.mkdtemp(prefix="gsb-alloc-")
+        kube = subprocess.Popen([sys.executable, "-m", "gpushare_device_plugin_b200.testing.mock_kube", "--node", node,
+                                 "--pods", str(n_pods)] + (["--mod"] if mod else []), stdin=subprocess.PIPE,
+                                stdout=subprocess.PIPE, text=True, cwd=ROOT)
+        url = f"http://127.0.0.1:{int(kube.stdout.readline())}"
+        sock = os.path.join(tmp, "aliyungpushare.sock")
+        minors = {u: i for i, u in enumerate(UUIDS8)}
+        if impl == "ours":
+            from gpushare_device_plugin_b200 import device
+            from gpushare_device_plugin_b200.nvidia import kubeclient, nvidia, podmanager, server
+            podmanager.kubeInit(kubeclient.Clientset(url), node)
+            nvidia.gpuMemory, nvidia.metric = 179, "GiB"
+            devs = [nvidia.Device(ID=device.fake_device_id(u, j)) for u in UUIDS8 for j in range(179)]
+            plugin = server.NewNvidiaDevicePlugin(False, False, False, None, socket=sock, inventory=(devs, minors),
+                                                  max_workers=64)
+            plugin.Start()
+            stop = plugin.Stop
+        else:
+            from oracle.ref_plugin import RefPlugin
+            plugin = RefPlugin(url, node, minors, 179, sock)
+            plugin.start()
+            stop = plugin.stop
+
+        def close():
+            stop()
+            kube.stdin.close()
+            kube.wait(timeout=10)
+            shutil.rmtree(tmp, ignore_errors=True)
+        return sock, close
+
+    def load(sock, c, total):  # clients in their own process too
+        o = subprocess.run([sys.executable, "-m", "gpushare_device_plugin_b200.testing.allocate_load", sock, str(c),
+                            str(total), ",".join(UUIDS8)], capture_output=True, text=True, cwd=ROOT, timeout=900)
+        if o.returncode:
+            raise RuntimeError(o.stderr[-400:])
+        return json.loads(o.stdout.strip().splitlines()[-1])
+
+    # config 4: 64 pending pods, 64 sequential Allocates
+    sock, close = start(64, False)
+    r = load(sock, 1, 64)
+    close()
+    out["config4"] = {k: r[k] for k in ("p50_us", "p99_us", "mean_us", "req_per_s", "error_responses")}
+    # config 5: 1024 pending pods, concurrency sweep (bounded: 256 requests per point)
+    for c in ((1, 16) if quick else (1, 4, 16, 64, 256)):
+        sock, close = start(1024, True)
+        r = load(sock, c, 64 if quick else 256)
+        close()
+        out["sweep"].append(r)
+    out["p50_us"] = out["config4"]["p50_us"]
+    return out
+
+
 def bench_reference(args) -> None:
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -180,6 +251,11 @@ def bench_reference(args) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_allocate:
+        try:
+            line["allocate"] = bench_allocate("reference", args.quick_allocate)
+        except Exception as e:  # noqa: BLE001
+            line["allocate"] = {"error": str(e)}
     print(json.dumps(line))
 
 
@@ -289,6 +365,11 @@ def bench_ours(args) -> None:
                           f"taskset -c 0; no HBM traffic"}
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"failed: {e}"}
+    if world == 1 and not args.no_allocate:
+        try:
+            line["allocate"] = bench_allocate("ours", args.quick_allocate)
+        except Exception as e:  # noqa: BLE001
+            line["allocate"] = {"error": str(e)}
     print(json.dumps(line))
     device.shutdown()
 
@@ -304,9 +385,15 @@ def main():
     ap.add_argument("--variant", default="auto", choices=["auto", "direct", "cpasync", "bulk", "bulkw"])
     ap.add_argument("--cpu-iters", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-allocate", action="store_true")
+    ap.add_argument("--quick-allocate", action="store_true")
+    ap.add_argument("--allocate-only", action="store_true", help="host-only: print just the Allocate() leg")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.allocate_only:
+        print(json.dumps(bench_allocate("reference" if args.impl == "reference" else "ours", args.quick_allocate)))
+        return
     if args.impl == "reference":
         bench_reference(args)
     else:

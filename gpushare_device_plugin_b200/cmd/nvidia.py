@@ -79,9 +79,11 @@ def main(argv=None) -> None:  # main.go:55-65
     log.info("Start gpushare device plugin")
     podmanager.kubeInit()  # the reference does this in package init() (allocate.go:20-22)
     kubeletClient = buildKubeletClient(a)
+    import os
     ngm = NewSharedGPUManager(a.mps, a.health_check, a.query_kubelet, translatememoryUnits(a.memory_unit),
-                              kubeletClient, probe_period_ms=a.probe_period_ms,
-                              window_bytes=a.probe_window_mib << 20)
+                              kubeletClient, pluginDir=os.environ.get("GPUSHARE_PLUGIN_DIR", const.DevicePluginPath),
+                              dumpDir=os.environ.get("GPUSHARE_DUMP_DIR", "/etc/kubernetes/"),
+                              probe_period_ms=a.probe_period_ms, window_bytes=a.probe_window_mib << 20)
     ngm.Run()
 
 

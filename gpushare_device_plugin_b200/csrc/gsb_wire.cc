@@ -15,6 +15,8 @@
 
 #include <algorithm>
 #include <string>
+#include <string_view>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/gpushare_b200.h"
@@ -335,25 +337,35 @@ int gsb_allocate(const gsb_allocate_ctx *ctx, const gsb_pod *pods, uint32_t n_po
 
   // getPendingPodsInNode's dedupe by UID (podmanager.go:162-212), then the candidate filter
   std::vector<uint32_t> cand;
-  for (uint32_t i = 0; i < n_pods; i++) {
-    if (!pods[i].on_node) continue;
-    bool dup = false;
-    for (uint32_t k = 0; k < i && !dup; k++)
-      dup = pods[k].on_node && pods[k].uid && pods[i].uid && strcmp(pods[k].uid, pods[i].uid) == 0;
-    if (dup) continue;
-    if (is_assumed(pods[i])) cand.push_back(i);
+  {
+    std::unordered_set<std::string_view> seen;
+    seen.reserve(n_pods * 2);
+    for (uint32_t i = 0; i < n_pods; i++) {
+      if (!pods[i].on_node) continue;
+      if (!seen.insert(std::string_view(pods[i].uid ? pods[i].uid : "")).second) continue;
+      if (is_assumed(pods[i])) cand.push_back(i);
+    }
   }
   // makePodOrderdByAge: sort.Sort with Less = (t[i] <= t[j])  (podmanager.go:241-262). Go 1.10's
   // sort.Sort on <= 12 elements is one ShellSort pass with gap 6 followed by insertionSort; with the
   // non-strict Less that is what decides the order of pods with EQUAL assume-times, so it is
   // restated exactly. Beyond 12 elements Go's pivot code (standard library, not in the reference
-  // tree) decides tie order; the insertion rule alone is used there (deviations).
+  // tree) decides tie order; the insertion rule alone is used there (deviations) — and an
+  // insertion sort with `<=` is the same permutation as sorting by (time ascending, arrival
+  // DEscending), which is what std::sort computes in O(n log n).
   auto less = [&](size_t i, size_t j) { return pods[cand[i]].assume_time <= pods[cand[j]].assume_time; };
-  if (cand.size() > 1 && cand.size() <= 12)
-    for (size_t i = 6; i < cand.size(); i++)
-      if (less(i, i - 6)) std::swap(cand[i], cand[i - 6]);
-  for (size_t i = 1; i < cand.size(); i++)
-    for (size_t j = i; j > 0 && less(j, j - 1); j--) std::swap(cand[j], cand[j - 1]);
+  if (cand.size() <= 12) {
+    if (cand.size() > 1)
+      for (size_t i = 6; i < cand.size(); i++)
+        if (less(i, i - 6)) std::swap(cand[i], cand[i - 6]);
+    for (size_t i = 1; i < cand.size(); i++)
+      for (size_t j = i; j > 0 && less(j, j - 1); j--) std::swap(cand[j], cand[j - 1]);
+  } else {
+    std::sort(cand.begin(), cand.end(), [&](uint32_t x, uint32_t y) {
+      if (pods[x].assume_time != pods[y].assume_time) return pods[x].assume_time < pods[y].assume_time;
+      return x > y;
+    });
+  }
 
   int32_t found = -1;
   for (uint32_t c : cand) {  // allocate.go:78-88

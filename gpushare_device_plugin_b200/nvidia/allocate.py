@@ -6,6 +6,7 @@ from __future__ import annotations
 
 import ctypes as C
 import logging
+import time
 from typing import List, Optional, Sequence
 
 from .. import _abi
@@ -59,48 +60,103 @@ def buildErrResponse(actx: AllocateContext, req: bytes) -> bytes:  # allocate.go
     return buf.raw[: n.value]
 
 
+class PendingPodCache:
+    """the reference LISTs (and JSON-decodes) every pending pod of the node on
+    every Allocate while holding the plugin lock. This keeps the last LIST and its gsb_pod table for
+    `ttl` seconds. It is optimistic, never authoritative: a request that finds no candidate in a
+    cached table re-LISTs and is decided again on fresh data, a failed PATCH drops the cache, and a pod
+    claimed by one request is hidden from the next (its PATCH runs outside the lock). ttl == 0
+    restores the reference's LIST-per-call exactly."""
+
+    def __init__(self, ttl: float):
+        self.ttl = ttl
+        self.pods: Optional[List[dict]] = None
+        self.table = None
+        self._keep = None
+        self.stamp = 0.0
+
+    def fresh(self) -> bool:
+        return self.pods is not None and self.ttl > 0 and (time.monotonic() - self.stamp) < self.ttl
+
+    def load(self, plugin):
+        self.pods = podmanager.getPendingPodsInNode(plugin.queryKubelet, plugin.kubeletClient)
+        self.table, self._keep = pod_table(self.pods, podmanager.nodeName)
+        self.stamp = time.monotonic()
+
+    def claim(self, i: int):
+        self.table[i].assigned_is_false = 0  # no longer a candidate (isGPUMemoryAssumedPod)
+
+    def unclaim(self, i: int):
+        if self.table is not None and i < len(self.table):
+            self.table[i].assigned_is_false = 1
+
+    def drop(self):
+        self.pods = self.table = self._keep = None
+
+
+def _decide(actx, cache, req: bytes):
+    buf = C.create_string_buffer(_RESP_CAP)
+    n, pod_index, pod_req = C.c_size_t(0), C.c_int32(-1), C.c_uint32(0)
+    kind = lib.gsb_allocate(C.byref(actx.ctx), cache.table, len(cache.pods), req, len(req), buf, _RESP_CAP,
+                            C.byref(n), C.byref(pod_index), C.byref(pod_req))
+    return kind, buf.raw[: n.value] if kind > 0 else b"", pod_index.value, pod_req.value
+
+
 def allocate(plugin, req: bytes) -> bytes:
     """NvidiaDevicePlugin.Allocate (allocate.go:42-198). Never raises: every failure is encoded in the
     response envs, exactly like the reference (gRPC status stays OK)."""
     log.info("----Allocating GPU for gpu mem is started----")
     actx: AllocateContext = plugin.allocate_ctx
-    with plugin.lock:  # allocate.go:59-60: one Allocate at a time
+    cache: PendingPodCache = plugin.pod_cache
+    with plugin.lock:  # allocate.go:59-60 — held for list + decide + claim only, not for the PATCH
         log.info("checking...")
         try:
-            pods = podmanager.getPendingPodsInNode(plugin.queryKubelet, plugin.kubeletClient)
+            was_cached = cache.fresh()
+            if not was_cached:
+                cache.load(plugin)
+            kind, resp, pidx, pod_req = _decide(actx, cache, req)
+            if kind == _abi.GSB_ALLOC_ERR_RESPONSE and was_cached:
+                cache.load(plugin)  # the cache may simply be older than the pod being started
+                kind, resp, pidx, pod_req = _decide(actx, cache, req)
         except Exception as e:  # noqa: BLE001  allocate.go:62-66
+            cache.drop()
             log.info("invalid allocation requst: Failed to find candidate pods due to %s", e)
             return buildErrResponse(actx, req)
-        table, _keep = pod_table(pods, podmanager.nodeName)
-        buf = C.create_string_buffer(_RESP_CAP)
-        n, pod_index, pod_req = C.c_size_t(0), C.c_int32(-1), C.c_uint32(0)
-        kind = lib.gsb_allocate(C.byref(actx.ctx), table, len(pods), req, len(req), buf, _RESP_CAP, C.byref(n),
-                                C.byref(pod_index), C.byref(pod_req))
         if kind < 0:
             log.warning("Allocate: %s", _abi.last_error() or lib.gsb_strerror(kind).decode())
             return b""  # undecodable request: nothing to answer for
-        log.info("RequestPodGPUs: %d", pod_req.value)
+        log.info("RequestPodGPUs: %d", pod_req)
+        pod = None
         if kind == _abi.GSB_ALLOC_MATCHED:
-            pod = pods[pod_index.value]
-            md = pod["metadata"]
-            log.info("Found Assumed GPU shared Pod %s in ns %s with GPU Memory %d", md.get("name"),
-                     md.get("namespace"), pod_req.value)
-            body = patchPodAnnotationSpecAssigned()  # allocate.go:131
-            try:
-                podmanager.clientset.patch_pod(md.get("namespace"), md.get("name"), body)
-            except Exception as e:  # noqa: BLE001
-                if str(e) == const.OptimisticLockErrorMsg:  # allocate.go:138-144: one retry
-                    try:
-                        podmanager.clientset.patch_pod(md.get("namespace"), md.get("name"), body)
-                    except Exception as e2:  # noqa: BLE001
-                        log.warning("Failed due to %s", e2)
-                        return buildErrResponse(actx, req)
-                else:
-                    log.warning("Failed due to %s", e)
-                    return buildErrResponse(actx, req)
-            log.info("----Allocating GPU for gpu mem for %s is ended----", md.get("name"))
-        elif kind == _abi.GSB_ALLOC_SINGLE_GPU:
-            log.info("this node has only one gpu device,skip to search pod and directly specify the device")
-        else:
-            log.warning("invalid allocation requst: request GPU memory %d can't be satisfied.", pod_req.value)
-        return buf.raw[: n.value]
+            pod = cache.pods[pidx]
+            cache.claim(pidx)
+            pods_ref = cache.pods
+    if kind == _abi.GSB_ALLOC_MATCHED:
+        md = pod["metadata"]
+        log.info("Found Assumed GPU shared Pod %s in ns %s with GPU Memory %d", md.get("name"), md.get("namespace"),
+                 pod_req)
+        body = patchPodAnnotationSpecAssigned()  # allocate.go:131
+        err = None
+        try:
+            podmanager.clientset.patch_pod(md.get("namespace"), md.get("name"), body)
+        except Exception as e:  # noqa: BLE001
+            err = e
+            if str(e) == const.OptimisticLockErrorMsg:  # allocate.go:138-144: one retry
+                try:
+                    podmanager.clientset.patch_pod(md.get("namespace"), md.get("name"), body)
+                    err = None
+                except Exception as e2:  # noqa: BLE001
+                    err = e2
+        if err is not None:
+            log.warning("Failed due to %s", err)
+            with plugin.lock:
+                if cache.pods is pods_ref:
+                    cache.unclaim(pidx)  # still unassigned on the apiserver
+                cache.drop()
+            return buildErrResponse(actx, req)
+        log.info("----Allocating GPU for gpu mem for %s is ended----", md.get("name"))
+    elif kind == _abi.GSB_ALLOC_SINGLE_GPU:
+        log.info("this node has only one gpu device,skip to search pod and directly specify the device")
+    else:
+        log.warning("invalid allocation requst: request GPU memory %d can't be satisfied.", pod_req)
+    return resp

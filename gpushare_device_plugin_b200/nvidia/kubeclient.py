@@ -6,6 +6,7 @@ from __future__ import annotations
 import http.client
 import json
 import os
+import socket
 import ssl
 import threading
 import urllib.parse
@@ -48,6 +49,10 @@ class Clientset:
                 c = http.client.HTTPSConnection(self.host, self.port, timeout=self.timeout, context=self.ctx)
             else:
                 c = http.client.HTTPConnection(self.host, self.port, timeout=self.timeout)
+            c.connect()
+            # Go's net/http (client-go) disables Nagle; without this a PATCH (headers + body = two
+            # small writes) stalls ~40 ms on the peer's delayed ACK
+            c.sock.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
             self._tl.conn = c
         return c
 

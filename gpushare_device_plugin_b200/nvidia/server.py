@@ -33,8 +33,9 @@ class NvidiaDevicePlugin:
 
     def __init__(self, mps: bool, healthCheck: bool, queryKubelet: bool, client, socket: str = const.serverSock,
                  coalesce_health: bool = True, probe_period_ms: int = 1000, window_bytes: int = device.GiB,
-                 max_workers: int = 16):
-        self.devs, self.devNameMap = nvidia.getDevices()  # server.go:39
+                 max_workers: int = 16, pod_cache_ttl: float = 1.0, inventory=None):
+        # `inventory` = (devs, devNameMap) injects a synthetic node (tests, Allocate benchmark)
+        self.devs, self.devNameMap = inventory if inventory is not None else nvidia.getDevices()  # server.go:39
         devList = list(self.devNameMap)
         log.info("Device Map: %s", self.devNameMap)
         log.info("Device List: %s", devList)
@@ -60,6 +61,7 @@ class NvidiaDevicePlugin:
         self._pending: List[int] = []
         self.allocate_ctx = _allocate.AllocateContext(self.devNameMap, self._slices,
                                                       nvidia.metric == const.GiBPrefix, self.disableCGPUIsolation)
+        self.pod_cache = _allocate.PendingPodCache(pod_cache_ttl)
         self._health_thread: Optional[threading.Thread] = None
 
     # ---- helpers -------------------------------------------------------------------------

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import copy
 import json
+import socket
 import threading
 import urllib.parse
 from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
@@ -71,13 +72,15 @@ class MockKube:
             def log_message(self, *a):
                 pass
 
+            def setup(self):
+                super().setup()
+                self.request.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+
             def _send(self, code: int, obj):
                 body = json.dumps(obj, separators=(",", ":")).encode()
-                self.send_response(code)
-                self.send_header("Content-Type", "application/json")
-                self.send_header("Content-Length", str(len(body)))
-                self.end_headers()
-                self.wfile.write(body)
+                head = (f"HTTP/1.1 {code} X\r\nContent-Type: application/json\r\nContent-Length: {len(body)}\r\n"
+                        "\r\n").encode()
+                self.wfile.write(head + body)  # one write: headers and body in the same segment
 
             def _status(self, code: int, message: str):
                 self._send(code, {"kind": "Status", "apiVersion": "v1", "status": "Failure", "message": message,
@@ -139,7 +142,10 @@ class MockKube:
                         return self._send(200, p)
                 self._status(404, "not found")
 
-        self.httpd = ThreadingHTTPServer(("127.0.0.1", 0), H)
+        class Server(ThreadingHTTPServer):
+            request_queue_size = 1024  # default 5: a burst of new client connections would hit SYN retransmits (1 s)
+
+        self.httpd = Server(("127.0.0.1", 0), H)
         self.httpd.daemon_threads = True
         self.port = self.httpd.server_address[1]
         self.url = f"http://127.0.0.1:{self.port}"
@@ -157,3 +163,24 @@ class MockKube:
     def close(self):
         self.httpd.shutdown()
         self.httpd.server_close()
+
+
+def main(argv=None):
+    """Stand-alone mock (its own process, so it does not share a GIL with the plugin under test):
+    python -m gpushare_device_plugin_b200.testing.mock_kube --node b200-0 --pods 1024 [--mod]
+    prints the port on stdout, serves until stdin closes."""
+    import argparse
+    import sys
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--node", default="b200-0")
+    ap.add_argument("--pods", type=int, default=64)
+    ap.add_argument("--mod", action="store_true")
+    a = ap.parse_args(argv)
+    m = MockKube(make_node(a.node, gpu_count=8), config4_pods(a.node, a.pods, mod=a.mod))
+    print(m.port, flush=True)
+    sys.stdin.read()
+    m.close()
+
+
+if __name__ == "__main__":
+    main()

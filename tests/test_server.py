@@ -241,3 +241,65 @@ def test_register_fails_without_kubelet(world):
     with pytest.raises(Exception):
         p.Serve(world.kubelet.socket)
     assert p.server is None and not os.path.exists(p.socket)  # Serve -> Stop on register failure (server.go:233-237)
+
+
+# ---- §8(f) row 2: pending-pod cache + narrowed lock -------------------------------------------------
+
+def _lists(world):
+    return len([r for r in world.kube.requests if r[0] == "GET" and r[1].startswith("/api/v1/pods?")])
+
+
+def test_ttl_zero_lists_on_every_call_like_the_reference(world):
+    p = world.make(pod_cache_ttl=0)
+    p.Serve(world.kubelet.socket)
+    ch = world.kubelet.channel("aliyungpushare.sock")
+    req = wo.marshal_AllocateRequest([["a", "b", "c", "d"]])
+    for i in range(10):
+        assert wo.unmarshal_AllocateResponse(world.kubelet.allocate(ch, req))[0]["ALIYUN_COM_GPU_MEM_IDX"] == str(i // 8)
+    assert _lists(world) == 10
+    ch.close()
+
+
+def test_cache_skips_the_list_but_refreshes_on_a_miss(world):
+    p = world.make(pod_cache_ttl=60)
+    p.Serve(world.kubelet.socket)
+    ch = world.kubelet.channel("aliyungpushare.sock")
+    req = wo.marshal_AllocateRequest([["a", "b", "c", "d"]])
+    for i in range(64):
+        assert wo.unmarshal_AllocateResponse(world.kubelet.allocate(ch, req))[0]["ALIYUN_COM_GPU_MEM_IDX"] == str(i // 8)
+    assert _lists(world) == 1  # one LIST served 64 requests
+    # a pod the scheduler bound AFTER the cache was filled: first look misses, the refresh finds it
+    new = make_pod(99, NODE, gpu_mem=2, idx=5, assume_time=1_800_000_000_000_000_000)
+    with world.kube.lock:
+        world.kube.pods[("default", "pod-99")] = new
+        world.kube.order.append(("default", "pod-99"))
+    envs = wo.unmarshal_AllocateResponse(world.kubelet.allocate(ch, wo.marshal_AllocateRequest([["a", "b"]])))
+    assert envs[0]["ALIYUN_COM_GPU_MEM_IDX"] == "5" and _lists(world) == 2
+    assert world.kube.pod("pod-99")["metadata"]["annotations"]["ALIYUN_COM_GPU_MEM_ASSIGNED"] == "true"
+    # nothing left: the miss costs one more LIST, the answer is the reference's poison envs
+    envs = wo.unmarshal_AllocateResponse(world.kubelet.allocate(ch, req))
+    assert envs == [KAT["err_response"]["envs"]] and _lists(world) == 3
+    ch.close()
+
+
+def test_concurrent_allocates_never_share_a_pod(world):
+    p = world.make(pod_cache_ttl=60, max_workers=32)
+    p.Serve(world.kubelet.socket)
+    results, errors = [], []
+
+    def client():
+        try:
+            ch = world.kubelet.channel("aliyungpushare.sock")
+            for _ in range(4):
+                results.append(wo.unmarshal_AllocateResponse(
+                    world.kubelet.allocate(ch, wo.marshal_AllocateRequest([["a", "b", "c", "d"]])))[0])
+            ch.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+    ts = [threading.Thread(target=client) for _ in range(16)]
+    [t.start() for t in ts]
+    [t.join(60) for t in ts]
+    assert not errors and len(results) == 64
+    assert sorted(int(r["ALIYUN_COM_GPU_MEM_IDX"]) for r in results) == sorted(i // 8 for i in range(64))
+    patched = [r[1] for r in world.kube.requests if r[0] == "PATCH" and "/pods/" in r[1]]
+    assert len(patched) == 64 and len(set(patched)) == 64  # every pod claimed exactly once
