@@ -46,7 +46,7 @@ SYMBOLS = [
     "gsb_device_count", "gsb_device_info_get", "gsb_slices", "gsb_fake_device_id", "gsb_real_device_id",
     "gsb_encode_list_and_watch", "gsb_encode_register_request",
     "gsb_arena_create", "gsb_arena_destroy", "gsb_arena_bytes", "gsb_probe", "gsb_probe_all",
-    "gsb_arena_read", "gsb_arena_write", "gsb_cycle",
+    "gsb_arena_read", "gsb_arena_write", "gsb_cycle", "gsb_cycle_all",
     "gsb_health_start", "gsb_health_stop", "gsb_health_wait", "gsb_health_inject", "gsb_xid_is_benign",
     "gsb_allocate", "gsb_allocate_err_response", "gsb_patch_assigned_body",
 ]
@@ -179,6 +179,7 @@ def _load() -> C.CDLL:
         "gsb_arena_read": (C.c_int, [C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64]),
         "gsb_arena_write": (C.c_int, [C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64]),
         "gsb_cycle": (C.c_int, [C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(CycleResult)]),
+        "gsb_cycle_all": (C.c_int64, [C.c_uint32, u32p, C.c_uint64, C.c_uint64, C.c_int, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(CycleResult)]),
         "gsb_health_start": (C.c_int, [C.c_uint32, C.c_uint64]),
         "gsb_health_stop": (C.c_int, []),
         "gsb_health_wait": (C.c_int, [C.c_uint32, C.POINTER(Event)]),

@@ -49,6 +49,8 @@ def parse(argv):
     # additions (not in the reference): active HBM probe cadence of the health watch
     add("probe-period-ms", default=1000, type=int)
     add("probe-window-mib", default=1024, type=int)
+    add("probe-arena-mib", default=4096, type=int)
+    add("startup-full-walk", default=False, **b)
     return p.parse_args(argv)
 
 
@@ -83,7 +85,8 @@ def main(argv=None) -> None:  # main.go:55-65
     ngm = NewSharedGPUManager(a.mps, a.health_check, a.query_kubelet, translatememoryUnits(a.memory_unit),
                               kubeletClient, pluginDir=os.environ.get("GPUSHARE_PLUGIN_DIR", const.DevicePluginPath),
                               dumpDir=os.environ.get("GPUSHARE_DUMP_DIR", "/etc/kubernetes/"),
-                              probe_period_ms=a.probe_period_ms, window_bytes=a.probe_window_mib << 20)
+                              probe_period_ms=a.probe_period_ms, window_bytes=a.probe_window_mib << 20,
+                              probe_arena_bytes=a.probe_arena_mib << 20, startup_full_walk=a.startup_full_walk)
     ngm.Run()
 
 

@@ -33,6 +33,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -143,6 +144,13 @@ struct Device {
   std::vector<uint32_t> gen;  // host mirror of seed_table: generation that last wrote each granule
   uint32_t next_gen = 1;
   bool faulted = false;  // prober: sticky
+
+  // persistent worker (gsb_cycle_all / gsb_probe_all): one host thread per device
+  std::thread worker;
+  std::mutex wmu;
+  std::condition_variable wcv;
+  std::function<void()> job;
+  bool job_ready = false, job_done = false, worker_quit = false;
 };
 
 struct Global {
@@ -575,6 +583,45 @@ int query_info(Device *d, gsb_device_info *out) {
   return GSB_OK;
 }
 
+// run `fn` on the device's own persistent thread (created on first use)
+void worker_submit(Device *d, std::function<void()> fn) {
+  std::unique_lock<std::mutex> lk(d->wmu);
+  if (!d->worker.joinable()) {
+    d->worker = std::thread([d] {
+      std::unique_lock<std::mutex> wl(d->wmu);
+      for (;;) {
+        d->wcv.wait(wl, [d] { return d->job_ready || d->worker_quit; });
+        if (d->worker_quit) return;
+        d->job_ready = false;
+        std::function<void()> f = std::move(d->job);
+        wl.unlock();
+        f();
+        wl.lock();
+        d->job_done = true;
+        d->wcv.notify_all();
+      }
+    });
+  }
+  d->job = std::move(fn);
+  d->job_done = false;
+  d->job_ready = true;
+  d->wcv.notify_all();
+}
+
+void worker_wait(Device *d) {
+  std::unique_lock<std::mutex> lk(d->wmu);
+  d->wcv.wait(lk, [d] { return d->job_done; });
+}
+
+void worker_stop(Device *d) {
+  {
+    std::lock_guard<std::mutex> lk(d->wmu);
+    d->worker_quit = true;
+  }
+  d->wcv.notify_all();
+  if (d->worker.joinable()) d->worker.join();
+}
+
 void push_event(const gsb_event &ev) {
   {
     std::lock_guard<std::mutex> lk(G.hmu);
@@ -681,6 +728,7 @@ int gsb_shutdown(void) {
   std::lock_guard<std::mutex> lk(G.mu);
   if (!G.inited) return GSB_OK;
   for (auto &d : G.devs) {
+    worker_stop(d.get());
     std::lock_guard<std::mutex> dl(d->mu);
     arena_destroy_locked(d.get());
     if (d->ready) {
@@ -760,14 +808,66 @@ int gsb_probe(uint32_t idx, const gsb_probe_cfg *cfg, gsb_probe_result *out) {
 
 int gsb_probe_all(uint32_t n, const uint32_t *idxs, const gsb_probe_cfg *cfg, gsb_probe_result *results) {
   if (!idxs || !cfg || !results) return GSB_ERR_INVALID_ARGUMENT;
-  std::vector<std::thread> ts;
-  ts.reserve(n);
-  for (uint32_t i = 0; i < n; i++) ts.emplace_back([=] { gsb_probe(idxs[i], cfg, &results[i]); });
-  for (auto &t : ts) t.join();
+  std::vector<Device *> ds(n, nullptr);
+  for (uint32_t i = 0; i < n; i++) {
+    ds[i] = device_at(idxs[i]);
+    if (!ds[i]) {
+      memset(&results[i], 0, sizeof results[i]);
+      results[i].status = G.inited ? GSB_ERR_NO_DEVICE : GSB_ERR_NOT_INITIALIZED;
+      continue;
+    }
+    const uint32_t idx = idxs[i];
+    gsb_probe_result *out = &results[i];
+    worker_submit(ds[i], [idx, cfg, out] { gsb_probe(idx, cfg, out); });
+  }
   int rc = GSB_OK;
-  for (uint32_t i = 0; i < n; i++)
+  for (uint32_t i = 0; i < n; i++) {
+    if (ds[i]) worker_wait(ds[i]);
     if (results[i].status != GSB_OK) rc = results[i].status;
+  }
   return rc;
+}
+
+int64_t gsb_cycle_all(uint32_t n, const uint32_t *idxs, uint64_t cycle_no, uint64_t window_bytes, int unit_gib,
+                      uint32_t variant, uint8_t *lw_buf, size_t lw_cap, gsb_cycle_result *results) {
+  if (!idxs || !results || n == 0 || n > GSB_MAX_DEVICES) return GSB_ERR_INVALID_ARGUMENT;
+  std::vector<Device *> ds(n, nullptr);
+  std::vector<int> rcs(n, GSB_OK);
+  std::vector<std::vector<uint8_t>> scratch(n);
+  for (uint32_t i = 0; i < n; i++) {
+    ds[i] = device_at(idxs[i]);
+    if (!ds[i]) return G.inited ? GSB_ERR_NO_DEVICE : GSB_ERR_NOT_INITIALIZED;
+  }
+  for (uint32_t i = 0; i < n; i++) {  // fan out: every device runs its own cycle on its own thread
+    scratch[i].resize(1 << 16);
+    const uint32_t idx = idxs[i];
+    gsb_cycle_result *out = &results[i];
+    int *rc = &rcs[i];
+    std::vector<uint8_t> *buf = &scratch[i];
+    worker_submit(ds[i], [=] {
+      *rc = gsb_cycle(idx, cycle_no, window_bytes, unit_gib, variant, buf->data(), buf->size(), out);
+    });
+  }
+  for (uint32_t i = 0; i < n; i++) worker_wait(ds[i]);
+  // the one join: concatenate in index order, slices from the first device, health from each verdict
+  const uint32_t slices = results[0].slices;
+  std::vector<const char *> uuids(n);
+  std::vector<uint8_t> bits(((size_t)n * slices + 7) / 8, 0);
+  bool any_bad = false;
+  int rc_all = GSB_OK;
+  for (uint32_t i = 0; i < n; i++) {
+    if (rcs[i] < 0 && rcs[i] != GSB_ERR_DRIVER) rc_all = rcs[i];  // a failed launch is a verdict, not an API error
+    uuids[i] = results[i].info.uuid;
+    if (!results[i].healthy) {
+      any_bad = true;
+      for (uint32_t j = 0; j < slices; j++) {
+        const size_t b = (size_t)i * slices + j;
+        bits[b >> 3] |= (uint8_t)(1u << (b & 7));
+      }
+    }
+  }
+  if (rc_all) return rc_all;
+  return gsb_encode_list_and_watch(uuids.data(), n, slices, any_bad ? bits.data() : nullptr, lw_buf, lw_cap);
 }
 
 int gsb_arena_read(uint32_t idx, uint64_t offset, void *dst, uint64_t bytes) {

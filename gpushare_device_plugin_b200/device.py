@@ -158,6 +158,30 @@ class Cycler:
         return self.buf.raw[: self.res.lw_len]
 
 
+class NodeCycler:
+    """gsb_cycle_all: every listed device's cycle concurrently (one persistent native thread per device)
+    and the concatenated ListAndWatchResponse of the node."""
+
+    def __init__(self, idxs: Sequence[int], window_bytes: int = GiB, unit_gib: bool = True,
+                 variant: int = _abi.GSB_VARIANT_AUTO, lw_cap: int = 1 << 20):
+        self.idxs = (C.c_uint32 * len(idxs))(*idxs)
+        self.n, self.window_bytes, self.unit_gib, self.variant = len(idxs), window_bytes, unit_gib, variant
+        self.buf = C.create_string_buffer(lw_cap)
+        self.res = (CycleResult * len(idxs))()
+        self.cycle_no, self.lw_len = 0, 0
+
+    def step(self):
+        n = lib.gsb_cycle_all(self.n, self.idxs, self.cycle_no, self.window_bytes, 1 if self.unit_gib else 0,
+                              self.variant, self.buf, len(self.buf), self.res)
+        check(int(n), "gsb_cycle_all")
+        self.lw_len = int(n)
+        self.cycle_no += 1
+        return self.res
+
+    def list_and_watch_bytes(self) -> bytes:
+        return self.buf.raw[: self.lw_len]
+
+
 def health_start(probe_period_ms: int = 0, window_bytes: int = GiB) -> None:
     check(lib.gsb_health_start(probe_period_ms, window_bytes), "gsb_health_start")
 

@@ -33,7 +33,8 @@ class NvidiaDevicePlugin:
 
     def __init__(self, mps: bool, healthCheck: bool, queryKubelet: bool, client, socket: str = const.serverSock,
                  coalesce_health: bool = True, probe_period_ms: int = 1000, window_bytes: int = device.GiB,
-                 max_workers: int = 16, pod_cache_ttl: float = 1.0, inventory=None):
+                 max_workers: int = 16, pod_cache_ttl: float = 1.0, inventory=None,
+                 probe_arena_bytes: int = 4 * device.GiB, startup_full_walk: bool = False):
         # `inventory` = (devs, devNameMap) injects a synthetic node (tests, Allocate benchmark)
         self.devs, self.devNameMap = inventory if inventory is not None else nvidia.getDevices()  # server.go:39
         devList = list(self.devNameMap)
@@ -47,6 +48,7 @@ class NvidiaDevicePlugin:
         self.mps, self.healthCheck, self.queryKubelet, self.kubeletClient = mps, healthCheck, queryKubelet, client
         self.coalesce_health = coalesce_health
         self.probe_period_ms, self.window_bytes = probe_period_ms, window_bytes
+        self.probe_arena_bytes, self.startup_full_walk = probe_arena_bytes, startup_full_walk
         self.max_workers = max_workers
         self.stop = threading.Event()
         self.lock = threading.RLock()  # sync.RWMutex of server.go:34; Allocate takes it exclusively
@@ -119,8 +121,31 @@ class NvidiaDevicePlugin:
             self._pending.append(self._index[dev.ID])
             self._cv.notify_all()
 
+    def setup_probe_arenas(self) -> None:
+        """The memory the active probe walks. Optionally one whole-device walk at start-up (everything the
+        driver hands out: allocate -> write -> verify -> release, ~0.4 s on an idle B200), then a small
+        steady-state arena per GPU whose 1 GiB windows the prober rotates through. A GPU whose memory is
+        fully taken by tenants simply has no arena: the XID half still watches it."""
+        from .._abi import GSB_OP_VERIFY, GsbError
+        for i, uuid in enumerate(self._uuids):
+            try:
+                if self.startup_full_walk:
+                    nbytes = device.arena_create(i)  # FILL of every mapped byte happens inside
+                    r = device.probe(i, GSB_OP_VERIFY, flags=3)  # timed + generation table
+                    log.info("start-up walk of %s: %d bytes allocatable, %d mismatching words, %.1f ms", uuid, nbytes,
+                             r.mismatch_words, r.kernel_ns / 1e6)
+                    if r.mismatch_words:
+                        device.health_inject(uuid, 0x100, 1)
+                    device.arena_destroy(i)
+                nbytes = device.arena_create(i, max_bytes=self.probe_arena_bytes, keep_free_bytes=device.GiB)
+                log.info("probe arena on %s: %d bytes", uuid, nbytes)
+            except GsbError as e:
+                log.warning("no probe arena on %s: %s", uuid, e)
+
     def healthcheck(self) -> None:
         if self.healthCheck:
+            if self.probe_period_ms > 0:
+                self.setup_probe_arenas()
             nvidia.watchXIDs(self.stop, self.devs, self.unhealthy, self.probe_period_ms, self.window_bytes)
         else:
             self.stop.wait()

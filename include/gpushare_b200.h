@@ -197,6 +197,18 @@ typedef struct gsb_cycle_result {
 int gsb_cycle(uint32_t idx, uint64_t cycle_no, uint64_t window_bytes, int unit_gib, uint32_t variant,
               uint8_t *lw_buf, size_t lw_cap, gsb_cycle_result *out);
 
+/*
+ * One NODE cycle: gsb_cycle on every listed device concurrently — one persistent host thread, one
+ * primary context and one non-blocking stream per device, no collective — then
+ * the single host-side join: the per-device lists concatenated in index order into ONE
+ * ListAndWatchResponse (what getDevices builds sequentially, nvidia.go:59-86). The slice count of
+ * device idxs[0] is applied to every device, as the reference's process-global gpuMemory does
+ * (nvidia.go:70-72). results[i] is device idxs[i]'s cycle; returns bytes written to lw_buf or a
+ * negative status.
+ */
+int64_t gsb_cycle_all(uint32_t n, const uint32_t *idxs, uint64_t cycle_no, uint64_t window_bytes, int unit_gib,
+                      uint32_t variant, uint8_t *lw_buf, size_t lw_cap, gsb_cycle_result *results);
+
 /* ---- health events (a10, a11) ------------------------------------------------------------ */
 
 enum {

@@ -118,3 +118,31 @@ def test_probe_all_one_thread_per_device(gsb):
     assert len(rs) == n and all(r.status == 0 and r.mismatch_words == 0 and r.bytes_walked == 2 * GiB for r in rs)
     for i in range(n):
         gsb.arena_destroy(i)
+
+
+def test_node_cycle_all_devices_in_one_process(gsb):
+    """gsb_cycle_all: every GPU of the box probed concurrently (own thread/context/stream), one joined
+    ListAndWatchResponse — equal to the reference's sequential getDevices + marshal."""
+    n = gsb.device_count()
+    for i in range(n):
+        gsb.arena_create(i, max_bytes=4 * GiB)
+    infos = [gsb.device_info(i) for i in range(n)]
+    want = wo.marshal_ListAndWatchResponse(wo.getDevices(
+        [{"uuid": d.uuid, "path": f"/dev/nvidia{d.minor}", "memory_mib": d.total_mib} for d in infos])[0])
+    node = gsb.NodeCycler(list(range(n)), window_bytes=GiB)
+    for k in range(6):  # wraps the 4 windows
+        res = node.step()
+        assert all(r.healthy == 1 and r.probe.bytes_walked == GiB and r.slices == 179 for r in res)
+        assert node.list_and_watch_bytes() == want
+    # corrupt the LAST device's next window: only its fake devices flip
+    victim = n - 1
+    gsb.arena_write(victim, (6 % 4) * GiB + 160, b"\x00" * 16)
+    res = node.step()
+    assert [r.healthy for r in res] == [1] * (n - 1) + [0]
+    devs = wo.unmarshal_ListAndWatchResponse(node.list_and_watch_bytes())
+    bad = {wo.extractRealDeviceID(i) for i, h in devs if h == wo.Unhealthy}
+    assert bad == {infos[victim].uuid} and len(devs) == 179 * n
+    for i in range(n):
+        gsb.arena_destroy(i)
+    gsb.shutdown()
+    gsb.init()
