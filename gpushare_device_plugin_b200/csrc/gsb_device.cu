@@ -33,6 +33,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <map>
 #include <functional>
 #include <memory>
 #include <mutex>
@@ -141,6 +142,7 @@ struct Device {
   size_t va_size = 0;
   std::vector<Chunk> chunks;
   uint64_t arena_bytes = 0;
+  std::map<uint64_t, gsb_launch_geom> geoms;  // (op, variant, grid request) -> resolved launch geometry
   std::vector<uint32_t> gen;  // host mirror of seed_table: generation that last wrote each granule
   uint32_t next_gen = 1;
   bool faulted = false;  // prober: sticky
@@ -461,7 +463,16 @@ int probe_begin_locked(Device *d, const gsb_probe_cfg *cfg, gsb_probe_result *ou
     set_error("seed-table probes need a 64 KiB aligned window offset");
     return out->status = GSB_ERR_INVALID_ARGUMENT;
   }
-  int e = gsb_kernel_geometry(cfg->op, cfg->variant, cfg->grid_ctas, (int)d->sm_count, &fl->geom);
+  // occupancy + function attributes are queried once per (op, variant, grid) and device, not per launch
+  const uint64_t gkey = ((uint64_t)cfg->op << 48) | ((uint64_t)cfg->variant << 32) | cfg->grid_ctas;
+  int e = 0;
+  auto git = d->geoms.find(gkey);
+  if (git != d->geoms.end()) {
+    fl->geom = git->second;
+  } else {
+    e = gsb_kernel_geometry(cfg->op, cfg->variant, cfg->grid_ctas, (int)d->sm_count, &fl->geom);
+    if (!e) d->geoms.emplace(gkey, fl->geom);
+  }
   if (e) {
     set_error("kernel geometry: %s", cudaGetErrorString((cudaError_t)e));
     return out->status = (e == (int)cudaErrorInvalidDeviceFunction || e == (int)cudaErrorNoKernelImageForDevice)
@@ -503,6 +514,18 @@ int probe_end_locked(Device *d, ProbeFlight *fl, gsb_probe_result *out) {
   const gsb_probe_cfg *cfg = &fl->cfg;
   const gsb_kernel_args &a = fl->args;
   if (fl->launched) {
+    // The last CTA stores the launch sequence number into pinned host memory after the results
+    // (__threadfence_system between them): poll that word for up to 2 ms before falling back to a
+    // blocking wait — a sleeping cudaStreamSynchronize costs 10-30 us of wake-up latency, a tenth of
+    // a 1 GiB-window cycle. The stream sync below then returns immediately and orders the events.
+    {
+      const volatile uint32_t *flag = &d->out_host->done_flag;
+      const uint64_t deadline = now_ns() + 2000000ull;
+      while (*flag != a.launch_seq) {
+        for (int i = 0; i < 64; i++) __builtin_ia32_pause();
+        if (now_ns() > deadline) break;
+      }
+    }
     cudaError_t se = cudaStreamSynchronize(d->stream);
     if (se != cudaSuccess) {
       set_error("probe kernel failed: %s", cudaGetErrorString(se));
