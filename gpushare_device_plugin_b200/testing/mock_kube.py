@@ -94,6 +94,9 @@ class MockKube:
                     if u.path == "/pods/" or u.path == "/pods":
                         return self._send(200, {"kind": "PodList", "apiVersion": "v1",
                                                 "items": [copy.deepcopy(mock.pods[k]) for k in mock.order]})
+                    if parts[:3] == ["api", "v1", "nodes"] and len(parts) == 3:
+                        return self._send(200, {"kind": "NodeList", "apiVersion": "v1",
+                                                "items": [copy.deepcopy(n) for n in mock.nodes.values()]})
                     if parts[:3] == ["api", "v1", "nodes"] and len(parts) == 4:
                         n = mock.nodes.get(parts[3])
                         return self._send(200, n) if n else self._status(404, f'nodes "{parts[3]}" not found')
