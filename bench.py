@@ -53,49 +53,75 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons of one GPU sampled DURING the timed region, every 200 ms.
 
-    def __init__(self, gpu_index: int):
-        self.idx, self.proc, self.lines = gpu_index, None, []
+    Sampled in-process through NVML (two calls per sample: nvmlDeviceGetClockInfo and
+    nvmlDeviceGetCurrentClocksEventReasons — the same values `nvidia-smi --query-gpu=clocks.sm,
+    clocks_event_reasons.*` prints). A separate `nvidia-smi -lms` process per rank was measurably
+    perturbing the thing being timed: its polling contends with the cycle's own NVML memory query on
+    the driver lock (inventory 6.6 us -> 50 us at N=1, -> 1.6 ms with 8 samplers; profiles/README.md).
+    Falls back to nvidia-smi only if pynvml is unusable."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, gpu_index: int, period_s: float = 0.2):
+        self.idx, self.period = gpu_index, period_s
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        self.source = "nvml"
+
+    def _run_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+            mask = int(get_reasons(h))
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+            self._stop.wait(self.period)
+
+    def _run_smi(self):
+        self.source = "nvidia-smi"
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            o = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.idx)],
+                               capture_output=True, text=True)
+            p = [x.strip() for x in o.stdout.split(",")]
+            if len(p) >= 6:
+                try:
+                    self.sm.append(float(p[0]))
+                    self.max_mhz = float(p[1])
+                except ValueError:
+                    pass
+                self.reasons.update(n for n, v in zip(names, p[2:6]) if v.lower().startswith("active"))
+            self._stop.wait(self.period)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+        def run():
+            try:
+                self._run_nvml()
+            except Exception:
+                try:
+                    self._run_smi()
+                except Exception:
+                    pass
+        self._t = threading.Thread(target=run, daemon=True)
+        self._t.start()
 
     def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=3)
-        except Exception:
-            self.proc.kill()
-        self.t.join(timeout=2)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            p = [x.strip() for x in ln.split(",")]
-            if len(p) < 9:
-                continue
-            try:
-                sm.append(float(p[1]))
-                mx.append(float(p[2]))
-            except ValueError:
-                continue
-            for name, v in zip(names, p[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=3)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(self.sm), "reasons": sorted(self.reasons), "source": self.source,
+                "period_ms": int(self.period * 1000)}
 
 
 def dist_setup(n_gpus: int):
@@ -304,6 +330,12 @@ def bench_ours(args) -> None:
     f_wall, f_kernel, f_inv, f_launches, f_last = timed_cycles(full, args.full_steps, 3, dist, local)
     clocks = sampler.stop()
 
+    if dist is not None:  # every rank sampled its own GPU: report the slowest median and the union of reasons
+        allc = [None] * world
+        dist.all_gather_object(allc, clocks)
+        meds = [c["sm_mhz"] for c in allc if c and c["sm_mhz"] is not None]
+        clocks = dict(clocks, sm_mhz=min(meds) if meds else None,
+                      reasons=sorted(set(r for c in allc if c for r in c["reasons"])), ranks=world)
     wall_s = allmax(dist, local, wall_ns / 1e9)
     kern_s = allmax(dist, local, kernel_ns / 1e9)
     f_wall_s = allmax(dist, local, f_wall / 1e9)
