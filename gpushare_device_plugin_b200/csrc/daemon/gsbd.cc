@@ -1,0 +1,886 @@
+// gsbd — native (C++) gpushare device-plugin daemon over libgpushare_b200.so.
+//
+// The same process the reference builds from cmd/nvidia/main.go + pkg/gpu/nvidia/*.go, with the same
+// flags, wire surface, side effects and exit codes, and no interpreter on any RPC path:
+//   main / flags                cmd/nvidia/main.go:15-78
+//   manager loop, watchers      pkg/gpu/nvidia/gpumanager.go:33-111, watchers.go:10-32
+//   plugin server               pkg/gpu/nvidia/server.go (Start/Stop/Register/ListAndWatch/healthcheck/Serve)
+//   Allocate                    pkg/gpu/nvidia/allocate.go:42-198 -> gsb_allocate (C ABI) + LIST/PATCH here
+//   pod / node helpers          pkg/gpu/nvidia/podmanager.go, podutils.go
+//   kubelet /pods/ client       pkg/kubelet/client/client.go:75-134
+// gRPC framing is csrc/daemon/h2.hpp; every message byte comes from the C ABI encoders.
+#include <fcntl.h>
+#include <poll.h>
+#include <signal.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/inotify.h>
+#include <sys/signalfd.h>
+#include <sys/stat.h>
+#include <sys/time.h>
+#include <time.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <fstream>
+#include <memory>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../../include/gpushare_b200.h"
+#include "h2.hpp"
+#include "http_client.hpp"
+#include "json.hpp"
+
+namespace {
+
+// ---------------------------------------------------------------- constants (const.go, v1beta1/constants.go)
+const char kResourceName[] = "aliyun.com/gpu-mem";
+const char kResourceCount[] = "aliyun.com/gpu-count";
+const char kDevicePluginPath[] = "/var/lib/kubelet/device-plugins/";
+const char kServerSockName[] = "aliyungpushare.sock";
+const char kOptimisticLockErrorMsg[] =
+    "the object has been modified; please apply your changes to the latest version and try again";
+const char kEnvResourceIndex[] = "ALIYUN_COM_GPU_MEM_IDX";
+const char kEnvAssignedFlag[] = "ALIYUN_COM_GPU_MEM_ASSIGNED";
+const char kEnvResourceAssumeTime[] = "ALIYUN_COM_GPU_MEM_ASSUME_TIME";
+const char kEnvNodeLabelForDisableCGPU[] = "cgpu.disable.isolation";
+
+// ---------------------------------------------------------------- logging (glog-shaped, stderr)
+int g_v = 0;
+std::mutex g_log_mu;
+void logf(char sev, const char *fmt, ...) {
+  char msg[2048];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(msg, sizeof msg, fmt, ap);
+  va_end(ap);
+  timeval tv;
+  gettimeofday(&tv, nullptr);
+  tm t;
+  localtime_r(&tv.tv_sec, &t);
+  std::lock_guard<std::mutex> lk(g_log_mu);
+  fprintf(stderr, "%c%02d%02d %02d:%02d:%02d.%06ld %7d gsbd] %s\n", sev, t.tm_mon + 1, t.tm_mday, t.tm_hour, t.tm_min,
+          t.tm_sec, (long)tv.tv_usec, (int)getpid(), msg);
+}
+#define INFO(...) logf('I', __VA_ARGS__)
+#define WARN(...) logf('W', __VA_ARGS__)
+#define VLOG(n, ...)                 \
+  do {                               \
+    if (g_v >= (n)) logf('I', __VA_ARGS__); \
+  } while (0)
+
+std::string last_error() {
+  char buf[512];
+  gsb_last_error(buf, sizeof buf);
+  return buf;
+}
+
+// ---------------------------------------------------------------- flags (cmd/nvidia/main.go:15-26 + glog's)
+struct Flags {
+  bool mps = false, health_check = false, query_kubelet = false;
+  std::string memory_unit = "GiB", kubelet_address = "0.0.0.0", client_cert, client_key, token;
+  int kubelet_port = 10250, timeout = 10;
+  // additions (active probe, test hooks); none changes the wire contract
+  int probe_period_ms = 1000, probe_window_mib = 1024, probe_arena_mib = 4096, fake_inventory = 0;
+  bool startup_full_walk = false, coalesce_health = true;
+  double pod_cache_ttl = 1.0;
+  std::string kube_api_url, kubelet_scheme = "https";
+};
+
+bool parse_bool(const std::string &v) { return v == "" || v == "1" || v == "t" || v == "T" || v == "true" || v == "TRUE" || v == "True"; }
+
+// Go's flag syntax: -f, --f, -f=v, -f v (non-boolean)
+bool parse_flags(int argc, char **argv, Flags *f) {
+  for (int i = 1; i < argc; i++) {
+    std::string a = argv[i];
+    if (a.size() < 2 || a[0] != '-') {
+      fprintf(stderr, "unexpected argument %s\n", a.c_str());
+      return false;
+    }
+    a.erase(0, a[1] == '-' ? 2 : 1);
+    std::string name = a, val;
+    bool has_val = false;
+    const size_t eq = a.find('=');
+    if (eq != std::string::npos) {
+      name = a.substr(0, eq);
+      val = a.substr(eq + 1);
+      has_val = true;
+    }
+    auto need = [&]() -> bool {
+      if (has_val) return true;
+      if (i + 1 >= argc) return false;
+      val = argv[++i];
+      return true;
+    };
+    auto boolean = [&](bool *dst) { *dst = has_val ? parse_bool(val) : true; };
+    if (name == "mps") boolean(&f->mps);
+    else if (name == "health-check") boolean(&f->health_check);
+    else if (name == "query-kubelet") boolean(&f->query_kubelet);
+    else if (name == "startup-full-walk") boolean(&f->startup_full_walk);
+    else if (name == "coalesce-health") boolean(&f->coalesce_health);
+    else if (name == "logtostderr" || name == "alsologtostderr") { bool ignored; boolean(&ignored); }
+    else if (name == "memory-unit") { if (!need()) return false; f->memory_unit = val; }
+    else if (name == "kubelet-address") { if (!need()) return false; f->kubelet_address = val; }
+    else if (name == "kubelet-port") { if (!need()) return false; f->kubelet_port = atoi(val.c_str()); }
+    else if (name == "client-cert") { if (!need()) return false; f->client_cert = val; }
+    else if (name == "client-key") { if (!need()) return false; f->client_key = val; }
+    else if (name == "token") { if (!need()) return false; f->token = val; }
+    else if (name == "timeout") { if (!need()) return false; f->timeout = atoi(val.c_str()); }
+    else if (name == "v") { if (!need()) return false; g_v = atoi(val.c_str()); }
+    else if (name == "stderrthreshold" || name == "log_dir" || name == "vmodule" || name == "log_backtrace_at") { if (!need()) return false; }
+    else if (name == "probe-period-ms") { if (!need()) return false; f->probe_period_ms = atoi(val.c_str()); }
+    else if (name == "probe-window-mib") { if (!need()) return false; f->probe_window_mib = atoi(val.c_str()); }
+    else if (name == "probe-arena-mib") { if (!need()) return false; f->probe_arena_mib = atoi(val.c_str()); }
+    else if (name == "pod-cache-ttl") { if (!need()) return false; f->pod_cache_ttl = atof(val.c_str()); }
+    else if (name == "kube-api-url") { if (!need()) return false; f->kube_api_url = val; }
+    else if (name == "kubelet-scheme") { if (!need()) return false; f->kubelet_scheme = val; }
+    else if (name == "fake-inventory") { if (!need()) return false; f->fake_inventory = atoi(val.c_str()); }
+    else {
+      fprintf(stderr, "flag provided but not defined: -%s\n", name.c_str());
+      return false;
+    }
+  }
+  return true;
+}
+
+std::string read_file(const std::string &p) {
+  std::ifstream f(p);
+  std::stringstream ss;
+  ss << f.rdbuf();
+  return ss.str();
+}
+bool file_exists(const std::string &p) {
+  struct stat st;
+  return !p.empty() && stat(p.c_str(), &st) == 0;
+}
+
+// ---------------------------------------------------------------- kube API (podmanager.go kubeInit + the calls)
+struct Kube {
+  http::Client api;
+  std::string node_name;
+
+  // kubeInit (podmanager.go:29-57): $KUBECONFIG if the file exists, else in-cluster; NODE_NAME required.
+  bool init(const Flags &f, std::string *err) {
+    const char *nn = getenv("NODE_NAME");
+    node_name = nn ? nn : "";
+    if (node_name.empty()) {
+      *err = "Please set env NODE_NAME";
+      return false;
+    }
+    if (!f.kube_api_url.empty()) return api.configure(f.kube_api_url, "", "", true, 30, err);
+    const char *kc = getenv("KUBECONFIG");
+    if (kc && file_exists(kc)) {
+      // first cluster / first user of the kubeconfig: server, token, CA, insecure-skip-tls-verify
+      std::string server, token, ca;
+      bool insecure = false;
+      std::istringstream in(read_file(kc));
+      std::string line;
+      auto val = [](const std::string &l) {
+        size_t c = l.find(':');
+        std::string v = l.substr(c + 1);
+        while (!v.empty() && (v.front() == ' ' || v.front() == '"')) v.erase(0, 1);
+        while (!v.empty() && (v.back() == ' ' || v.back() == '"' || v.back() == '\r')) v.pop_back();
+        return v;
+      };
+      while (std::getline(in, line)) {
+        std::string t = line;
+        t.erase(0, t.find_first_not_of(" -"));
+        if (t.compare(0, 7, "server:") == 0 && server.empty()) server = val(t);
+        else if (t.compare(0, 6, "token:") == 0 && token.empty()) token = val(t);
+        else if (t.compare(0, 22, "certificate-authority:") == 0 && ca.empty()) ca = val(t);
+        else if (t.compare(0, 25, "insecure-skip-tls-verify:") == 0) insecure = val(t) == "true";
+      }
+      if (server.empty()) {
+        *err = std::string("no cluster server in ") + kc;
+        return false;
+      }
+      return api.configure(server, token, ca, insecure, 30, err);
+    }
+    const char *h = getenv("KUBERNETES_SERVICE_HOST"), *p = getenv("KUBERNETES_SERVICE_PORT");
+    if (!h || !p) {
+      *err = "unable to load in-cluster configuration, KUBERNETES_SERVICE_HOST and KUBERNETES_SERVICE_PORT must be defined";
+      return false;
+    }
+    const std::string sa = "/var/run/secrets/kubernetes.io/serviceaccount/";
+    return api.configure(std::string("https://") + h + ":" + p, read_file(sa + "token"), sa + "ca.crt", false, 30, err);
+  }
+
+  // returns false + *err (= Status.message when the apiserver answered) on failure
+  bool call(const std::string &method, const std::string &path, const std::string &body, const std::string &ctype,
+            json::Value *out, std::string *err) {
+    http::Response r;
+    if (!api.request(method, path, body, ctype, &r, err)) return false;
+    json::Value v;
+    const bool parsed = json::parse(r.body, &v);
+    if (r.status >= 400) {
+      const json::Value *m = parsed ? v.get("message") : nullptr;
+      *err = m ? m->str() : "HTTP " + std::to_string(r.status);
+      return false;
+    }
+    if (!parsed) {
+      *err = "undecodable response from apiserver";
+      return false;
+    }
+    if (out) *out = std::move(v);
+    return true;
+  }
+};
+
+// resource.Quantity.Value(): integers with optional SI / binary suffix, fractions round up
+uint64_t quantity_value(const json::Value &q) {
+  std::string s = q.str();
+  while (!s.empty() && s.back() == ' ') s.pop_back();
+  static const struct { const char *suf; long double mult; } kSuf[] = {
+      {"Ki", 1024.0L}, {"Mi", 1048576.0L}, {"Gi", 1073741824.0L}, {"Ti", 1099511627776.0L},
+      {"Pi", 1125899906842624.0L}, {"Ei", 1152921504606846976.0L}, {"k", 1e3L}, {"M", 1e6L}, {"G", 1e9L},
+      {"T", 1e12L}, {"P", 1e15L}, {"E", 1e18L}, {"m", 1e-3L}};
+  long double mult = 1.0L;
+  for (auto &e : kSuf) {
+    const size_t n = strlen(e.suf);
+    if (s.size() > n && s.compare(s.size() - n, n, e.suf) == 0) {
+      mult = e.mult;
+      s.resize(s.size() - n);
+      break;
+    }
+  }
+  const long double v = strtold(s.c_str(), nullptr) * mult;
+  return v <= 0 ? 0 : (uint64_t)ceill(v - 1e-9L);
+}
+
+// ---------------------------------------------------------------- pending pods -> gsb_pod table
+struct PodRec {
+  std::string name, ns, uid;
+};
+struct PodTable {
+  std::vector<PodRec> recs;
+  std::vector<gsb_pod> pods;
+  std::chrono::steady_clock::time_point stamp;
+  bool valid = false;
+};
+
+bool atoi_strict(const std::string &s, long long *out) {  // strconv.Atoi
+  size_t i = (s.size() && (s[0] == '+' || s[0] == '-')) ? 1 : 0;
+  if (i >= s.size()) return false;
+  for (size_t k = i; k < s.size(); k++)
+    if (s[k] < '0' || s[k] > '9') return false;
+  errno = 0;
+  const long long v = strtoll(s.c_str(), nullptr, 10);
+  if (errno) return false;
+  *out = v;
+  return true;
+}
+bool parse_uint64(const std::string &s, uint64_t *out) {  // strconv.ParseUint(s, 10, 64)
+  if (s.empty()) return false;
+  for (char c : s)
+    if (c < '0' || c > '9') return false;
+  errno = 0;
+  const unsigned long long v = strtoull(s.c_str(), nullptr, 10);
+  if (errno) return false;
+  *out = v;
+  return true;
+}
+
+// v1.PodList JSON -> table; `pending_only` = the kubelet path's phase filter (podmanager.go:101-123)
+void build_table(const json::Value &list, const std::string &node, bool pending_only, PodTable *t) {
+  t->recs.clear();
+  t->pods.clear();
+  const json::Value *items = list.get("items");
+  if (!items || items->type != json::Value::Array) return;
+  t->recs.reserve(items->arr.size());
+  for (const json::Value &p : items->arr) {
+    if (pending_only) {
+      const json::Value *ph = p.path({"status", "phase"});
+      if (!ph || ph->str() != "Pending") continue;
+    }
+    PodRec r;
+    const json::Value *md = p.get("metadata");
+    if (md) {
+      if (auto *v = md->get("name")) r.name = v->str();
+      if (auto *v = md->get("namespace")) r.ns = v->str();
+      if (auto *v = md->get("uid")) r.uid = v->str();
+    }
+    gsb_pod g;
+    memset(&g, 0, sizeof g);
+    g.gpu_idx = -1;
+    if (const json::Value *cs = p.path({"spec", "containers"}))  // podutils.go:122-131: spec.containers only
+      for (const json::Value &c : cs->arr)
+        if (const json::Value *lim = c.path({"resources", "limits", kResourceName})) g.gpu_mem_limit += quantity_value(*lim);
+    const json::Value *ann = md ? md->get("annotations") : nullptr;
+    if (ann && ann->type == json::Value::Object) {
+      if (auto *v = ann->get(kEnvResourceIndex)) {
+        long long id;
+        if (atoi_strict(v->str(), &id) && id >= -2147483648LL && id <= 2147483647LL) g.gpu_idx = id < 0 ? -1 : (int32_t)id;
+      }
+      if (auto *v = ann->get(kEnvResourceAssumeTime)) {
+        g.has_assume_time = 1;
+        uint64_t at;
+        if (parse_uint64(v->str(), &at)) g.assume_time = at;
+      }
+      if (auto *v = ann->get(kEnvAssignedFlag)) {
+        g.has_assigned = 1;
+        g.assigned_is_false = v->str() == "false";
+      }
+    }
+    const json::Value *nn = p.path({"spec", "nodeName"});
+    g.on_node = nn && nn->str() == node;
+    t->recs.push_back(std::move(r));
+    t->pods.push_back(g);
+  }
+  for (size_t i = 0; i < t->recs.size(); i++) {  // pointers only after recs stopped growing
+    t->pods[i].name = t->recs[i].name.c_str();
+    t->pods[i].ns = t->recs[i].ns.c_str();
+    t->pods[i].uid = t->recs[i].uid.c_str();
+  }
+}
+
+// ---------------------------------------------------------------- the plugin (server.go)
+class Plugin {
+ public:
+  Plugin(const Flags &f, Kube *kube, const std::string &socket) : f_(f), kube_(kube), socket_(socket) {}
+  ~Plugin() { stop(); }
+
+  // NewNvidiaDevicePlugin (server.go:38-70): getDevices + patchGPUCount + disableCGPUIsolationOrNot
+  bool build(std::string *err) {
+    const bool gib = f_.memory_unit == "GiB";
+    if (f_.fake_inventory > 0) {  // test hook: synthetic node, no driver needed
+      static const unsigned minors[16] = {2, 3, 0, 1, 6, 7, 4, 5, 8, 9, 10, 11, 12, 13, 14, 15};
+      for (int i = 0; i < f_.fake_inventory && i < 16; i++) {
+        char u[64];
+        snprintf(u, sizeof u, "GPU-%08x-4820-abfc-e83e-9431819757%02x", 0xfef80890u + i, i);
+        uuids_.push_back(u);
+        minors_.push_back(minors[i]);
+      }
+      slices_ = gsb_slices(183359, gib);
+    } else {
+      uint32_t n = 0;
+      if (gsb_device_count(&n) != GSB_OK) {
+        *err = last_error();
+        return false;
+      }
+      for (uint32_t i = 0; i < n; i++) {  // getDevices (nvidia.go:53-89)
+        gsb_device_info info;
+        if (gsb_device_info_get(i, &info) != GSB_OK) {
+          *err = last_error();  // check(err): fatal
+          return false;
+        }
+        INFO("Deivce %s's Path is /dev/nvidia%u", info.uuid, info.minor);
+        INFO("# device Memory: %llu", (unsigned long long)info.total_mib);
+        uuids_.push_back(info.uuid);
+        minors_.push_back(info.minor);
+        if (slices_ == 0) {  // process-global gpuMemory: first GPU only (nvidia.go:70-72)
+          slices_ = gsb_slices(info.total_mib, gib);
+          INFO("set gpu memory: %u", slices_);
+        }
+      }
+    }
+    for (auto &u : uuids_) uuid_ptrs_.push_back(u.c_str());
+    bits_.assign(((size_t)uuids_.size() * slices_ + 7) / 8, 0);
+    if (!patch_gpu_count((int)uuids_.size(), err)) return false;
+    if (!cgpu_disabled(&disable_cgpu_, err)) return false;
+    actx_.uuids = uuid_ptrs_.data();
+    actx_.minors = minors_.data();
+    actx_.n_gpus = (uint32_t)uuids_.size();
+    actx_.slices = slices_;
+    actx_.unit_gib = gib;
+    actx_.disable_cgpu_isolation = disable_cgpu_;
+    return true;
+  }
+
+  // Start (server.go:106-134)
+  bool start(std::string *err) {
+    ::unlink(socket_.c_str());  // cleanup()
+    stopping_ = false;
+    srv_.reset(new h2::Server());
+    srv_->handle("/v1beta1.DevicePlugin/GetDevicePluginOptions", [](h2::Call &c, const std::string &) {
+      c.send_message("", 0);
+      return 0;
+    });
+    srv_->handle("/v1beta1.DevicePlugin/PreStartContainer", [](h2::Call &c, const std::string &) {
+      c.send_message("", 0);
+      return 0;
+    });
+    srv_->handle("/v1beta1.DevicePlugin/ListAndWatch", [this](h2::Call &c, const std::string &) { return list_and_watch(c); });
+    srv_->handle("/v1beta1.DevicePlugin/Allocate", [this](h2::Call &c, const std::string &req) {
+      const std::string resp = allocate(req);
+      c.send_message(resp.data(), resp.size());
+      return 0;  // Allocate never returns a gRPC error (allocate.go: every failure is in the envs)
+    });
+    if (f_.fake_inventory > 0) {
+      // test hook (synthetic-inventory mode only): "<uuid|-> <etype> <edata>" -> gsb_health_inject, i.e. an
+      // event as the driver would deliver it
+      srv_->handle("/gsbd.Test/InjectEvent", [](h2::Call &c, const std::string &req) {
+        char uuid[GSB_UUID_BUFFER_SIZE] = {0};
+        unsigned long long etype = 0, edata = 0;
+        if (sscanf(req.c_str(), "%79s %llu %llu", uuid, &etype, &edata) != 3) return 3;
+        gsb_event ev;
+        memset(&ev, 0, sizeof ev);
+        if (strcmp(uuid, "-") != 0) snprintf(ev.uuid, sizeof ev.uuid, "%s", uuid);
+        ev.etype = etype;
+        ev.edata = edata;
+        gsb_health_inject(&ev);
+        c.send_message("", 0);
+        return 0;
+      });
+    }
+    if (!srv_->start(socket_, err)) return false;
+    health_thread_ = std::thread([this] { healthcheck(); });
+    return true;
+  }
+
+  void stop() {  // Stop (server.go:137-147)
+    if (!srv_) return;
+    stopping_ = true;
+    if (f_.health_check) gsb_health_stop();
+    {
+      std::lock_guard<std::mutex> lk(hmu_);
+      hcv_.notify_all();
+    }
+    srv_->stop();
+    srv_.reset();
+    if (health_thread_.joinable()) health_thread_.join();
+    ::unlink(socket_.c_str());
+  }
+
+  // Register (server.go:150-169)
+  bool register_with(const std::string &kubelet_sock, std::string *err) {
+    uint8_t buf[512];
+    const int64_t n = gsb_encode_register_request("v1beta1", kServerSockName, kResourceName, buf, sizeof buf);
+    std::string resp;
+    const int st = h2::unary_call(kubelet_sock, "/v1beta1.Registration/Register", std::string((char *)buf, (size_t)n),
+                                  &resp, 5, err);
+    if (st != 0) {
+      if (err->empty()) *err = "Register returned grpc-status " + std::to_string(st);
+      return false;
+    }
+    return true;
+  }
+
+ private:
+  // ---- node helpers (podmanager.go:59-99)
+  bool patch_gpu_count(int count, std::string *err) {
+    json::Value node;
+    if (!kube_->call("GET", "/api/v1/nodes/" + kube_->node_name, "", "", &node, err)) return false;
+    if (const json::Value *cap = node.path({"status", "capacity", kResourceCount}))
+      if (quantity_value(*cap) == (uint64_t)count) {
+        INFO("No need to update Capacity %s", kResourceCount);
+        return true;
+      }
+    char body[256];
+    snprintf(body, sizeof body, "{\"status\":{\"allocatable\":{\"%s\":\"%d\"},\"capacity\":{\"%s\":\"%d\"}}}",
+             kResourceCount, count, kResourceCount, count);
+    if (!kube_->call("PATCH", "/api/v1/nodes/" + kube_->node_name + "/status", body,
+                     "application/strategic-merge-patch+json", nullptr, err)) {
+      INFO("Failed to update Capacity %s.", kResourceCount);
+      return false;
+    }
+    INFO("Updated Capacity %s successfully.", kResourceCount);
+    return true;
+  }
+  bool cgpu_disabled(int *out, std::string *err) {
+    json::Value node;
+    if (!kube_->call("GET", "/api/v1/nodes/" + kube_->node_name, "", "", &node, err)) return false;
+    const json::Value *l = node.path({"metadata", "labels", kEnvNodeLabelForDisableCGPU});
+    *out = l && l->str() == "true";
+    return true;
+  }
+
+  std::string list_bytes_locked() {
+    bool any = false;
+    for (uint8_t b : bits_) any = any || b;
+    const int64_t need = gsb_encode_list_and_watch(uuid_ptrs_.data(), (uint32_t)uuids_.size(), slices_,
+                                                   any ? bits_.data() : nullptr, nullptr, 0);
+    std::string out((size_t)(need > 0 ? need : 0), '\0');
+    if (need > 0)
+      gsb_encode_list_and_watch(uuid_ptrs_.data(), (uint32_t)uuids_.size(), slices_, any ? bits_.data() : nullptr,
+                                (uint8_t *)&out[0], out.size());
+    return out;
+  }
+
+  // ListAndWatch (server.go:172-185)
+  int list_and_watch(h2::Call &c) {
+    std::string frame;
+    size_t cursor;
+    {
+      std::lock_guard<std::mutex> lk(hmu_);
+      frame = list_bytes_locked();
+      cursor = pending_.size();
+    }
+    if (!c.send_message(frame.data(), frame.size())) return 1;
+    for (;;) {
+      std::vector<std::string> frames;
+      {
+        std::unique_lock<std::mutex> lk(hmu_);
+        while (cursor >= pending_.size() && !stopping_ && !c.cancelled()) hcv_.wait_for(lk, std::chrono::milliseconds(250));
+        if (stopping_ || c.cancelled()) return 0;  // `case <-m.stop: return nil`
+        for (; cursor < pending_.size(); cursor++) {
+          const size_t i = pending_[cursor];
+          bits_[i >> 3] |= (uint8_t)(1u << (i & 7));  // d.Health = Unhealthy, never recovers (server.go:180)
+          if (!f_.coalesce_health) frames.push_back(list_bytes_locked());  // the reference's stream: one resend per event
+        }
+        if (f_.coalesce_health) frames.push_back(list_bytes_locked());
+      }
+      for (auto &fr : frames)
+        if (!c.send_message(fr.data(), fr.size())) return 1;
+    }
+  }
+
+  void mark_unhealthy(const std::string &uuid) {  // watchXIDs' fan-out (nvidia.go:138-150) + m.unhealthy
+    std::lock_guard<std::mutex> lk(hmu_);
+    for (size_t g = 0; g < uuids_.size(); g++)
+      if (uuid.empty() || uuids_[g] == uuid)
+        for (uint32_t j = 0; j < slices_; j++) pending_.push_back(g * slices_ + j);
+    hcv_.notify_all();
+  }
+
+  void setup_probe_arenas() {
+    for (uint32_t i = 0; i < uuids_.size(); i++) {
+      uint64_t nbytes = 0;
+      if (f_.startup_full_walk) {
+        if (gsb_arena_create(i, 0, 0, &nbytes) == GSB_OK) {
+          gsb_probe_cfg cfg;
+          memset(&cfg, 0, sizeof cfg);
+          cfg.op = GSB_OP_VERIFY;
+          cfg.flags = GSB_PROBE_TIMED | GSB_PROBE_SEED_TABLE;
+          gsb_probe_result r;
+          gsb_probe(i, &cfg, &r);
+          INFO("start-up walk of %s: %llu bytes allocatable, %llu mismatching words, %.1f ms", uuids_[i].c_str(),
+               (unsigned long long)nbytes, (unsigned long long)r.mismatch_words, r.kernel_ns / 1e6);
+          if (r.status != GSB_OK || r.mismatch_words) mark_unhealthy(uuids_[i]);
+          gsb_arena_destroy(i);
+        }
+      }
+      if (gsb_arena_create(i, (uint64_t)f_.probe_arena_mib << 20, 1ull << 30, &nbytes) == GSB_OK)
+        INFO("probe arena on %s: %llu bytes", uuids_[i].c_str(), (unsigned long long)nbytes);
+      else
+        WARN("no probe arena on %s: %s", uuids_[i].c_str(), last_error().c_str());
+    }
+  }
+
+  // healthcheck + watchXIDs (server.go:203-221, nvidia.go:100-152) over gsb_health_wait
+  void healthcheck() {
+    if (!f_.health_check) return;
+    if (f_.fake_inventory == 0) {
+      if (f_.probe_period_ms > 0) setup_probe_arenas();
+      if (gsb_health_start((uint32_t)f_.probe_period_ms, (uint64_t)f_.probe_window_mib << 20) != GSB_OK)
+        WARN("health start: %s", last_error().c_str());
+    }
+    while (!stopping_) {
+      gsb_event ev;
+      const int rc = gsb_health_wait(5000, &ev);  // nvidia.go:126
+      if (rc != GSB_OK) continue;                 // timeout / stopped
+      if (ev.etype != GSB_EVENT_XID && ev.etype != GSB_EVENT_PROBE) continue;   // nvidia.go:127-129
+      if (ev.etype == GSB_EVENT_XID && gsb_xid_is_benign(ev.edata)) continue;  // nvidia.go:134-136
+      mark_unhealthy(ev.uuid);
+    }
+    if (f_.fake_inventory == 0) gsb_health_stop();
+  }
+
+  // ---- Allocate
+  bool load_pods(std::string *err) {
+    json::Value list;
+    bool pending_only = false;
+    bool ok = false;
+    if (f_.query_kubelet) {  // podmanager.go:125-140: 1 try + 8 retries of the kubelet, then the apiserver
+      for (int attempt = 0; attempt <= 8 && !ok; attempt++) {
+        http::Response r;
+        std::string e;
+        if (kubelet_.request("GET", "/pods/", "", "", &r, &e) && r.status == 200 && json::parse(r.body, &list)) {
+          PodTable probe;
+          build_table(list, kube_->node_name, true, &probe);
+          if (!probe.pods.empty()) {
+            ok = true;
+            pending_only = true;
+            break;
+          }
+        }
+        if (attempt < 8) {
+          WARN("failed to get pending pod list, retry");
+          std::this_thread::sleep_for(std::chrono::milliseconds(100));
+        }
+      }
+      if (!ok) WARN("not found from kubelet /pods api, start to list apiserver");
+    }
+    if (!ok) {  // podmanager.go:142-160: 1 try + 3 retries, 1 s apart
+      const std::string path = "/api/v1/pods?fieldSelector=spec.nodeName%3D" + kube_->node_name + "%2Cstatus.phase%3DPending";
+      for (int attempt = 0; attempt < 4 && !ok; attempt++) {
+        ok = kube_->call("GET", path, "", "", &list, err);
+        if (!ok && attempt < 3) std::this_thread::sleep_for(std::chrono::milliseconds(retry_sleep_ms_));
+      }
+      if (!ok) {
+        *err = "failed to get Pods assigned to node " + kube_->node_name;
+        return false;
+      }
+    }
+    build_table(list, kube_->node_name, pending_only, &table_);
+    table_.stamp = std::chrono::steady_clock::now();
+    table_.valid = true;
+    return true;
+  }
+  bool cache_fresh() const {
+    return table_.valid && f_.pod_cache_ttl > 0 &&
+           std::chrono::duration<double>(std::chrono::steady_clock::now() - table_.stamp).count() < f_.pod_cache_ttl;
+  }
+  int decide(const std::string &req, std::string *resp, int32_t *pod_index, uint32_t *pod_req) {
+    resp->resize(1 << 16);
+    size_t n = 0;
+    const int kind = gsb_allocate(&actx_, table_.pods.data(), (uint32_t)table_.pods.size(), (const uint8_t *)req.data(),
+                                  req.size(), (uint8_t *)&(*resp)[0], resp->size(), &n, pod_index, pod_req);
+    resp->resize(kind > 0 ? n : 0);
+    return kind;
+  }
+  std::string err_response(const std::string &req) {  // buildErrResponse (allocate.go:24-39)
+    std::string out(1 << 16, '\0');
+    size_t n = 0;
+    if (gsb_allocate_err_response(&actx_, (const uint8_t *)req.data(), req.size(), (uint8_t *)&out[0], out.size(), &n) != GSB_OK)
+      n = 0;
+    out.resize(n);
+    return out;
+  }
+
+  std::string allocate(const std::string &req) {  // allocate.go:42-198
+    VLOG(1, "----Allocating GPU for gpu mem is started----");
+    std::string resp, name, ns, err;
+    int32_t pidx = -1;
+    uint32_t pod_req = 0;
+    int kind;
+    {
+      std::lock_guard<std::mutex> lk(amu_);  // held for list + decide + claim, not for the PATCH
+      const bool was_cached = cache_fresh();
+      if (!was_cached && !load_pods(&err)) {
+        table_.valid = false;
+        INFO("invalid allocation requst: Failed to find candidate pods due to %s", err.c_str());
+        return err_response(req);
+      }
+      kind = decide(req, &resp, &pidx, &pod_req);
+      if (kind == GSB_ALLOC_ERR_RESPONSE && was_cached) {  // the cache may be older than the pod being started
+        if (!load_pods(&err)) {
+          table_.valid = false;
+          return err_response(req);
+        }
+        kind = decide(req, &resp, &pidx, &pod_req);
+      }
+      if (kind < 0) {
+        WARN("Allocate: %s", last_error().c_str());
+        return "";
+      }
+      VLOG(1, "RequestPodGPUs: %u", pod_req);
+      if (kind == GSB_ALLOC_MATCHED) {
+        name = table_.recs[pidx].name;
+        ns = table_.recs[pidx].ns;
+        table_.pods[pidx].assigned_is_false = 0;  // claimed: hidden from the next request
+      }
+    }
+    if (kind == GSB_ALLOC_MATCHED) {
+      VLOG(1, "Found Assumed GPU shared Pod %s in ns %s with GPU Memory %u", name.c_str(), ns.c_str(), pod_req);
+      char body[256];
+      timespec ts;
+      clock_gettime(CLOCK_REALTIME, &ts);
+      gsb_patch_assigned_body((uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec, body, sizeof body);
+      const std::string path = "/api/v1/namespaces/" + ns + "/pods/" + name;
+      const char *ct = "application/strategic-merge-patch+json";
+      bool ok = kube_->call("PATCH", path, body, ct, nullptr, &err);
+      if (!ok && err == kOptimisticLockErrorMsg) ok = kube_->call("PATCH", path, body, ct, nullptr, &err);  // one retry
+      if (!ok) {
+        WARN("Failed due to %s", err.c_str());
+        std::lock_guard<std::mutex> lk(amu_);
+        table_.valid = false;  // drop the cache: it no longer reflects the apiserver
+        return err_response(req);
+      }
+      VLOG(1, "----Allocating GPU for gpu mem for %s is ended----", name.c_str());
+    } else if (kind == GSB_ALLOC_ERR_RESPONSE) {
+      WARN("invalid allocation requst: request GPU memory %u can't be satisfied.", pod_req);
+    }
+    return resp;
+  }
+
+ public:
+  void configure_kubelet(std::string *err) {
+    std::string token = f_.token;
+    if (f_.client_cert.empty() && f_.client_key.empty() && token.empty())
+      token = read_file("/var/run/secrets/kubernetes.io/serviceaccount/token");  // main.go:29-36
+    kubelet_.configure(f_.kubelet_scheme + "://" + f_.kubelet_address + ":" + std::to_string(f_.kubelet_port), token, "",
+                       true, f_.timeout, err);
+  }
+  void set_retry_sleep_ms(int ms) { retry_sleep_ms_ = ms; }
+  size_t n_gpus() const { return uuids_.size(); }
+  std::string dump() {
+    std::lock_guard<std::mutex> lk(hmu_);
+    std::ostringstream o;
+    o << "gsbd state\nsocket " << socket_ << "\ngpus " << uuids_.size() << " slices " << slices_ << "\n";
+    for (size_t g = 0; g < uuids_.size(); g++) {
+      size_t bad = 0;
+      for (uint32_t j = 0; j < slices_; j++) bad += (bits_[(g * slices_ + j) >> 3] >> ((g * slices_ + j) & 7)) & 1;
+      o << uuids_[g] << " minor " << minors_[g] << " unhealthy_slices " << bad << "\n";
+    }
+    o << "health events queued " << pending_.size() << "\n";
+    return o.str();
+  }
+
+ private:
+  Flags f_;
+  Kube *kube_;
+  http::Client kubelet_;
+  std::string socket_;
+  std::vector<std::string> uuids_;
+  std::vector<const char *> uuid_ptrs_;
+  std::vector<uint32_t> minors_;
+  uint32_t slices_ = 0;
+  int disable_cgpu_ = 0;
+  gsb_allocate_ctx actx_;
+  std::unique_ptr<h2::Server> srv_;
+  std::atomic<bool> stopping_{false};
+  std::thread health_thread_;
+  // health: bitset over fake devices + event log with per-stream cursors (never blocks without a stream)
+  std::mutex hmu_;
+  std::condition_variable hcv_;
+  std::vector<uint8_t> bits_;
+  std::vector<size_t> pending_;
+  // Allocate
+  std::mutex amu_;
+  PodTable table_;
+  int retry_sleep_ms_ = 1000;
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------- main + manager loop (gpumanager.go:33-111)
+int main(int argc, char **argv) {
+  Flags f;
+  if (!parse_flags(argc, argv, &f)) return 2;
+  if (f.memory_unit != "GiB" && f.memory_unit != "MiB") {  // translatememoryUnits (main.go:67-78)
+    WARN("Unsupported memory unit: %s, use memoryUnit Gi as default", f.memory_unit.c_str());
+    f.memory_unit = "GiB";
+  }
+  VLOG(1, "Start gpushare device plugin");
+  const char *pd = getenv("GPUSHARE_PLUGIN_DIR");
+  std::string plugin_dir = pd ? pd : kDevicePluginPath;
+  if (plugin_dir.back() != '/') plugin_dir += '/';
+  const char *dd = getenv("GPUSHARE_DUMP_DIR");
+  const std::string dump_dir = dd ? dd : "/etc/kubernetes/";
+
+  // signals are consumed through a signalfd by the manager loop (newOSWatcher, watchers.go:27-32)
+  sigset_t mask;
+  sigemptyset(&mask);
+  sigaddset(&mask, SIGHUP);
+  sigaddset(&mask, SIGINT);
+  sigaddset(&mask, SIGTERM);
+  sigaddset(&mask, SIGQUIT);
+  pthread_sigmask(SIG_BLOCK, &mask, nullptr);
+  signal(SIGPIPE, SIG_IGN);
+
+  Kube kube;
+  std::string err;
+  if (!kube.init(f, &err)) {  // kubeInit: log.Fatalf
+    logf('F', "Failed due to %s", err.c_str());
+    return 255;
+  }
+
+  VLOG(1, "Loading NVML");
+  if (f.fake_inventory == 0) {
+    if (gsb_init() != GSB_OK) {  // gpumanager.go:36-40: park forever, no crash loop
+      VLOG(1, "Failed to initialize NVML: %s.", last_error().c_str());
+      VLOG(1, "If this is a GPU node, did you set the docker default runtime to `nvidia`?");
+      for (;;) pause();
+    }
+    VLOG(1, "Fetching devices.");
+    uint32_t n = 0;
+    if (gsb_device_count(&n) != GSB_OK || n == 0) {
+      VLOG(1, "No devices found. Waiting indefinitely.");
+      for (;;) pause();
+    }
+  }
+
+  VLOG(1, "Starting FS watcher.");
+  const int ifd = inotify_init1(IN_NONBLOCK | IN_CLOEXEC);
+  if (ifd < 0 || inotify_add_watch(ifd, plugin_dir.c_str(), IN_CREATE | IN_DELETE) < 0) {
+    VLOG(1, "Failed to created FS watcher.");
+    logf('F', "Failed due to inotify on %s: %s", plugin_dir.c_str(), strerror(errno));
+    return 255;
+  }
+  VLOG(1, "Starting OS watcher.");
+  const int sfd = signalfd(-1, &mask, SFD_NONBLOCK | SFD_CLOEXEC);
+
+  const std::string kubelet_sock = plugin_dir + "kubelet.sock";
+  const std::string socket = plugin_dir + kServerSockName;
+  std::unique_ptr<Plugin> plugin;
+  bool restart = true;
+  int rc = 0;
+  for (;;) {
+    if (restart) {
+      if (plugin) plugin->stop();
+      plugin.reset(new Plugin(f, &kube, socket));
+      if (!plugin->build(&err)) {
+        WARN("Failed to get device plugin due to %s", err.c_str());
+        _exit(1);  // gpumanager.go:73
+      }
+      plugin->configure_kubelet(&err);
+      if (getenv("GPUSHARE_RETRY_SLEEP_MS")) plugin->set_retry_sleep_ms(atoi(getenv("GPUSHARE_RETRY_SLEEP_MS")));
+      if (!plugin->start(&err)) {
+        INFO("Could not start device plugin: %s", err.c_str());
+        WARN("Failed to start device plugin due to %s", err.c_str());
+        _exit(2);  // gpumanager.go:76
+      }
+      INFO("Starting to serve on %s", socket.c_str());
+      if (!plugin->register_with(kubelet_sock, &err)) {
+        INFO("Could not register device plugin: %s", err.c_str());
+        plugin->stop();
+        WARN("Failed to start device plugin due to %s", err.c_str());
+        _exit(2);
+      }
+      INFO("Registered device plugin with Kubelet");
+      restart = false;
+    }
+    pollfd fds[2] = {{ifd, POLLIN, 0}, {sfd, POLLIN, 0}};
+    if (poll(fds, 2, -1) < 0) continue;
+    if (fds[0].revents & POLLIN) {
+      alignas(inotify_event) char buf[4096];
+      ssize_t n;
+      while ((n = read(ifd, buf, sizeof buf)) > 0) {
+        for (char *p = buf; p < buf + n;) {
+          inotify_event *ev = reinterpret_cast<inotify_event *>(p);
+          if (ev->len && (ev->mask & IN_CREATE) && strcmp(ev->name, "kubelet.sock") == 0) {
+            VLOG(1, "inotify: %s created, restarting.", kubelet_sock.c_str());  // gpumanager.go:83-87
+            restart = true;
+          }
+          p += sizeof(inotify_event) + ev->len;
+        }
+      }
+    }
+    if (fds[1].revents & POLLIN) {
+      signalfd_siginfo si;
+      while (read(sfd, &si, sizeof si) == (ssize_t)sizeof si) {
+        if (si.ssi_signo == SIGHUP) {
+          VLOG(1, "Received SIGHUP, restarting.");
+          restart = true;
+        } else if (si.ssi_signo == SIGQUIT) {  // gpumanager.go:97-101: dump, keep running
+          INFO("generate core dump");
+          char ts[32];
+          time_t now = time(nullptr);
+          tm t;
+          localtime_r(&now, &t);
+          strftime(ts, sizeof ts, "%Y%m%d%H%M%S", &t);
+          std::ofstream(dump_dir + (dump_dir.back() == '/' ? "" : "/") + "go_" + ts + ".txt") << plugin->dump();
+        } else {
+          VLOG(1, "Received signal \"%s\", shutting down.", strsignal((int)si.ssi_signo));
+          plugin->stop();
+          goto out;
+        }
+      }
+    }
+  }
+out:
+  if (f.fake_inventory == 0) {
+    const int s = gsb_shutdown();
+    VLOG(1, "Shutdown of NVML returned: %s", s == GSB_OK ? "<nil>" : gsb_strerror(s));
+  }
+  return rc;
+}

@@ -1,0 +1,266 @@
+"""gsbd — the native (C++) daemon — end to end on CPU with a synthetic 8-GPU inventory: real HTTP/2
+from grpcio (fake kubelet: Registration server + device-manager client), the stateful mock apiserver,
+signals and inotify. Same expectations as tests/test_server.py has of the Python front end; wire
+bytes are checked against the oracle's restatement of the reference."""
+import json
+import os
+import re
+import signal
+import subprocess
+import threading
+import time
+
+import grpc
+import pytest
+
+from gpushare_device_plugin_b200.testing.fake_kubelet import FakeKubelet
+from gpushare_device_plugin_b200.testing.mock_kube import MockKube, config4_pods, make_node, make_pod
+from oracle import wire_oracle as wo
+
+from . import fakes
+from .test_server import Frames, next_frame
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GSBD = os.path.join(ROOT, "gpushare_device_plugin_b200", "gsbd")
+KAT = json.load(open(os.path.join(ROOT, "tests", "golden", "wire_kat.json")))
+NODE = "b200-0"
+
+pytestmark = pytest.mark.skipif(not os.access(GSBD, os.X_OK), reason="gsbd not built")
+
+
+class Daemon:
+    def __init__(self, tmp_path, kube, *extra, n_gpus=8, wait_register=True, kubelet=None):
+        self.dir = tmp_path
+        self.kubelet = kubelet or FakeKubelet(str(tmp_path))
+        env = dict(os.environ, NODE_NAME=NODE, GPUSHARE_PLUGIN_DIR=str(tmp_path) + "/", GPUSHARE_DUMP_DIR=str(tmp_path),
+                   GPUSHARE_RETRY_SLEEP_MS="1")
+        env.pop("KUBECONFIG", None)
+        self.log = open(tmp_path / "gsbd.log", "w")
+        self.proc = subprocess.Popen([GSBD, "-logtostderr", "--v=5", "--memory-unit=GiB", "--health-check",
+                                      "--fake-inventory", str(n_gpus), "--kube-api-url", kube.url, *extra],
+                                     env=env, stderr=self.log, stdout=self.log)
+        self.register_request = self.kubelet.register_requests.get(timeout=20) if wait_register else None
+
+    def channel(self):
+        return self.kubelet.channel("aliyungpushare.sock")
+
+    def inject(self, ch, uuid, etype, edata):
+        ch.unary_unary("/gsbd.Test/InjectEvent")(f"{uuid or '-'} {etype} {edata}".encode(), timeout=5)
+
+    def close(self):
+        if self.proc.poll() is None:
+            self.proc.send_signal(signal.SIGTERM)
+            try:
+                self.proc.wait(timeout=10)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        self.log.close()
+        self.kubelet.stop()
+
+
+@pytest.fixture
+def world(tmp_path):
+    kube = MockKube(make_node(NODE), config4_pods(NODE))
+    daemons = []
+
+    def start(*extra, **kw):
+        d = Daemon(tmp_path, kube, *extra, **kw)
+        daemons.append(d)
+        return d
+    yield type("W", (), {"kube": kube, "start": staticmethod(start), "dir": tmp_path})
+    for d in daemons:
+        d.close()
+    kube.close()
+    print(open(tmp_path / "gsbd.log").read()[-2500:])
+
+
+def all_devs(unhealthy=()):
+    return [[wo.generateFakeDeviceID(u, j), wo.Unhealthy if g in unhealthy else wo.Healthy]
+            for g, u in enumerate(fakes.UUIDS) for j in range(179)]
+
+
+def test_register_node_capacity_and_trivial_rpcs(world):
+    d = world.start()
+    assert d.register_request.hex() == KAT["register_request_hex"]
+    node = world.kube.nodes[NODE]
+    assert node["status"]["capacity"]["aliyun.com/gpu-count"] == "8" == node["status"]["allocatable"]["aliyun.com/gpu-count"]
+    patch = [r for r in world.kube.requests if r[0] == "PATCH"][0]
+    assert patch[1] == f"/api/v1/nodes/{NODE}/status" and patch[3] == "application/strategic-merge-patch+json"
+    assert json.loads(patch[2]) == {"status": {"allocatable": {"aliyun.com/gpu-count": "8"},
+                                               "capacity": {"aliyun.com/gpu-count": "8"}}}
+    ch = d.channel()
+    assert d.kubelet.get_options(ch) == b"" and d.kubelet.pre_start(ch) == b""
+    with pytest.raises(grpc.RpcError) as e:
+        ch.unary_unary("/v1beta1.DevicePlugin/Nope")(b"", timeout=5)
+    assert e.value.code() == grpc.StatusCode.UNIMPLEMENTED
+    ch.close()
+
+
+@pytest.mark.parametrize("coalesce", [True, False], ids=["coalesced", "reference-stream"])
+def test_list_and_watch_stream(world, coalesce):
+    d = world.start("--coalesce-health=" + ("true" if coalesce else "false"))
+    ch = d.channel()
+    it = Frames(d.kubelet.list_and_watch(ch))
+    first = next_frame(it)
+    assert first == wo.marshal_ListAndWatchResponse(all_devs()) and len(first) == 83608
+    d.inject(ch, fakes.UUIDS[5], 8, 31)  # application-error XID: stays healthy (nvidia.go:134)
+    assert next_frame(it, 0.7) == "timeout"
+    d.inject(ch, fakes.UUIDS[5], 8, 79)
+    ids = [x[0] for x in all_devs()]
+    want = wo.list_and_watch_stream(all_devs(), wo.xid_event_effects(ids, 8, 79, fakes.UUIDS[5]))
+    if coalesce:
+        assert next_frame(it) == want[-1]  # one resend carrying all 179 flips
+    else:
+        assert [next_frame(it) for _ in range(179)] == want[1:]  # the reference's exact stream
+    d.inject(ch, fakes.UUIDS[2], 0x100, 1)  # active-probe verdict
+    last = next_frame(it)
+    while True:
+        f = next_frame(it, 1)
+        if f == "timeout":
+            break
+        last = f
+    assert wo.unmarshal_ListAndWatchResponse(last) == all_devs(unhealthy={2, 5})
+    d.inject(ch, "", 8, 48)  # no UUID: every device (nvidia.go:138-144)
+    last = next_frame(it, 10)
+    while True:
+        f = next_frame(it, 1)
+        if f == "timeout":
+            break
+        last = f
+    assert all(h == wo.Unhealthy for _, h in wo.unmarshal_ListAndWatchResponse(last))
+    ch.close()
+
+
+def test_allocate_config4_end_to_end(world):
+    d = world.start()
+    ch = d.channel()
+    t0 = time.time_ns()
+    for i in range(64):
+        req = wo.marshal_AllocateRequest([[wo.generateFakeDeviceID(fakes.UUIDS[(i * 3) % 8], j) for j in range(4)]])
+        raw = d.kubelet.allocate(ch, req)
+        envs = wo.unmarshal_AllocateResponse(raw)
+        assert envs == [{"NVIDIA_VISIBLE_DEVICES": str(i // 8), "ALIYUN_COM_GPU_MEM_IDX": str(i // 8),
+                         "ALIYUN_COM_GPU_MEM_POD": "4", "ALIYUN_COM_GPU_MEM_CONTAINER": "4",
+                         "ALIYUN_COM_GPU_MEM_DEV": "179"}]
+        assert raw == wo.marshal_AllocateResponse(envs)
+        ann = world.kube.pod(f"pod-{i:02d}")["metadata"]["annotations"]
+        assert ann["ALIYUN_COM_GPU_MEM_ASSIGNED"] == "true" and int(ann["ALIYUN_COM_GPU_MEM_ASSUME_TIME"]) >= t0
+    envs = wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, wo.marshal_AllocateRequest([["a", "b", "c", "d"]])))
+    assert envs == [KAT["err_response"]["envs"]]
+    pod_patches = [r for r in world.kube.requests if r[0] == "PATCH" and "/pods/" in r[1]]
+    assert len(pod_patches) == 64 and pod_patches[0][3] == "application/strategic-merge-patch+json"
+    assert re.fullmatch(rb'\{"metadata":\{"annotations":\{"ALIYUN_COM_GPU_MEM_ASSIGNED":"true",'
+                        rb'"ALIYUN_COM_GPU_MEM_ASSUME_TIME":"\d{19}"\}\}\}', pod_patches[0][2])
+    lists = [r for r in world.kube.requests if r[0] == "GET" and r[1].startswith("/api/v1/pods?")]
+    assert "spec.nodeName%3Db200-0%2Cstatus.phase%3DPending" in lists[0][1] and len(lists) <= 4  # pod cache
+    ch.close()
+
+
+def test_allocate_failure_paths_and_cache(world):
+    d = world.start("--pod-cache-ttl", "60")
+    ch = d.channel()
+    req = wo.marshal_AllocateRequest([["a", "b", "c", "d"]])
+    err = [KAT["err_response"]["envs"]]
+
+    def n(kind, sub):
+        return len([r for r in world.kube.requests if r[0] == kind and sub in r[1]])
+    world.kube.fail_next_patch("the object has been modified; please apply your changes to the latest version and try again", 1)
+    before = n("PATCH", "/pods/")
+    assert wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, req))[0]["ALIYUN_COM_GPU_MEM_IDX"] == "0"
+    assert n("PATCH", "/pods/") == before + 2  # exactly one retry (allocate.go:138-144)
+    world.kube.fail_next_patch("pods is forbidden", 1)
+    before = n("PATCH", "/pods/")
+    assert wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, req)) == err and n("PATCH", "/pods/") == before + 1
+    world.kube.fail_lists = 4  # cache was dropped by the failed PATCH: 1 try + 3 retries all fail
+    assert wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, req)) == err
+    world.kube.fail_lists = 3
+    assert wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, req))[0]["ALIYUN_COM_GPU_MEM_IDX"] == "0"
+    lists = n("GET", "/api/v1/pods?")
+    for _ in range(10):
+        d.kubelet.allocate(ch, req)
+    assert n("GET", "/api/v1/pods?") == lists  # served from the cache
+    new = make_pod(99, NODE, gpu_mem=2, idx=5, assume_time=1_800_000_000_000_000_000)
+    with world.kube.lock:
+        world.kube.pods[("default", "pod-99")] = new
+        world.kube.order.append(("default", "pod-99"))
+    envs = wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, wo.marshal_AllocateRequest([["a", "b"]])))
+    assert envs[0]["ALIYUN_COM_GPU_MEM_IDX"] == "5" and n("GET", "/api/v1/pods?") == lists + 1  # refresh on a miss
+    # malformed request bytes: answered with an empty message, not a crash
+    assert d.kubelet.allocate(ch, b"\x0a\x05\x0a") == b""
+    ch.close()
+
+
+def test_concurrent_allocates_never_share_a_pod(world):
+    d = world.start("--pod-cache-ttl", "60")
+    results, errors = [], []
+
+    def client():
+        try:
+            ch = d.channel()
+            for _ in range(4):
+                results.append(wo.unmarshal_AllocateResponse(
+                    d.kubelet.allocate(ch, wo.marshal_AllocateRequest([["a", "b", "c", "d"]])))[0])
+            ch.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+    ts = [threading.Thread(target=client) for _ in range(16)]
+    [t.start() for t in ts]
+    [t.join(60) for t in ts]
+    assert not errors and len(results) == 64
+    assert sorted(int(r["ALIYUN_COM_GPU_MEM_IDX"]) for r in results) == sorted(i // 8 for i in range(64))
+    patched = [r[1] for r in world.kube.requests if r[0] == "PATCH" and "/pods/" in r[1]]
+    assert len(patched) == 64 and len(set(patched)) == 64
+
+
+def test_query_kubelet_cgpu_label_and_single_gpu(world):
+    world.kube.nodes[NODE]["metadata"]["labels"]["cgpu.disable.isolation"] = "true"
+    d = world.start("--query-kubelet", "--kubelet-address", "127.0.0.1", "--kubelet-port", str(world.kube.port),
+                    "--kubelet-scheme", "http", "--token", "t")
+    ch = d.channel()
+    envs = wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, wo.marshal_AllocateRequest([["a", "b", "c", "d"]])))
+    assert envs[0]["CGPU_DISABLE"] == "true" and envs[0]["ALIYUN_COM_GPU_MEM_IDX"] == "0"
+    assert any(r[:2] == ("GET", "/pods/") for r in world.kube.requests)
+    ch.close()
+    d.close()
+    for k in list(world.kube.pods):
+        world.kube.pods[k]["status"]["phase"] = "Running"
+    d1 = world.start(n_gpus=1)
+    ch = d1.channel()
+    envs = wo.unmarshal_AllocateResponse(d1.kubelet.allocate(ch, wo.marshal_AllocateRequest([["a", "b"]])))
+    assert envs == [{"NVIDIA_VISIBLE_DEVICES": fakes.UUIDS[0], "ALIYUN_COM_GPU_MEM_IDX": str(fakes.MINORS[0]),
+                     "ALIYUN_COM_GPU_MEM_POD": "2", "ALIYUN_COM_GPU_MEM_CONTAINER": "2", "ALIYUN_COM_GPU_MEM_DEV": "179",
+                     "CGPU_DISABLE": "true"}]
+    ch.close()
+
+
+def test_lifecycle_restart_dump_and_exit_codes(world, tmp_path):
+    d = world.start()
+    ch = d.channel()
+    assert len(wo.unmarshal_ListAndWatchResponse(next(iter(d.kubelet.list_and_watch(ch))))) == 1432
+    ch.close()
+    d.proc.send_signal(signal.SIGQUIT)  # dump, keep running (gpumanager.go:97-101)
+    deadline = time.time() + 5
+    while time.time() < deadline and not [f for f in os.listdir(tmp_path) if f.startswith("go_")]:
+        time.sleep(0.05)
+    dumps = [f for f in os.listdir(tmp_path) if f.startswith("go_")]
+    assert dumps and "gpus 8 slices 179" in open(tmp_path / dumps[0]).read() and d.proc.poll() is None
+    d.kubelet.stop()  # kubelet restart: socket re-created -> rebuild + re-register (gpumanager.go:83-87)
+    time.sleep(0.2)
+    d.kubelet.start()
+    assert d.kubelet.register_requests.get(timeout=20) == d.register_request
+    d.proc.send_signal(signal.SIGHUP)  # same via SIGHUP (:94-96)
+    assert d.kubelet.register_requests.get(timeout=20) == d.register_request
+    d.proc.send_signal(signal.SIGTERM)
+    assert d.proc.wait(timeout=10) == 0 and not os.path.exists(tmp_path / "aliyungpushare.sock")
+    # no kubelet to register with: exit status 2 (gpumanager.go:76)
+    d.kubelet.stop()
+    d2 = Daemon(tmp_path, world.kube, wait_register=False, kubelet=d.kubelet)
+    assert d2.proc.wait(timeout=20) == 2
+    d2.log.close()
+    # NODE_NAME missing: fatal at kubeInit
+    env = dict(os.environ)
+    env.pop("NODE_NAME", None)
+    p = subprocess.run([GSBD, "--fake-inventory", "1", "--kube-api-url", world.kube.url], env=env, capture_output=True, text=True)
+    assert p.returncode != 0 and "Please set env NODE_NAME" in p.stderr
+    p = subprocess.run([GSBD, "--no-such-flag"], capture_output=True, text=True)
+    assert p.returncode == 2 and "flag provided but not defined" in p.stderr
