@@ -189,8 +189,9 @@ def bench_allocate(impl: str, quick: bool = False) -> dict:
     """p50 Allocate() (BASELINE.json's second metric), SURVEY.md §8(d) configs 4-5, host-only: real grpc over
     a unix socket, a stateful loopback mock apiserver that applies the PATCH, synthetic 8-GPU inventory
     (the RPC never touches a GPU in either implementation). `ours` = nvidia/server.py over the C ABI
-    (gsb_allocate) with the pending-pod cache; `reference` = oracle/ref_plugin.py (global lock across I/O,
-    LIST per call, Python codec, synchronous log lines)."""
+    (gsb_allocate) with the pending-pod cache — `ours` = the native daemon gsbd, `ours_py` = the Python front
+    end; `reference` = oracle/ref_plugin.py (global lock across I/O, LIST per call, Python codec, synchronous
+    log lines)."""
     import logging
     import shutil
     import tempfile
@@ -208,7 +209,20 @@ def bench_allocate(impl: str, quick: bool = False) -> dict:
         url = f"http://127.0.0.1:{int(kube.stdout.readline())}"
         sock = os.path.join(tmp, "aliyungpushare.sock")
         minors = {u: i for i, u in enumerate(UUIDS8)}
-        if impl == "ours":
+        if impl == "ours":  # the native daemon (gsbd): C++ HTTP/2 front end + C ABI, no interpreter on the RPC path
+            from gpushare_device_plugin_b200.testing.fake_kubelet import FakeKubelet
+            kubelet = FakeKubelet(tmp)
+            env = dict(os.environ, NODE_NAME=node, GPUSHARE_PLUGIN_DIR=tmp + "/", GPUSHARE_DUMP_DIR=tmp)
+            env.pop("KUBECONFIG", None)
+            proc = subprocess.Popen([os.path.join(ROOT, "gpushare_device_plugin_b200", "gsbd"), "--fake-inventory", "8",
+                                     "--kube-api-url", url], env=env, stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL)
+            kubelet.register_requests.get(timeout=30)
+
+            def stop():
+                proc.terminate()
+                proc.wait(timeout=10)
+                kubelet.stop()
+        elif impl == "ours_py":  # the Python front end (nvidia/server.py, grpcio) over the same C ABI
             from gpushare_device_plugin_b200 import device
             from gpushare_device_plugin_b200.nvidia import kubeclient, nvidia, podmanager, server
             podmanager.kubeInit(kubeclient.Clientset(url), node)
@@ -400,6 +414,7 @@ def bench_ours(args) -> None:
     if world == 1 and not args.no_allocate:
         try:
             line["allocate"] = bench_allocate("ours", args.quick_allocate)
+            line["allocate"]["python_front_end"] = bench_allocate("ours_py", True)
         except Exception as e:  # noqa: BLE001
             line["allocate"] = {"error": str(e)}
     print(json.dumps(line))
@@ -420,11 +435,13 @@ def main():
     ap.add_argument("--no-allocate", action="store_true")
     ap.add_argument("--quick-allocate", action="store_true")
     ap.add_argument("--allocate-only", action="store_true", help="host-only: print just the Allocate() leg")
+    ap.add_argument("--allocate-impl", default="", choices=["", "ours", "ours_py", "reference"])
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.allocate_only:
-        print(json.dumps(bench_allocate("reference" if args.impl == "reference" else "ours", args.quick_allocate)))
+        print(json.dumps(bench_allocate(args.allocate_impl or ("reference" if args.impl == "reference" else "ours"),
+                                        args.quick_allocate)))
         return
     if args.impl == "reference":
         bench_reference(args)

@@ -20,7 +20,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 NODE = "b200-0"
 
 
-def test_daemon_end_to_end(tmp_path):
+GSBD = os.path.join(ROOT, "gpushare_device_plugin_b200", "gsbd")
+
+
+@pytest.mark.parametrize("front_end", ["python", "native"])
+def test_daemon_end_to_end(tmp_path, front_end):
     import pynvml
     pynvml.nvmlInit()
     h = pynvml.nvmlDeviceGetHandleByIndex(0)
@@ -36,9 +40,10 @@ def test_daemon_end_to_end(tmp_path):
     env = dict(os.environ, KUBECONFIG=str(kubeconfig), NODE_NAME=NODE, GPUSHARE_PLUGIN_DIR=str(tmp_path) + "/",
                GPUSHARE_DUMP_DIR=str(tmp_path), PYTHONPATH=ROOT)
     log = open(tmp_path / "daemon.log", "w")
-    proc = subprocess.Popen([sys.executable, "-m", "gpushare_device_plugin_b200.cmd.nvidia", "-logtostderr", "--v=5",
-                             "--memory-unit=GiB", "--health-check", "--token", "t", "--probe-period-ms", "100",
-                             "--probe-arena-mib", "2048", "--startup-full-walk"], env=env, stderr=log, stdout=log, cwd=ROOT)
+    argv = [sys.executable, "-m", "gpushare_device_plugin_b200.cmd.nvidia"] if front_end == "python" else [GSBD]
+    proc = subprocess.Popen(argv + ["-logtostderr", "--v=5", "--memory-unit=GiB", "--health-check", "--token", "t",
+                                    "--probe-period-ms", "100", "--probe-arena-mib", "2048", "--startup-full-walk"],
+                            env=env, stderr=log, stdout=log, cwd=ROOT)
     try:
         req = kubelet.register_requests.get(timeout=120)
         assert req == wo.marshal_RegisterRequest("v1beta1", "aliyungpushare.sock", "aliyun.com/gpu-mem")
