@@ -56,7 +56,8 @@ def config4_pods(node: str = "b200-0", n: int = 64, per_gpu: int = 8, mod: bool 
 
 
 class MockKube:
-    def __init__(self, node: dict, pods: List[dict]):
+    def __init__(self, node: dict, pods: List[dict], chunked_lists: bool = False):
+        self.chunked_lists = chunked_lists  # answer pod LISTs with Transfer-Encoding: chunked, like the apiserver
         self.lock = threading.Lock()
         self.nodes: Dict[str, dict] = {node["metadata"]["name"]: node}
         self.pods: Dict[tuple, dict] = {(p["metadata"]["namespace"], p["metadata"]["name"]): p for p in pods}
@@ -76,8 +77,16 @@ class MockKube:
                 super().setup()
                 self.request.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
 
-            def _send(self, code: int, obj):
-                body = json.dumps(obj, separators=(",", ":")).encode()
+            def _send(self, code: int, obj, chunked: bool = False):
+                body = json.dumps(obj, separators=(",", ":"), ensure_ascii=not chunked).encode()
+                if chunked:
+                    out = [b"HTTP/1.1 200 OK\r\nContent-Type: application/json\r\nTransfer-Encoding: chunked\r\n\r\n"]
+                    for i in range(0, len(body), 1000):  # uneven chunks that split UTF-8 sequences and tokens
+                        piece = body[i:i + 1000]
+                        out.append(b"%x\r\n" % len(piece) + piece + b"\r\n")
+                    out.append(b"0\r\n\r\n")
+                    self.wfile.write(b"".join(out))
+                    return
                 head = (f"HTTP/1.1 {code} X\r\nContent-Type: application/json\r\nContent-Length: {len(body)}\r\n"
                         "\r\n").encode()
                 self.wfile.write(head + body)  # one write: headers and body in the same segment
@@ -114,7 +123,8 @@ class MockKube:
                             if "status.phase" in sel and p["status"].get("phase") != sel["status.phase"]:
                                 continue
                             items.append(copy.deepcopy(p))
-                        return self._send(200, {"kind": "PodList", "apiVersion": "v1", "items": items})
+                        return self._send(200, {"kind": "PodList", "apiVersion": "v1", "items": items},
+                                          chunked=mock.chunked_lists)
                 self._status(404, "not found")
 
             def do_PATCH(self):

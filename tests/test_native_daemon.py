@@ -264,3 +264,34 @@ def test_lifecycle_restart_dump_and_exit_codes(world, tmp_path):
     assert p.returncode != 0 and "Please set env NODE_NAME" in p.stderr
     p = subprocess.run([GSBD, "--no-such-flag"], capture_output=True, text=True)
     assert p.returncode == 2 and "flag provided but not defined" in p.stderr
+
+
+def test_chunked_lists_and_awkward_json(tmp_path):
+    """The real apiserver answers LISTs chunked; pods carry escapes, non-ASCII text, numeric and
+    suffixed quantities, nulls and nested objects. The native JSON/HTTP code must read them exactly like
+    the reference's decoder: same pod picked, same envs."""
+    pods = config4_pods(NODE, 8)
+    pods[0]["metadata"]["annotations"]["note"] = 'quote " backslash \\ tab \t newline \n unicode é 漢字 \U0001F600'
+    pods[0]["metadata"]["labels"] = {"a": None, "deep": {"x": [1, 2.5, -3e2, True, False, None, {"y": []}]}}
+    pods[0]["spec"]["containers"][0]["resources"]["limits"]["aliyun.com/gpu-mem"] = 3          # a JSON number
+    pods[1]["spec"]["containers"][0]["resources"]["limits"]["aliyun.com/gpu-mem"] = "2k"       # 2000
+    pods[2]["spec"]["containers"][0]["resources"]["limits"]["aliyun.com/gpu-mem"] = "1500m"    # rounds up to 2
+    pods[2]["metadata"]["annotations"]["ALIYUN_COM_GPU_MEM_IDX"] = "6"
+    pods[3]["metadata"]["annotations"]["ALIYUN_COM_GPU_MEM_ASSUME_TIME"] = "12x"               # unparsable -> 0 = oldest
+    pods[3]["metadata"]["annotations"]["ALIYUN_COM_GPU_MEM_IDX"] = "7"
+    kube = MockKube(make_node(NODE), pods, chunked_lists=True)
+    d = Daemon(tmp_path, kube, "--pod-cache-ttl", "0")
+    try:
+        ch = d.channel()
+        minors = {u: m for u, m in zip(fakes.UUIDS, fakes.MINORS)}
+        for n_ids in (3, 2, 4, 2000):
+            req = [["x"] * n_ids]
+            want, want_pod = wo.Allocate(req, [kube.pod(f"pod-{i:02d}") for i in range(8)], NODE, minors, 179)
+            got = wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, wo.marshal_AllocateRequest(req)))
+            assert got == want, (n_ids, got, want)
+            if want_pod is not None:
+                assert kube.pod(want_pod["metadata"]["name"])["metadata"]["annotations"]["ALIYUN_COM_GPU_MEM_ASSIGNED"] == "true"
+        ch.close()
+    finally:
+        d.close()
+        kube.close()
