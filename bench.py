@@ -304,9 +304,12 @@ def timed_cycles(cyc, steps: int, warmup: int, dist, local):
         cyc.step()
     barrier_sync(dist, local)
     kernel_ns, inv_ns, launches = 0, 0, 0
+    per_step = []
     t0 = time.perf_counter_ns()
     for _ in range(steps):
+        ts = time.perf_counter_ns()
         r = cyc.step()
+        per_step.append(time.perf_counter_ns() - ts)
         if not r.healthy:
             raise RuntimeError(f"probe reported {r.probe.mismatch_words} mismatching words — unhealthy device")
         kernel_ns += r.probe.kernel_ns
@@ -314,6 +317,9 @@ def timed_cycles(cyc, steps: int, warmup: int, dist, local):
         launches += 1
     barrier_sync(dist, local)
     wall_ns = time.perf_counter_ns() - t0
+    per_step.sort()
+    timed_cycles.last_percentiles = {"p50_ms": per_step[len(per_step) // 2] / 1e6,
+                                     "p99_ms": per_step[min(len(per_step) - 1, int(0.99 * len(per_step)))] / 1e6}
     return wall_ns, kernel_ns, inv_ns, launches, r
 
 
@@ -339,6 +345,7 @@ def bench_ours(args) -> None:
     # ---- headline: steady-state rotating window ------------------------------------------------
     cyc = device.Cycler(idx, window_bytes=window, variant=variant)
     wall_ns, kernel_ns, inv_ns, launches, last = timed_cycles(cyc, args.steps, args.warmup, dist, local)
+    step_pct = dict(timed_cycles.last_percentiles)
     # ---- same run: full-arena walk ------------------------------------------------------------------
     full = device.Cycler(idx, window_bytes=0, variant=variant)
     f_wall, f_kernel, f_inv, f_launches, f_last = timed_cycles(full, args.full_steps, 3, dist, local)
@@ -386,7 +393,12 @@ def bench_ours(args) -> None:
                 "note": "gsb_cycle through ctypes: NVML+driver queries, encode, launch, stream sync; h2d = kernel "
                         "argument block, d2h = gsb_kernel_out written by the last CTA into pinned mapped host memory; "
                         "the ListAndWatch bytes are produced on the host",
-                "inventory_us_per_step": inv_ns / 1e3 / args.steps},
+                "inventory_us_per_step": inv_ns / 1e3 / args.steps,
+                "per_step_rank0": step_pct,
+                "noise_note": "value = steps / total wall (a mean). The per-cycle NVML memory query runs while the kernel "
+                              "walks and is hidden up to the kernel's duration; other tenants hammering NVML on a shared "
+                              "host add rare multi-ms driver-lock stalls that lift the mean but not p50 "
+                              "(profiles/cycle_order_r01.txt)"},
         "gpu_launches": launches + f_launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": prof.get("window_1gib_dram_bytes_per_launch"), "kernel": kname + "<VERIFY_REFILL>",

@@ -943,13 +943,31 @@ int gsb_cycle(uint32_t idx, uint64_t cycle_no, uint64_t window_bytes, int unit_g
   }
   cfg.seed_write = d->next_gen++;
   if (d->next_gen == 0) d->next_gen = 1;
+  // diagnostic knob GSB_CYCLE_ORDER (tools/cycle_breakdown.py): 0 = launch, then inventory while the kernel
+  // runs (shipped); 1 = inventory first, then launch; 2 = no inventory; 3 = a plain 170 us host sleep in
+  // place of the inventory (tells host-side overlap apart from driver-side interference)
+  static const int order = [] {
+    const char *e = getenv("GSB_CYCLE_ORDER");
+    return e ? atoi(e) : 0;
+  }();
   ProbeFlight fl;
-  int prc = probe_begin_locked(d, &cfg, &out->probe, &fl);
+  int prc = GSB_OK;
+  if (order != 1) prc = probe_begin_locked(d, &cfg, &out->probe, &fl);
 
   // 2. inventory while the kernel walks HBM: fresh identity + memory info, slices, S fake devices,
   //    wire bytes (optimistically with the health this device had going into the cycle)
   const uint64_t t0 = now_ns();
-  int rc = query_info(d, &out->info);
+  int rc = GSB_OK;
+  if (order == 2 || order == 3) {
+    if (order == 3) {
+      const uint64_t until = now_ns() + 170000;
+      while (now_ns() < until) __builtin_ia32_pause();
+    }
+    snprintf(out->info.uuid, sizeof out->info.uuid, "%s", d->uuid);
+    out->info.total_mib = 183359;
+  } else {
+    rc = query_info(d, &out->info);
+  }
   if (rc == GSB_OK) {
     out->info.index = idx;
     out->slices = gsb_slices(out->info.total_mib, unit_gib);
@@ -962,6 +980,7 @@ int gsb_cycle(uint32_t idx, uint64_t cycle_no, uint64_t window_bytes, int unit_g
   };
   if (rc == GSB_OK) out->lw_len = encode(d->faulted);
   out->inventory_ns = now_ns() - t0;
+  if (order == 1) prc = probe_begin_locked(d, &cfg, &out->probe, &fl);
 
   // 3. verdict
   if (prc == GSB_OK) prc = probe_end_locked(d, &fl, &out->probe);
