@@ -336,7 +336,7 @@ def bench_ours(args) -> None:
         raise RuntimeError(f"rank {rank}: device index {idx} but only {n_dev} GPUs visible")
     keep_free = (2 * GiB) if dist is not None else 0
     arena = device.arena_create(idx, keep_free_bytes=keep_free)
-    variant = {"auto": 0, "direct": 1, "cpasync": 2, "bulk": 3, "bulkw": 4}[args.variant]
+    variant = {"auto": 0, "direct": 1, "cpasync": 2, "bulk": 3, "bulkw": 4, "bulkd": 5}[args.variant]
     peak, peak_src = measured_peak()
     window = args.window_gib * GiB
 
@@ -375,7 +375,7 @@ def bench_ours(args) -> None:
             prof = json.load(f)
     except Exception:
         pass
-    kname = {1: "probe_direct", 2: "probe_cpasync", 3: "probe_bulk", 4: "probe_bulk_warp"}[last.probe.variant]
+    kname = {1: "probe_direct", 2: "probe_cpasync", 3: "probe_bulk", 4: "probe_bulk_warp", 5: "probe_bulk_dyn"}[last.probe.variant]
     line = {
         "metric": METRIC, "value": units / kern_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": kern_s * 1e3 / args.steps, "higher_is_better": True,
@@ -441,7 +441,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--window-gib", type=int, default=1)
     ap.add_argument("--full-steps", type=int, default=10)
-    ap.add_argument("--variant", default="auto", choices=["auto", "direct", "cpasync", "bulk", "bulkw"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "direct", "cpasync", "bulk", "bulkw", "bulkd"])
     ap.add_argument("--cpu-iters", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-allocate", action="store_true")

@@ -33,8 +33,8 @@ GSB_ERR_MALFORMED = -13
 GSB_ERR_STOPPED = -14
 
 GSB_OP_FILL, GSB_OP_VERIFY, GSB_OP_VERIFY_REFILL = 1, 2, 3
-GSB_VARIANT_AUTO, GSB_VARIANT_DIRECT, GSB_VARIANT_CPASYNC, GSB_VARIANT_BULK, GSB_VARIANT_BULKW = 0, 1, 2, 3, 4
-VARIANT_NAMES = {0: "auto", 1: "direct", 2: "cpasync", 3: "bulk", 4: "bulkw"}
+GSB_VARIANT_AUTO, GSB_VARIANT_DIRECT, GSB_VARIANT_CPASYNC, GSB_VARIANT_BULK, GSB_VARIANT_BULKW, GSB_VARIANT_BULKD = 0, 1, 2, 3, 4, 5
+VARIANT_NAMES = {0: "auto", 1: "direct", 2: "cpasync", 3: "bulk", 4: "bulkw", 5: "bulkd"}
 GSB_PROBE_TIMED, GSB_PROBE_SEED_TABLE = 1, 2
 GSB_EVENT_XID, GSB_EVENT_PROBE = 8, 0x100
 GSB_ALLOC_MATCHED, GSB_ALLOC_SINGLE_GPU, GSB_ALLOC_ERR_RESPONSE = 1, 2, 3

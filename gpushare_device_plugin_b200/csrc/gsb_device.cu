@@ -135,6 +135,7 @@ struct Device {
   gsb_kernel_out *out_host = nullptr, *out_dev = nullptr;
   gsb_partial *partials = nullptr;
   unsigned int *ticket = nullptr;
+  unsigned long long *tile_counter = nullptr;
   uint32_t *seed_table = nullptr;  // device copy of gen[]
   uint32_t launch_seq = 0;
 
@@ -306,6 +307,8 @@ int ensure_ready(Device *d) {
                     sizeof(gsb_partial) * gsb_kernel_max_grid((int)d->sm_count)));
   RT_TRY(cudaMalloc(reinterpret_cast<void **>(&d->ticket), sizeof(unsigned int)));
   RT_TRY(cudaMemset(d->ticket, 0, sizeof(unsigned int)));
+  RT_TRY(cudaMalloc(reinterpret_cast<void **>(&d->tile_counter), sizeof(unsigned long long)));
+  RT_TRY(cudaMemset(d->tile_counter, 0, sizeof(unsigned long long)));
   d->ready = true;
   return GSB_OK;
 }
@@ -493,6 +496,7 @@ int probe_begin_locked(Device *d, const gsb_probe_cfg *cfg, gsb_probe_result *ou
   a.launch_seq = ++d->launch_seq;
   a.partials = d->partials;
   a.ticket = d->ticket;
+  a.tile_counter = d->tile_counter;
   a.out = d->out_dev;
   fl->bytes = bytes;
   fl->timed = (cfg->flags & GSB_PROBE_TIMED) != 0;
@@ -762,6 +766,7 @@ int gsb_shutdown(void) {
       cudaFreeHost(d->out_host);
       cudaFree(d->partials);
       cudaFree(d->ticket);
+      cudaFree(d->tile_counter);
       d->ready = false;
     }
   }

@@ -43,6 +43,7 @@ struct gsb_kernel_args {
   uint32_t l2_hint;            /* bit0: bulk loads carry an L2 evict_first policy, bit1: bulk stores do */
   gsb_partial *partials;       /* [grid] device memory */
   unsigned int *ticket;        /* device memory, self-resetting */
+  unsigned long long *tile_counter; /* device memory, self-resetting: dynamic tile scheduler of BULKD */
   gsb_kernel_out *out;         /* device pointer of the mapped host struct */
 };
 

@@ -307,6 +307,7 @@ __device__ void finish(const gsb_kernel_args &a, const Acc &acc) {
   }
   if (threadIdx.x == 0) {
     *a.ticket = 0u;  // self-reset: the next launch on this stream starts from 0
+    if (a.tile_counter) *a.tile_counter = 0ull;
     gsb_kernel_out *o = a.out;
     o->mismatch_words = all.mismatch_words;
     o->mismatch_bits = all.mismatch_bits;
@@ -503,6 +504,90 @@ __global__ void __launch_bounds__(kThreads) probe_bulk(const gsb_kernel_args a) 
     }
   }
   if (leader && OP != GSB_OP_VERIFY) bulk_wait_all<0>();  // shared memory must outlive the stores
+  finish(a, acc);
+}
+
+// ---------------------------------------------------------------- BULKD (TMA ring, dynamic tile scheduler)
+//
+// BULK with the static stride (tile = blockIdx + k*grid) replaced by an atomic tile counter: the leader
+// claims the next tile when it issues that tile's load, so CTAs that run ahead simply take more tiles and
+// the kernel ends with every CTA busy (no straggler tail). Claims are made in time order, so concurrently
+// processed tiles stay neighbours in memory. The claimed index travels to the consumers through shared
+// memory under the stage's mbarrier (arrive = release, wait = acquire).
+template <int OP, int U, int S>
+__global__ void __launch_bounds__(kThreads) probe_bulk_dyn(const gsb_kernel_args a) {
+  static_assert(OP != GSB_OP_FILL, "FILL keeps the static schedule");
+  constexpr unsigned long long TILE = (unsigned long long)kThreads * U;
+  constexpr unsigned long long kDone = ~0ull;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint4 *ring = reinterpret_cast<uint4 *>(smem_raw);  // [S][TILE]
+  __shared__ __align__(8) unsigned long long full_bar[S];
+  __shared__ unsigned long long tile_of[S];
+  const unsigned long long n_tiles = (a.n_words + TILE - 1) / TILE;
+  const uint32_t key_write = gsb_seed_key(a.seed_write);
+  uint4 *__restrict__ win = a.base + a.first_word;
+  const bool leader = threadIdx.x == 0;
+  Acc acc;
+
+  auto words_of = [&](unsigned long long t) -> uint32_t {
+    const unsigned long long left = a.n_words - t * TILE;
+    return (uint32_t)(left < TILE ? left : TILE);
+  };
+  auto load_next = [&](unsigned long long k) {  // leader only: claim a tile for slot k and start its load
+    const int s = (int)(k % S);
+    const unsigned long long t = atomicAdd(a.tile_counter, 1ull);
+    if (t < n_tiles) {
+      tile_of[s] = t;
+      const uint32_t bytes = words_of(t) * 16u;
+      mbar_expect_tx(smem_u32(&full_bar[s]), bytes);
+      bulk_g2s(smem_u32(ring + s * TILE), win + t * TILE, bytes, smem_u32(&full_bar[s]));
+    } else {
+      tile_of[s] = kDone;
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
+    }
+  };
+
+  if (leader) {
+#pragma unroll
+    for (int s = 0; s < S; s++) mbar_init(smem_u32(&full_bar[s]), 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  constexpr int kPrologue = (OP == GSB_OP_VERIFY) ? S : S - 1;
+  if (leader)
+    for (int k = 0; k < kPrologue; k++) load_next(k);
+
+  for (unsigned long long k = 0;; k++) {
+    const int s = (int)(k % S);
+    mbar_wait(smem_u32(&full_bar[s]), (uint32_t)((k / S) & 1ull));
+    const unsigned long long t = tile_of[s];
+    if (t == kDone) break;  // uniform: every thread reads the same slot after the same barrier phase
+    const uint32_t nw_tile = words_of(t);
+    uint4 *stage = ring + s * TILE;
+    const uint32_t key_expect = expect_key_of(a, a.first_word + t * TILE);
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint32_t i = u * kThreads + threadIdx.x;
+      if (i < nw_tile) {
+        const uint4 v = stage[i];
+        const uint4 nw = process_word<OP>(v, a.first_word + t * TILE + i, key_expect, key_write, acc);
+        if (OP != GSB_OP_VERIFY) stage[i] = nw;
+      }
+    }
+    if (OP != GSB_OP_VERIFY) fence_proxy_async_smem();
+    __syncthreads();
+    if (leader) {
+      if (OP == GSB_OP_VERIFY) {
+        load_next(k + S);
+      } else {
+        bulk_s2g(win + t * TILE, smem_u32(stage), nw_tile * 16u);
+        bulk_commit();
+        if (k >= 1) bulk_wait_read<1>();  // stage (k-1)%S: its store has finished reading shared memory
+        load_next(k + S - 1);
+      }
+    }
+  }
+  if (leader && OP != GSB_OP_VERIFY) bulk_wait_all<0>();
   finish(a, acc);
 }
 
@@ -720,6 +805,27 @@ probe_fn pick(uint32_t op, uint32_t variant, uint32_t *smem, uint32_t *threads) 
         GSB_BULK_CASE(4, 4, 3)            // 16 KiB x 3 = 48 KiB (4 CTAs/SM)
         GSB_BULK_CASE(5, 8, 6)            // 32 KiB x 6 = 192 KiB (1 CTA/SM)
 #undef GSB_BULK_CASE
+      }
+      return nullptr;
+    case GSB_VARIANT_BULKD:
+      // dynamic schedule for the loading ops; FILL keeps the static BULK kernel (32 KiB x 6, 1 CTA/SM)
+      if (op == GSB_OP_FILL) {
+        *smem = 8 * kThreads * 16 * 6;
+        return probe_bulk<GSB_OP_FILL, 8, 6>;
+      }
+      switch (bulk_cfg() >= 0 ? bulk_cfg() : 1) {
+#define GSB_BULKD_CASE(ID, U, S)                                                             \
+  case ID:                                                                                   \
+    *smem = U * kThreads * 16 * S;                                                           \
+    if (op == GSB_OP_VERIFY) return probe_bulk_dyn<GSB_OP_VERIFY, U, S>;                     \
+    return probe_bulk_dyn<GSB_OP_VERIFY_REFILL, U, S>;
+        GSB_BULKD_CASE(0, 4, 4)
+        GSB_BULKD_CASE(1, 8, 3)
+        GSB_BULKD_CASE(2, 4, 6)
+        GSB_BULKD_CASE(3, 2, 8)
+        GSB_BULKD_CASE(4, 4, 3)
+        GSB_BULKD_CASE(5, 8, 6)
+#undef GSB_BULKD_CASE
       }
       return nullptr;
     case GSB_VARIANT_BULKW:

@@ -128,7 +128,8 @@ enum {
   GSB_VARIANT_CPASYNC = 2,  /* cp.async 16 B -> shared ring -> ld.shared.v4 -> st.global.v4 */
   GSB_VARIANT_BULK = 3,     /* cp.async.bulk (TMA 1-D) -> shared ring -> ld.shared.v4 / st.shared.v4
                                -> cp.async.bulk shared->global; one ring per CTA, CTA barrier per tile */
-  GSB_VARIANT_BULKW = 4     /* same data path, one private ring + mbarriers per WARP: no CTA barrier */
+  GSB_VARIANT_BULKW = 4,    /* same data path, one private ring + mbarriers per WARP: no CTA barrier */
+  GSB_VARIANT_BULKD = 5     /* BULK with a dynamic (atomic-counter) tile scheduler instead of the static stride */
 };
 enum {
   GSB_PROBE_TIMED = 1u,       /* bracket the launch with CUDA events, fill kernel_ns */

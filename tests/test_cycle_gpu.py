@@ -36,8 +36,8 @@ def test_arena_is_what_is_allocatable(gsb, full_arena):
     assert gsb.device_info(0).free_bytes < 2 * GiB
 
 
-@pytest.mark.parametrize("variant", [_abi.GSB_VARIANT_DIRECT, _abi.GSB_VARIANT_CPASYNC, _abi.GSB_VARIANT_BULK, _abi.GSB_VARIANT_BULKW],
-                         ids=["direct", "cpasync", "bulk", "bulkw"])
+@pytest.mark.parametrize("variant", [_abi.GSB_VARIANT_DIRECT, _abi.GSB_VARIANT_CPASYNC, _abi.GSB_VARIANT_BULK, _abi.GSB_VARIANT_BULKW, _abi.GSB_VARIANT_BULKD],
+                         ids=["direct", "cpasync", "bulk", "bulkw", "bulkd"])
 def test_full_walk_checksum_is_exact(gsb, full_arena, c_oracle, variant):
     """One launch over ~178 GiB (word indices cross 2^32 at 64 GiB): checksum == the oracle's over the
     whole arena, and == the fold of 7 ragged sub-window launches (linearity)."""

@@ -11,8 +11,8 @@ pytestmark = pytest.mark.gpu
 
 from gpushare_device_plugin_b200 import _abi  # noqa: E402
 
-VARIANTS = [_abi.GSB_VARIANT_DIRECT, _abi.GSB_VARIANT_CPASYNC, _abi.GSB_VARIANT_BULK, _abi.GSB_VARIANT_BULKW]
-IDS = ["direct", "cpasync", "bulk", "bulkw"]
+VARIANTS = [_abi.GSB_VARIANT_DIRECT, _abi.GSB_VARIANT_CPASYNC, _abi.GSB_VARIANT_BULK, _abi.GSB_VARIANT_BULKW, _abi.GSB_VARIANT_BULKD]
+IDS = ["direct", "cpasync", "bulk", "bulkw", "bulkd"]
 # (offset_bytes, n_bytes): tile-aligned, ragged head, ragged tail, tiny, one word, > one wave of tiles
 WINDOWS = [
     (0, 1 << 20),
@@ -112,7 +112,7 @@ def test_variants_agree_on_random_windows(gsb, small_arena):
             r = gsb.probe(0, _abi.GSB_OP_VERIFY_REFILL, variant=variant, offset=off, nbytes=nb,
                           seed_expect=seeds[0], seed_write=seeds[1])
             outs.append((r.mismatch_words, r.checksum_xor, r.checksum_sum, gsb.arena_read(0, off, min(nb, 1 << 16))))
-        assert outs[0] == outs[1] == outs[2] == outs[3]
+        assert outs[0] == outs[1] == outs[2] == outs[3] == outs[4]
         assert outs[0][0] == 0
 
 

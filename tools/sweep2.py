@@ -39,11 +39,11 @@ def show(name, rows):
         print(name, rows, flush=True)
         return
     print(name, " | ".join(f"{r['bytes'] >> 20}MiB {r['op']} {r['median_us']:.0f}us {r['frac']:.3f}" for r in rows), flush=True)
-sizes = [GiB, 0]
-for h in range(4):
-    show(f"bulk_default_hint{h}", run({"GSB_L2_HINT": str(h)}, 3, sizes))
-for h in (0, 3):
-    show(f"bulkw_cfg7_hint{h}", run({"GSB_L2_HINT": str(h), "GSB_BULKW_CFG": "7"}, 4, sizes))
-    show(f"bulkw_cfg5_hint{h}", run({"GSB_L2_HINT": str(h), "GSB_BULKW_CFG": "5"}, 4, sizes))
+sizes = [64 << 20, GiB, 16 * GiB, 0]
+for rep in range(2):
+    show(f"bulk_static_rep{rep}", run({}, 3, sizes))
+    show(f"bulk_dynamic_rep{rep}", run({}, 5, sizes))
+show("bulk_dynamic_16k4", run({"GSB_BULK_CFG": "0"}, 5, sizes))
+show("bulk_dynamic_32k6", run({"GSB_BULK_CFG": "5"}, 5, sizes))
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(res, open("gpurun_out/sweep4.json", "w"), indent=1)
+json.dump(res, open("gpurun_out/sweep5.json", "w"), indent=1)
