@@ -63,6 +63,20 @@ int main(int argc, char **argv) {
     printf(" %s\n", err.c_str());
     return st == 0 ? 0 : 2;
   }
-  fprintf(stderr, "usage: h2_selftest serve <socket> | call <socket> <path> <hex>\n");
+  if (argc >= 3 && std::string(argv[1]) == "hpack") {  // decode header blocks in sequence with ONE decoder
+    h2::HpackDecoder dec;
+    for (int i = 2; i < argc; i++) {
+      const std::string block = unhex(argv[i]);
+      h2::Headers hs;
+      if (!dec.decode((const uint8_t *)block.data(), block.size(), &hs)) {
+        printf("ERROR\n");
+        return 1;
+      }
+      for (auto &h : hs) printf("%s: %s\n", h.first.c_str(), h.second.c_str());
+      printf("--\n");
+    }
+    return 0;
+  }
+  fprintf(stderr, "usage: h2_selftest serve <socket> | call <socket> <path> <hex request> | hpack <hex>...\n");
   return 64;
 }

@@ -103,3 +103,106 @@ def test_native_client_against_grpcio_server(tmp_path):
         srv.stop(0)
     out = subprocess.run([BIN, "call", sock, "/x/y", "00"], capture_output=True, text=True, timeout=10)
     assert out.stdout.split()[0] == "-1"  # nobody listening: dial error
+
+
+# ---- HPACK against the RFC's own vectors, and raw frames a C-core client never produces ---------------
+
+def hpack(*blocks):
+    out = subprocess.run([BIN, "hpack", *blocks], capture_output=True, text=True, timeout=10)
+    return out.returncode, [b.strip().split("\n") if b.strip() else [] for b in out.stdout.split("--\n")[:-1]]
+
+
+def test_hpack_rfc7541_appendix_c_request_examples():
+    # C.3 (no Huffman) and C.4 (Huffman): three requests on one connection, dynamic table carried across
+    rc, got = hpack("828684410f7777772e6578616d706c652e636f6d",
+                    "828684be58086e6f2d6361636865",
+                    "828785bf400a637573746f6d2d6b65790c637573746f6d2d76616c7565")
+    assert rc == 0
+    assert got[0] == [":method: GET", ":scheme: http", ":path: /", ":authority: www.example.com"]
+    assert got[1] == [":method: GET", ":scheme: http", ":path: /", ":authority: www.example.com", "cache-control: no-cache"]
+    assert got[2] == [":method: GET", ":scheme: https", ":path: /index.html", ":authority: www.example.com",
+                      "custom-key: custom-value"]
+    rc, hgot = hpack("828684418cf1e3c2e5f23a6ba0ab90f4ff",
+                     "828684be5886a8eb10649cbf",
+                     "828785bf408825a849e95ba97d7f8925a849e95bb8e8b4bf")
+    assert rc == 0 and hgot == got
+    # never-indexed literal, table-size update to 0 (evicts everything) then a stale index must fail
+    rc, g = hpack("100870617373776f726406736563726574")
+    assert rc == 0 and g[0] == ["password: secret"]
+    rc, _ = hpack("828684410f7777772e6578616d706c652e636f6d", "20be")
+    assert rc == 1
+
+
+def frame(ftype, flags, stream, payload=b""):
+    return len(payload).to_bytes(3, "big") + bytes([ftype, flags]) + stream.to_bytes(4, "big") + payload
+
+
+def read_frames(sock, want_stream_end):
+    import socket as _s
+    sock.settimeout(5)
+    buf, frames = b"", []
+    while True:
+        while len(buf) < 9:
+            chunk = sock.recv(65536)
+            if not chunk:
+                return frames
+            buf += chunk
+        ln = int.from_bytes(buf[:3], "big")
+        while len(buf) < 9 + ln:
+            buf += sock.recv(65536)
+        f = (buf[3], buf[4], int.from_bytes(buf[5:9], "big") & 0x7FFFFFFF, buf[9:9 + ln])
+        buf = buf[9 + ln:]
+        frames.append(f)
+        if f[0] == 1 and f[2] == want_stream_end and f[1] & 0x1:  # HEADERS + END_STREAM = trailers
+            return frames
+
+
+def test_raw_frames_continuation_padding_priority(server):
+    import socket as _s
+    _, sock_path, _ = server
+    s = _s.socket(_s.AF_UNIX, _s.SOCK_STREAM)
+    s.connect(sock_path)
+    s.sendall(b"PRI * HTTP/2.0\r\n\r\nSM\r\n\r\n" + frame(4, 0, 0, (4).to_bytes(2, "big") + (1 << 20).to_bytes(4, "big")))
+    # header block: indexed POST/http, literal :path (no huffman), content-type, te — split over HEADERS+2 CONTINUATIONs,
+    # the HEADERS frame padded and carrying a PRIORITY section
+    path = b"/test.Echo/Unary"
+    block = bytes([0x83, 0x86, 0x04, len(path)]) + path + bytes([0x0f, 0x10, 16]) + b"application/grpc" + \
+        bytes([0x00, 2]) + b"te" + bytes([8]) + b"trailers"
+    a, b, c = block[:5], block[5:17], block[17:]
+    padded = bytes([3]) + bytes([0x80, 0, 0, 0, 200]) + a + b"\0\0\0"   # pad length 3, exclusive dep on 0, weight 200
+    s.sendall(frame(1, 0x8 | 0x20, 1, padded) + frame(9, 0, 1, b) + frame(9, 0x4, 1, c))
+    msg = b"padded and split"
+    grpc_msg = b"\0" + len(msg).to_bytes(4, "big") + msg
+    s.sendall(frame(0, 0x8, 1, bytes([2]) + grpc_msg[:7] + b"\0\0") + frame(6, 0, 0, b"pingpong") +
+              frame(0, 0x1, 1, grpc_msg[7:]))
+    frames = read_frames(s, 1)
+    assert any(f[0] == 6 and f[1] & 1 and f[3] == b"pingpong" for f in frames)  # PING ack, same payload
+    assert any(f[0] == 4 and f[1] & 1 for f in frames)                         # SETTINGS ack
+    data = b"".join(f[3] for f in frames if f[0] == 0 and f[2] == 1)
+    assert data == grpc_msg
+    trailers = [f for f in frames if f[0] == 1 and f[2] == 1 and f[1] & 1][0]
+    assert b"grpc-status" in trailers[3] and trailers[3].endswith(b"\x010")
+    # second request on the same connection, tiny peer window: the 100 KB answer must wait for WINDOW_UPDATEs
+    s.sendall(frame(4, 0, 0, (4).to_bytes(2, "big") + (1000).to_bytes(4, "big")))
+    block2 = bytes([0x83, 0x86, 0x04, 17]) + b"/test.Echo/Stream" + bytes([0x0f, 0x10, 16]) + b"application/grpc"
+    req = b"1 100000"
+    s.sendall(frame(1, 0x4, 3, block2) + frame(0, 0x1, 3, b"\0" + len(req).to_bytes(4, "big") + req))
+    got, done = b"", False
+    s.settimeout(5)
+    buf = b""
+    while not done:
+        buf += s.recv(65536)
+        while len(buf) >= 9:
+            ln = int.from_bytes(buf[:3], "big")
+            if len(buf) < 9 + ln:
+                break
+            t, fl, sid, pl = buf[3], buf[4], int.from_bytes(buf[5:9], "big"), buf[9:9 + ln]
+            buf = buf[9 + ln:]
+            if t == 0 and sid == 3:
+                assert len(pl) <= 1000  # never more than the stream window we granted
+                got += pl
+                s.sendall(frame(8, 0, 3, len(pl).to_bytes(4, "big")) + frame(8, 0, 0, len(pl).to_bytes(4, "big")))
+            if t == 1 and sid == 3 and fl & 1:
+                done = True
+    assert len(got) == 5 + 100000 and got[5:] == b"a" * 100000
+    s.close()
