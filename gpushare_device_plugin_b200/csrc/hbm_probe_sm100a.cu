@@ -860,7 +860,9 @@ uint32_t gsb_kernel_max_grid(int sm_count) { return (uint32_t)(sm_count * kMaxCt
 
 int gsb_kernel_geometry(uint32_t op, uint32_t variant, uint32_t grid_request, int sm_count,
                         gsb_launch_geom *geom) {
-  if (variant == GSB_VARIANT_AUTO) variant = GSB_VARIANT_BULK;
+  // shipped choice per op (profiles/sweep_r01_dynamic_scheduler.json): the refill op wants the dynamic tile
+  // scheduler (1.07 vs 0.95 of the copy peak on the full walk), the single-direction ops the static one
+  if (variant == GSB_VARIANT_AUTO) variant = op == GSB_OP_VERIFY_REFILL ? GSB_VARIANT_BULKD : GSB_VARIANT_BULK;
   uint32_t smem = 0, threads = 0;
   probe_fn fn = pick(op, variant, &smem, &threads);
   if (!fn) return (int)cudaErrorInvalidValue;

@@ -1,6 +1,6 @@
 """Small, short target for `ncu --set full` (ncu replays each launch ~40x and saves/restores device
 memory around every pass, which it cannot do for the 178 GiB arena): a 2 GiB arena, 1 GiB windows.
-usage: profile_target.py <variant 1..4> [n_launches]"""
+usage: profile_target.py <variant 1..5> [n_launches]"""
 import os
 import sys
 
