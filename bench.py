@@ -41,6 +41,8 @@ GiB = 1 << 30
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "ref_inventory")
 METRIC = "inventory+health-probe cycles/sec"
 UNIT = "cycles/s"
+WORKLOAD = ("1xB200-per-rank inventory+health cycle: ListAndWatch inventory of 1-GiB aliyun.com/gpu-mem slices "
+            "(BASELINE.json configs[1]) + health check, steady state")
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -279,8 +281,9 @@ def bench_reference(args) -> None:
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean_us / 1e3 / max(n, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "reference NVML path: N x nvml.NewDevice (11 getters) + fan-out + gogo marshal, "
-                               "RegisterEventForDevice x S*N, one WaitForEvent(0 ms); no HBM traffic",
+        "config": {"workload": WORKLOAD,
+                   "reference_path": "N x nvml.NewDevice (11 getters) + fan-out + gogo marshal, RegisterEventForDevice x "
+                                     "S*N, one WaitForEvent(0 ms); sequential, 1 thread; the reference moves no HBM bytes",
                    "devices_seen": n, "fake_devices": r["n_devices"], "lw_bytes": r["lw_len"],
                    "register_calls_per_cycle": r["register_calls_per_cycle"], "register_rc": r["register_rc"],
                    "phases_us_p50": {"inventory": r["inventory_us"]["p50"], "health_setup": r["health_setup_us"]["p50"],
@@ -380,8 +383,9 @@ def bench_ours(args) -> None:
         "metric": METRIC, "value": units / kern_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": kern_s * 1e3 / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": f"1xB200-per-rank ListAndWatch inventory ({last.slices} x 1-GiB aliyun.com/gpu-mem slices, "
-                               f"{last.lw_len} B) + VERIFY_REFILL HBM probe of a rotating {args.window_gib} GiB window",
+        "config": {"workload": WORKLOAD,
+                   "ours_path": f"{last.slices} slices / {last.lw_len} B ListAndWatchResponse + VERIFY_REFILL HBM probe of a "
+                                f"rotating {args.window_gib} GiB window (one advertised slice) over the whole arena",
                    "window_bytes": window, "arena_bytes": arena, "variant": _abi.VARIANT_NAMES[last.probe.variant],
                    "grid_ctas": last.probe.grid_ctas, "block_threads": last.probe.block_threads,
                    "l2_policy": "inputs larger than L2: the window rotates over the whole arena, no flush needed",

@@ -516,7 +516,6 @@ __global__ void __launch_bounds__(kThreads) probe_bulk(const gsb_kernel_args a) 
 // memory under the stage's mbarrier (arrive = release, wait = acquire).
 template <int OP, int U, int S>
 __global__ void __launch_bounds__(kThreads) probe_bulk_dyn(const gsb_kernel_args a) {
-  static_assert(OP != GSB_OP_FILL, "FILL keeps the static schedule");
   constexpr unsigned long long TILE = (unsigned long long)kThreads * U;
   constexpr unsigned long long kDone = ~0ull;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -528,21 +527,28 @@ __global__ void __launch_bounds__(kThreads) probe_bulk_dyn(const gsb_kernel_args
   uint4 *__restrict__ win = a.base + a.first_word;
   const bool leader = threadIdx.x == 0;
   Acc acc;
-
+  // the leader always holds one claim in hand: the atomic for the NEXT tile is issued when the current one
+  // is consumed, so its ~L2 round trip overlaps the tile being processed instead of delaying the next load
+  unsigned long long in_hand = 0;
+  if (leader) in_hand = atomicAdd(a.tile_counter, 1ull);
+  auto claim = [&]() -> unsigned long long {
+    const unsigned long long t = in_hand;
+    in_hand = atomicAdd(a.tile_counter, 1ull);
+    return t < n_tiles ? t : kDone;
+  };
   auto words_of = [&](unsigned long long t) -> uint32_t {
     const unsigned long long left = a.n_words - t * TILE;
     return (uint32_t)(left < TILE ? left : TILE);
   };
   auto load_next = [&](unsigned long long k) {  // leader only: claim a tile for slot k and start its load
     const int s = (int)(k % S);
-    const unsigned long long t = atomicAdd(a.tile_counter, 1ull);
-    if (t < n_tiles) {
-      tile_of[s] = t;
+    const unsigned long long t = claim();
+    tile_of[s] = t;
+    if (t != kDone) {
       const uint32_t bytes = words_of(t) * 16u;
       mbar_expect_tx(smem_u32(&full_bar[s]), bytes);
       bulk_g2s(smem_u32(ring + s * TILE), win + t * TILE, bytes, smem_u32(&full_bar[s]));
     } else {
-      tile_of[s] = kDone;
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
     }
   };
@@ -554,22 +560,31 @@ __global__ void __launch_bounds__(kThreads) probe_bulk_dyn(const gsb_kernel_args
   }
   __syncthreads();
   constexpr int kPrologue = (OP == GSB_OP_VERIFY) ? S : S - 1;
-  if (leader)
+  if (OP != GSB_OP_FILL && leader)
     for (int k = 0; k < kPrologue; k++) load_next(k);
 
   for (unsigned long long k = 0;; k++) {
     const int s = (int)(k % S);
-    mbar_wait(smem_u32(&full_bar[s]), (uint32_t)((k / S) & 1ull));
+    if (OP == GSB_OP_FILL) {
+      if (leader) {
+        bulk_wait_read<S - 1>();  // the store that last read this stage (slot k-S) has drained it
+        tile_of[s] = claim();
+      }
+      __syncthreads();
+    } else {
+      mbar_wait(smem_u32(&full_bar[s]), (uint32_t)((k / S) & 1ull));
+    }
     const unsigned long long t = tile_of[s];
-    if (t == kDone) break;  // uniform: every thread reads the same slot after the same barrier phase
+    if (t == kDone) break;  // uniform: every thread reads the same slot after the same barrier
     const uint32_t nw_tile = words_of(t);
     uint4 *stage = ring + s * TILE;
-    const uint32_t key_expect = expect_key_of(a, a.first_word + t * TILE);
+    const uint32_t key_expect = (OP != GSB_OP_FILL) ? expect_key_of(a, a.first_word + t * TILE) : 0u;
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const uint32_t i = u * kThreads + threadIdx.x;
       if (i < nw_tile) {
-        const uint4 v = stage[i];
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (OP != GSB_OP_FILL) v = stage[i];
         const uint4 nw = process_word<OP>(v, a.first_word + t * TILE + i, key_expect, key_write, acc);
         if (OP != GSB_OP_VERIFY) stage[i] = nw;
       }
@@ -582,8 +597,10 @@ __global__ void __launch_bounds__(kThreads) probe_bulk_dyn(const gsb_kernel_args
       } else {
         bulk_s2g(win + t * TILE, smem_u32(stage), nw_tile * 16u);
         bulk_commit();
-        if (k >= 1) bulk_wait_read<1>();  // stage (k-1)%S: its store has finished reading shared memory
-        load_next(k + S - 1);
+        if (OP == GSB_OP_VERIFY_REFILL) {
+          if (k >= 1) bulk_wait_read<1>();  // stage (k-1)%S: its store has finished reading shared memory
+          load_next(k + S - 1);
+        }
       }
     }
   }
@@ -723,6 +740,15 @@ int resident_ctas(K kernel, uint32_t smem, int threads) {
 
 typedef void (*probe_fn)(const gsb_kernel_args);
 
+// experiment knob GSB_DYN_FILL=1: FILL under GSB_VARIANT_BULKD uses the dynamic scheduler too
+bool dyn_fill() {
+  static const bool f = [] {
+    const char *e = getenv("GSB_DYN_FILL");
+    return e && atoi(e) != 0;
+  }();
+  return f;
+}
+
 // experiment knob GSB_BULKW_CFG: warp-tile size x ring depth x warps per CTA of the per-warp TMA path
 int bulkw_cfg() {
   static const int f = [] {
@@ -809,14 +835,15 @@ probe_fn pick(uint32_t op, uint32_t variant, uint32_t *smem, uint32_t *threads) 
       return nullptr;
     case GSB_VARIANT_BULKD:
       // dynamic schedule for the loading ops; FILL keeps the static BULK kernel (32 KiB x 6, 1 CTA/SM)
-      if (op == GSB_OP_FILL) {
+      if (op == GSB_OP_FILL && !dyn_fill()) {
         *smem = 8 * kThreads * 16 * 6;
         return probe_bulk<GSB_OP_FILL, 8, 6>;
       }
-      switch (bulk_cfg() >= 0 ? bulk_cfg() : 1) {
+      switch (bulk_cfg() >= 0 ? bulk_cfg() : (op == GSB_OP_FILL ? 5 : 1)) {
 #define GSB_BULKD_CASE(ID, U, S)                                                             \
   case ID:                                                                                   \
     *smem = U * kThreads * 16 * S;                                                           \
+    if (op == GSB_OP_FILL) return probe_bulk_dyn<GSB_OP_FILL, U, S>;                         \
     if (op == GSB_OP_VERIFY) return probe_bulk_dyn<GSB_OP_VERIFY, U, S>;                     \
     return probe_bulk_dyn<GSB_OP_VERIFY_REFILL, U, S>;
         GSB_BULKD_CASE(0, 4, 4)

@@ -39,11 +39,12 @@ def show(name, rows):
         print(name, rows, flush=True)
         return
     print(name, " | ".join(f"{r['bytes'] >> 20}MiB {r['op']} {r['median_us']:.0f}us {r['frac']:.3f}" for r in rows), flush=True)
-sizes = [64 << 20, GiB, 16 * GiB, 0]
-for rep in range(2):
-    show(f"bulk_static_rep{rep}", run({}, 3, sizes))
-    show(f"bulk_dynamic_rep{rep}", run({}, 5, sizes))
-show("bulk_dynamic_16k4", run({"GSB_BULK_CFG": "0"}, 5, sizes))
-show("bulk_dynamic_32k6", run({"GSB_BULK_CFG": "5"}, 5, sizes))
+sizes = [GiB, 16 * GiB, 0]
+show("bulk_static", run({}, 3, sizes))
+show("bulk_dynamic_prefetched_claim", run({}, 5, sizes))
+show("bulk_dynamic_fill_32k6", run({"GSB_DYN_FILL": "1"}, 5, sizes))
+show("bulk_dynamic_all_32k3", run({"GSB_DYN_FILL": "1", "GSB_BULK_CFG": "1"}, 5, sizes))
+show("bulk_dynamic_all_16k4", run({"GSB_DYN_FILL": "1", "GSB_BULK_CFG": "0"}, 5, sizes))
+show("bulk_dynamic_all_16k6", run({"GSB_DYN_FILL": "1", "GSB_BULK_CFG": "2"}, 5, sizes))
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(res, open("gpurun_out/sweep5.json", "w"), indent=1)
+json.dump(res, open("gpurun_out/sweep6.json", "w"), indent=1)
