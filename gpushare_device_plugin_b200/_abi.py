@@ -37,6 +37,7 @@ GSB_VARIANT_AUTO, GSB_VARIANT_DIRECT, GSB_VARIANT_CPASYNC, GSB_VARIANT_BULK, GSB
 VARIANT_NAMES = {0: "auto", 1: "direct", 2: "cpasync", 3: "bulk", 4: "bulkw", 5: "bulkd"}
 GSB_PROBE_TIMED, GSB_PROBE_SEED_TABLE = 1, 2
 GSB_EVENT_XID, GSB_EVENT_PROBE = 8, 0x100
+GSB_PROBE_FAULT_MISMATCH, GSB_PROBE_FAULT_LAUNCH, GSB_PROBE_RECOVERED = 1, 2, 3
 GSB_ALLOC_MATCHED, GSB_ALLOC_SINGLE_GPU, GSB_ALLOC_ERR_RESPONSE = 1, 2, 3
 UINT64_MAX = (1 << 64) - 1
 
@@ -47,7 +48,7 @@ SYMBOLS = [
     "gsb_encode_list_and_watch", "gsb_encode_register_request",
     "gsb_arena_create", "gsb_arena_destroy", "gsb_arena_bytes", "gsb_probe", "gsb_probe_all",
     "gsb_arena_read", "gsb_arena_write", "gsb_cycle", "gsb_cycle_all",
-    "gsb_health_start", "gsb_health_stop", "gsb_health_wait", "gsb_health_inject", "gsb_xid_is_benign",
+    "gsb_health_start", "gsb_health_stop", "gsb_health_wait", "gsb_health_inject", "gsb_health_set_recovery", "gsb_xid_is_benign",
     "gsb_allocate", "gsb_allocate_err_response", "gsb_patch_assigned_body",
 ]
 
@@ -184,6 +185,7 @@ def _load() -> C.CDLL:
         "gsb_health_stop": (C.c_int, []),
         "gsb_health_wait": (C.c_int, [C.c_uint32, C.POINTER(Event)]),
         "gsb_health_inject": (C.c_int, [C.POINTER(Event)]),
+        "gsb_health_set_recovery": (C.c_int, [C.c_uint32]),
         "gsb_xid_is_benign": (C.c_int, [C.c_uint64]),
         "gsb_allocate": (C.c_int, [C.POINTER(AllocateCtx), C.POINTER(Pod), C.c_uint32, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int32), u32p]),
         "gsb_allocate_err_response": (C.c_int, [C.POINTER(AllocateCtx), C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -51,6 +51,7 @@ def parse(argv):
     add("probe-window-mib", default=1024, type=int)
     add("probe-arena-mib", default=4096, type=int)
     add("startup-full-walk", default=False, **b)
+    add("health-recovery-cycles", default=0, type=int)
     return p.parse_args(argv)
 
 
@@ -86,7 +87,8 @@ def main(argv=None) -> None:  # main.go:55-65
                               kubeletClient, pluginDir=os.environ.get("GPUSHARE_PLUGIN_DIR", const.DevicePluginPath),
                               dumpDir=os.environ.get("GPUSHARE_DUMP_DIR", "/etc/kubernetes/"),
                               probe_period_ms=a.probe_period_ms, window_bytes=a.probe_window_mib << 20,
-                              probe_arena_bytes=a.probe_arena_mib << 20, startup_full_walk=a.startup_full_walk)
+                              probe_arena_bytes=a.probe_arena_mib << 20, startup_full_walk=a.startup_full_walk,
+                              health_recovery_cycles=a.health_recovery_cycles)
     ngm.Run()
 
 

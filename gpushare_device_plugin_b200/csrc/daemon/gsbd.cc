@@ -91,6 +91,7 @@ struct Flags {
   int kubelet_port = 10250, timeout = 10;
   // additions (active probe, test hooks); none changes the wire contract
   int probe_period_ms = 1000, probe_window_mib = 1024, probe_arena_mib = 4096, fake_inventory = 0;
+  int health_recovery_cycles = 0;  // 0 = the reference's sticky Unhealthy
   bool startup_full_walk = false, coalesce_health = true;
   double pod_cache_ttl = 1.0;
   std::string kube_api_url, kubelet_scheme = "https";
@@ -140,6 +141,7 @@ bool parse_flags(int argc, char **argv, Flags *f) {
     else if (name == "probe-period-ms") { if (!need()) return false; f->probe_period_ms = atoi(val.c_str()); }
     else if (name == "probe-window-mib") { if (!need()) return false; f->probe_window_mib = atoi(val.c_str()); }
     else if (name == "probe-arena-mib") { if (!need()) return false; f->probe_arena_mib = atoi(val.c_str()); }
+    else if (name == "health-recovery-cycles") { if (!need()) return false; f->health_recovery_cycles = atoi(val.c_str()); }
     else if (name == "pod-cache-ttl") { if (!need()) return false; f->pod_cache_ttl = atof(val.c_str()); }
     else if (name == "kube-api-url") { if (!need()) return false; f->kube_api_url = val; }
     else if (name == "kubelet-scheme") { if (!need()) return false; f->kubelet_scheme = val; }
@@ -522,8 +524,13 @@ class Plugin {
         while (cursor >= pending_.size() && !stopping_ && !c.cancelled()) hcv_.wait_for(lk, std::chrono::milliseconds(250));
         if (stopping_ || c.cancelled()) return 0;  // `case <-m.stop: return nil`
         for (; cursor < pending_.size(); cursor++) {
-          const size_t i = pending_[cursor];
-          bits_[i >> 3] |= (uint8_t)(1u << (i & 7));  // d.Health = Unhealthy, never recovers (server.go:180)
+          const long long e = pending_[cursor];
+          if (e >= 0) {
+            bits_[(size_t)e >> 3] |= (uint8_t)(1u << (e & 7));  // d.Health = Unhealthy (server.go:181)
+          } else {  // optional recovery (not in the reference): ~e is the device index
+            const size_t i = (size_t)~e;
+            bits_[i >> 3] &= (uint8_t)~(1u << (i & 7));
+          }
           if (!f_.coalesce_health) frames.push_back(list_bytes_locked());  // the reference's stream: one resend per event
         }
         if (f_.coalesce_health) frames.push_back(list_bytes_locked());
@@ -533,13 +540,17 @@ class Plugin {
     }
   }
 
-  void mark_unhealthy(const std::string &uuid) {  // watchXIDs' fan-out (nvidia.go:138-150) + m.unhealthy
+  void mark(const std::string &uuid, bool healthy) {  // watchXIDs' fan-out (nvidia.go:138-150) + m.unhealthy
     std::lock_guard<std::mutex> lk(hmu_);
     for (size_t g = 0; g < uuids_.size(); g++)
       if (uuid.empty() || uuids_[g] == uuid)
-        for (uint32_t j = 0; j < slices_; j++) pending_.push_back(g * slices_ + j);
+        for (uint32_t j = 0; j < slices_; j++) {
+          const long long i = (long long)(g * slices_ + j);
+          pending_.push_back(healthy ? ~i : i);
+        }
     hcv_.notify_all();
   }
+  void mark_unhealthy(const std::string &uuid) { mark(uuid, false); }
 
   void setup_probe_arenas() {
     for (uint32_t i = 0; i < uuids_.size(); i++) {
@@ -570,6 +581,7 @@ class Plugin {
     if (!f_.health_check) return;
     if (f_.fake_inventory == 0) {
       if (f_.probe_period_ms > 0) setup_probe_arenas();
+      gsb_health_set_recovery((uint32_t)f_.health_recovery_cycles);
       if (gsb_health_start((uint32_t)f_.probe_period_ms, (uint64_t)f_.probe_window_mib << 20) != GSB_OK)
         WARN("health start: %s", last_error().c_str());
     }
@@ -579,6 +591,10 @@ class Plugin {
       if (rc != GSB_OK) continue;                 // timeout / stopped
       if (ev.etype != GSB_EVENT_XID && ev.etype != GSB_EVENT_PROBE) continue;   // nvidia.go:127-129
       if (ev.etype == GSB_EVENT_XID && gsb_xid_is_benign(ev.edata)) continue;  // nvidia.go:134-136
+      if (ev.etype == GSB_EVENT_PROBE && ev.edata == GSB_PROBE_RECOVERED) {  // not in the reference: flag-gated
+        if (f_.health_recovery_cycles > 0 && ev.uuid[0]) mark(ev.uuid, true);
+        continue;
+      }
       mark_unhealthy(ev.uuid);
     }
     if (f_.fake_inventory == 0) gsb_health_stop();
@@ -743,7 +759,7 @@ class Plugin {
   std::mutex hmu_;
   std::condition_variable hcv_;
   std::vector<uint8_t> bits_;
-  std::vector<size_t> pending_;
+  std::vector<long long> pending_;  // i >= 0: device i Unhealthy; ~i: device i Healthy again (recovery flag)
   // Allocate
   std::mutex amu_;
   PodTable table_;

@@ -169,6 +169,7 @@ struct Global {
   std::deque<gsb_event> events;
   bool health_running = false;
   std::atomic<bool> health_stop{false};
+  std::atomic<uint32_t> recovery_cycles{0};
   uint64_t stop_gen = 0;  // bumped by every gsb_health_stop: wakes all gsb_health_wait callers
   std::vector<std::thread> health_threads;
   nvmlEventSet_t event_set{};
@@ -1004,6 +1005,11 @@ int gsb_cycle(uint32_t idx, uint64_t cycle_no, uint64_t window_bytes, int unit_g
 
 int gsb_xid_is_benign(uint64_t xid) { return xid == 31 || xid == 43 || xid == 45; }
 
+int gsb_health_set_recovery(uint32_t clean_cycles) {
+  G.recovery_cycles = clean_cycles;
+  return GSB_OK;
+}
+
 int gsb_health_inject(const gsb_event *ev) {
   if (!ev) return GSB_ERR_INVALID_ARGUMENT;
   push_event(*ev);
@@ -1070,10 +1076,12 @@ int gsb_health_start(uint32_t probe_period_ms, uint64_t window_bytes) {
         std::vector<uint8_t> buf(1 << 16);
         uint64_t cycle = 0;
         bool reported = false;
+        uint32_t clean = 0;
         while (!G.health_stop.load()) {
           gsb_cycle_result cr;
           int rc = gsb_cycle(i, cycle++, window_bytes, 1, GSB_VARIANT_AUTO, buf.data(), buf.size(), &cr);
-          if (rc != GSB_ERR_NO_ARENA && !cr.healthy && !reported) {
+          const bool this_cycle_clean = rc == GSB_OK && cr.probe.mismatch_words == 0;
+          if (rc != GSB_ERR_NO_ARENA && !this_cycle_clean && !reported) {
             gsb_event ev;
             memset(&ev, 0, sizeof ev);
             snprintf(ev.uuid, sizeof ev.uuid, "%s", G.devs[i]->uuid);
@@ -1081,6 +1089,24 @@ int gsb_health_start(uint32_t probe_period_ms, uint64_t window_bytes) {
             ev.edata = rc == GSB_OK ? GSB_PROBE_FAULT_MISMATCH : GSB_PROBE_FAULT_LAUNCH;
             push_event(ev);
             reported = true;
+            clean = 0;
+          } else if (reported) {
+            clean = this_cycle_clean ? clean + 1 : 0;
+            const uint32_t need = G.recovery_cycles.load();
+            if (need > 0 && clean >= need) {  // optional recovery: the refills since the fault all verified
+              {
+                std::lock_guard<std::mutex> dl(G.devs[i]->mu);
+                G.devs[i]->faulted = false;
+              }
+              gsb_event ev;
+              memset(&ev, 0, sizeof ev);
+              snprintf(ev.uuid, sizeof ev.uuid, "%s", G.devs[i]->uuid);
+              ev.etype = GSB_EVENT_PROBE;
+              ev.edata = GSB_PROBE_RECOVERED;
+              push_event(ev);
+              reported = false;
+              clean = 0;
+            }
           }
           for (uint32_t slept = 0; slept < probe_period_ms && !G.health_stop.load(); slept += 10)
             std::this_thread::sleep_for(std::chrono::milliseconds(10));

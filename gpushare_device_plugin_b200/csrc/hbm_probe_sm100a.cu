@@ -740,11 +740,11 @@ int resident_ctas(K kernel, uint32_t smem, int threads) {
 
 typedef void (*probe_fn)(const gsb_kernel_args);
 
-// experiment knob GSB_DYN_FILL=1: FILL under GSB_VARIANT_BULKD uses the dynamic scheduler too
+// knob GSB_DYN_FILL=0: FILL under GSB_VARIANT_BULKD falls back to the static kernel (32 KiB x 6)
 bool dyn_fill() {
   static const bool f = [] {
     const char *e = getenv("GSB_DYN_FILL");
-    return e && atoi(e) != 0;
+    return !e || atoi(e) != 0;
   }();
   return f;
 }
@@ -839,7 +839,7 @@ probe_fn pick(uint32_t op, uint32_t variant, uint32_t *smem, uint32_t *threads) 
         *smem = 8 * kThreads * 16 * 6;
         return probe_bulk<GSB_OP_FILL, 8, 6>;
       }
-      switch (bulk_cfg() >= 0 ? bulk_cfg() : (op == GSB_OP_FILL ? 5 : 1)) {
+      switch (bulk_cfg() >= 0 ? bulk_cfg() : 1) {  // 32 KiB x 3, 2 CTAs/SM for all three ops
 #define GSB_BULKD_CASE(ID, U, S)                                                             \
   case ID:                                                                                   \
     *smem = U * kThreads * 16 * S;                                                           \
@@ -887,9 +887,10 @@ uint32_t gsb_kernel_max_grid(int sm_count) { return (uint32_t)(sm_count * kMaxCt
 
 int gsb_kernel_geometry(uint32_t op, uint32_t variant, uint32_t grid_request, int sm_count,
                         gsb_launch_geom *geom) {
-  // shipped choice per op (profiles/sweep_r01_dynamic_scheduler.json): the refill op wants the dynamic tile
-  // scheduler (1.07 vs 0.95 of the copy peak on the full walk), the single-direction ops the static one
-  if (variant == GSB_VARIANT_AUTO) variant = op == GSB_OP_VERIFY_REFILL ? GSB_VARIANT_BULKD : GSB_VARIANT_BULK;
+  // shipped choice per op (profiles/sweep_r01_dynamic_scheduler{,2}.json): the writing ops want the dynamic
+  // tile scheduler (refill 1.07 vs 0.95, fill 1.07 vs 1.02 of the copy peak on the full arena); VERIFY is as
+  // fast or faster on the static one
+  if (variant == GSB_VARIANT_AUTO) variant = op == GSB_OP_VERIFY ? GSB_VARIANT_BULK : GSB_VARIANT_BULKD;
   uint32_t smem = 0, threads = 0;
   probe_fn fn = pick(op, variant, &smem, &threads);
   if (!fn) return (int)cudaErrorInvalidValue;

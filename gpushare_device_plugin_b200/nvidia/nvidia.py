@@ -10,10 +10,10 @@ from __future__ import annotations
 import logging
 import threading
 from dataclasses import dataclass
-from typing import Callable, Dict, List, Tuple
+from typing import Callable, Dict, List, Optional, Tuple
 
 from .. import device
-from .._abi import GSB_EVENT_PROBE, GSB_EVENT_XID, GsbError, lib
+from .._abi import GSB_EVENT_PROBE, GSB_EVENT_XID, GSB_PROBE_RECOVERED, GsbError, lib
 from . import const
 
 log = logging.getLogger("gpushare.nvidia")
@@ -87,11 +87,13 @@ def deviceExists(devs: List[Device], id_: str) -> bool:  # nvidia.go:91-98
 
 
 def watchXIDs(stop: threading.Event, devs: List[Device], xids: Callable[[Device], None],
-              probe_period_ms: int = 0, window_bytes: int = device.GiB) -> None:
+              probe_period_ms: int = 0, window_bytes: int = device.GiB,
+              recovered: Optional[Callable[[Device], None]] = None, recovery_cycles: int = 0) -> None:
     """nvidia.go:100-152 with the event source replaced: gsb_health_wait delivers both XID critical
     errors (same NVML event type, registered once per GPU) and verdicts of the active HBM probe.
     The loop shape, the 5 s wait, the XID 31/43/45 filter, "empty UUID = every device" and "every
     fake device of that UUID" are the reference's."""
+    lib.gsb_health_set_recovery(recovery_cycles if recovered is not None else 0)
     device.health_start(probe_period_ms, window_bytes)
     try:
         while not stop.is_set():
@@ -103,6 +105,13 @@ def watchXIDs(stop: threading.Event, devs: List[Device], xids: Callable[[Device]
             if e.etype == GSB_EVENT_XID and lib.gsb_xid_is_benign(e.edata):  # nvidia.go:134-136
                 continue
             uuid = e.uuid.decode()
+            if e.etype == GSB_EVENT_PROBE and e.edata == GSB_PROBE_RECOVERED:
+                # not in the reference (server.go:180 FIXME): only when --health-recovery-cycles > 0
+                if recovered is not None and recovery_cycles > 0:
+                    for d in devs:
+                        if extractRealDeviceID(d.ID) == uuid:
+                            recovered(d)
+                continue
             if len(uuid) == 0:  # nvidia.go:138-144: all devices are unhealthy
                 for d in devs:
                     xids(d)

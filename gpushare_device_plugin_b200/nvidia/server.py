@@ -34,7 +34,8 @@ class NvidiaDevicePlugin:
     def __init__(self, mps: bool, healthCheck: bool, queryKubelet: bool, client, socket: str = const.serverSock,
                  coalesce_health: bool = True, probe_period_ms: int = 1000, window_bytes: int = device.GiB,
                  max_workers: int = 16, pod_cache_ttl: float = 1.0, inventory=None,
-                 probe_arena_bytes: int = 4 * device.GiB, startup_full_walk: bool = False):
+                 probe_arena_bytes: int = 4 * device.GiB, startup_full_walk: bool = False,
+                 health_recovery_cycles: int = 0):
         # `inventory` = (devs, devNameMap) injects a synthetic node (tests, Allocate benchmark)
         self.devs, self.devNameMap = inventory if inventory is not None else nvidia.getDevices()  # server.go:39
         devList = list(self.devNameMap)
@@ -49,6 +50,7 @@ class NvidiaDevicePlugin:
         self.coalesce_health = coalesce_health
         self.probe_period_ms, self.window_bytes = probe_period_ms, window_bytes
         self.probe_arena_bytes, self.startup_full_walk = probe_arena_bytes, startup_full_walk
+        self.health_recovery_cycles = health_recovery_cycles
         self.max_workers = max_workers
         self.stop = threading.Event()
         self.lock = threading.RLock()  # sync.RWMutex of server.go:34; Allocate takes it exclusively
@@ -96,19 +98,20 @@ class NvidiaDevicePlugin:
                     self._cv.wait(0.25)
                 if self.stop.is_set() or not context.is_active():
                     return
-                if self.coalesce_health:
-                    for i in self._pending[cursor:]:
-                        self._bits[i >> 3] |= 1 << (i & 7)
-                        self.devs[i].Health = const.Unhealthy
-                    cursor = len(self._pending)
-                    frames = [self._list_bytes()]
-                else:
-                    frames = []
-                    for i in self._pending[cursor:]:
-                        self._bits[i >> 3] |= 1 << (i & 7)  # d.Health = Unhealthy; never recovers (:180)
-                        self.devs[i].Health = const.Unhealthy
+                frames = []
+                for e in self._pending[cursor:]:
+                    if e >= 0:  # d.Health = Unhealthy (server.go:181)
+                        self._bits[e >> 3] |= 1 << (e & 7)
+                        self.devs[e].Health = const.Unhealthy
+                    else:       # optional recovery (not in the reference): ~e is the device index
+                        i = ~e
+                        self._bits[i >> 3] &= ~(1 << (i & 7)) & 0xFF
+                        self.devs[i].Health = const.Healthy
+                    if not self.coalesce_health:
                         frames.append(self._list_bytes())
-                    cursor = len(self._pending)
+                cursor = len(self._pending)
+                if self.coalesce_health:
+                    frames = [self._list_bytes()]
             for f in frames:
                 yield f
 
@@ -142,11 +145,17 @@ class NvidiaDevicePlugin:
             except GsbError as e:
                 log.warning("no probe arena on %s: %s", uuid, e)
 
+    def recovered(self, dev: nvidia.Device) -> None:
+        with self._cv:
+            self._pending.append(~self._index[dev.ID])
+            self._cv.notify_all()
+
     def healthcheck(self) -> None:
         if self.healthCheck:
             if self.probe_period_ms > 0:
                 self.setup_probe_arenas()
-            nvidia.watchXIDs(self.stop, self.devs, self.unhealthy, self.probe_period_ms, self.window_bytes)
+            nvidia.watchXIDs(self.stop, self.devs, self.unhealthy, self.probe_period_ms, self.window_bytes,
+                             self.recovered, self.health_recovery_cycles)
         else:
             self.stop.wait()
 

@@ -216,7 +216,7 @@ enum {
   GSB_EVENT_XID = 8,   /* = nvmlEventTypeXidCriticalError (nvml.h:1082); edata = XID */
   GSB_EVENT_PROBE = 0x100 /* active probe verdict; edata = GSB_PROBE_FAULT_* */
 };
-enum { GSB_PROBE_FAULT_MISMATCH = 1, GSB_PROBE_FAULT_LAUNCH = 2 };
+enum { GSB_PROBE_FAULT_MISMATCH = 1, GSB_PROBE_FAULT_LAUNCH = 2, GSB_PROBE_RECOVERED = 3 };
 
 typedef struct gsb_event {
   char uuid[GSB_UUID_BUFFER_SIZE]; /* empty => applies to all devices (nvidia.go:138-144) */
@@ -231,6 +231,10 @@ int gsb_health_start(uint32_t probe_period_ms, uint64_t window_bytes);
 int gsb_health_stop(void);
 /* ≙ nvml.WaitForEvent(set, timeout) (bindings.go:134-146): GSB_OK + event, or GSB_ERR_TIMEOUT. */
 int gsb_health_wait(uint32_t timeout_ms, gsb_event *ev);
+/* SURVEY.md §8(f) rank 1, optional: after `clean_cycles` consecutive clean probe cycles a GPU that a PROBE
+ * verdict had marked unhealthy is reported again with edata = GSB_PROBE_RECOVERED. 0 (default) keeps the
+ * reference's behaviour: Unhealthy is sticky (server.go:180 FIXME). XID faults never recover. */
+int gsb_health_set_recovery(uint32_t clean_cycles);
 /* test hook: enqueue an event as if the driver had delivered it */
 int gsb_health_inject(const gsb_event *ev);
 /* nvidia.go:134: XIDs 31, 43, 45 are application errors and do not mark the GPU unhealthy. Pure. */

@@ -146,3 +146,26 @@ def test_node_cycle_all_devices_in_one_process(gsb):
         gsb.arena_destroy(i)
     gsb.shutdown()
     gsb.init()
+
+
+def test_prober_reports_a_fault_and_optionally_a_recovery(gsb):
+    """The daemon's prober thread on a real GPU: a corrupted word in its window raises a PROBE event; with
+    recovery enabled, K clean cycles later (the refill repaired the word) a RECOVERED event follows."""
+    from gpushare_device_plugin_b200._abi import lib
+    gsb.arena_create(0, max_bytes=2 * GiB)
+    lib.gsb_health_set_recovery(5)
+    gsb.health_start(probe_period_ms=5, window_bytes=GiB)
+    try:
+        assert gsb.health_wait(300) is None  # clean windows: silence
+        gsb.arena_write(0, 4096, b"\x5a" * 16)
+        gsb.arena_write(0, GiB + 4096, b"\x5a" * 16)  # whichever window comes next
+        ev = gsb.health_wait(5000)
+        assert ev is not None and ev.etype == 0x100 and ev.edata == 1 and ev.uuid.decode() == gsb.device_info(0).uuid
+        ev2 = gsb.health_wait(5000)
+        assert ev2 is not None and (ev2.etype, ev2.edata) == (0x100, 3)
+    finally:
+        gsb.health_stop()
+        lib.gsb_health_set_recovery(0)
+        gsb.arena_destroy(0)
+        gsb.shutdown()
+        gsb.init()

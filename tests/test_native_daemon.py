@@ -295,3 +295,25 @@ def test_chunked_lists_and_awkward_json(tmp_path):
     finally:
         d.close()
         kube.close()
+
+
+def test_native_optional_recovery(world):
+    d = world.start()
+    ch = d.channel()
+    it = Frames(d.kubelet.list_and_watch(ch))
+    first = next_frame(it)
+    d.inject(ch, fakes.UUIDS[1], 0x100, 1)
+    bad = next_frame(it)
+    d.inject(ch, fakes.UUIDS[1], 0x100, 3)
+    assert next_frame(it, 0.8) == "timeout"  # default: sticky like the reference
+    ch.close()
+    d.close()
+    d2 = world.start("--health-recovery-cycles", "3")
+    ch = d2.channel()
+    it = Frames(d2.kubelet.list_and_watch(ch))
+    assert next_frame(it) == first
+    d2.inject(ch, fakes.UUIDS[1], 0x100, 1)
+    assert next_frame(it) == bad
+    d2.inject(ch, fakes.UUIDS[1], 0x100, 3)
+    assert next_frame(it) == first
+    ch.close()

@@ -303,3 +303,43 @@ def test_concurrent_allocates_never_share_a_pod(world):
     assert sorted(int(r["ALIYUN_COM_GPU_MEM_IDX"]) for r in results) == sorted(i // 8 for i in range(64))
     patched = [r[1] for r in world.kube.requests if r[0] == "PATCH" and "/pods/" in r[1]]
     assert len(patched) == 64 and len(set(patched)) == 64  # every pod claimed exactly once
+
+
+def test_optional_recovery_is_off_by_default_and_flag_gated(world):
+    """server.go:180 FIXME: the reference never leaves Unhealthy. Default: a RECOVERED probe event changes
+    nothing; with health_recovery_cycles > 0 the GPU's fake devices flip back — but only after a PROBE
+    fault, never after an XID."""
+    p = world.make()
+    p.Serve(world.kubelet.socket)
+    ch = world.kubelet.channel("aliyungpushare.sock")
+    it = Frames(world.kubelet.list_and_watch(ch))
+    next_frame(it)
+    device.health_inject(fakes.UUIDS[1], 0x100, 1)
+    bad = next_frame(it)
+    while True:
+        f = next_frame(it, 1)
+        if f == "timeout":
+            break
+        bad = f
+    assert {wo.extractRealDeviceID(i) for i, h in wo.unmarshal_ListAndWatchResponse(bad) if h == wo.Unhealthy} == {fakes.UUIDS[1]}
+    device.health_inject(fakes.UUIDS[1], 0x100, 3)  # GSB_PROBE_RECOVERED
+    assert next_frame(it, 0.8) == "timeout"          # sticky, like the reference
+    ch.close()
+    p.Stop()
+    p2 = world.make(health_recovery_cycles=3)
+    p2.Serve(world.kubelet.socket)
+    ch = world.kubelet.channel("aliyungpushare.sock")
+    it = Frames(world.kubelet.list_and_watch(ch))
+    first = next_frame(it)
+    def settle(want):  # per-device events may straddle a wake-up of the stream: the end state is what counts
+        for _ in range(200):
+            f = next_frame(it)
+            if f == want:
+                return True
+            assert f != "timeout"
+        return False
+    device.health_inject(fakes.UUIDS[1], 0x100, 1)
+    assert settle(bad)
+    device.health_inject(fakes.UUIDS[1], 0x100, 3)
+    assert settle(first)  # all Healthy again, byte-identical to the initial list
+    ch.close()
