@@ -37,6 +37,7 @@
 #include <functional>
 #include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -157,6 +158,10 @@ struct Device {
 };
 
 struct Global {
+  // every device-touching entry point holds this shared; gsb_init/gsb_shutdown take it exclusively, so a
+  // shutdown waits for calls still running on other threads (e.g. a start-up walk) instead of freeing
+  // devices under them
+  std::shared_mutex api_mu;
   std::mutex mu;
   bool inited = false;
   DriverApi cu;
@@ -694,6 +699,7 @@ int gsb_last_error(char *buf, size_t cap) {
 }
 
 int gsb_init(void) {
+  std::unique_lock<std::shared_mutex> api_lk(G.api_mu);
   std::lock_guard<std::mutex> lk(G.mu);
   if (G.inited) return GSB_OK;
   int rc = load_libraries();
@@ -753,6 +759,7 @@ int gsb_init(void) {
 
 int gsb_shutdown(void) {
   gsb_health_stop();
+  std::unique_lock<std::shared_mutex> api_lk(G.api_mu);  // waits for in-flight calls of other threads
   std::lock_guard<std::mutex> lk(G.mu);
   if (!G.inited) return GSB_OK;
   for (auto &d : G.devs) {
@@ -782,6 +789,7 @@ int gsb_shutdown(void) {
 }
 
 int gsb_device_count(uint32_t *n) {
+  std::shared_lock<std::shared_mutex> api_lk(G.api_mu);
   if (!n) return GSB_ERR_INVALID_ARGUMENT;
   if (!G.inited) {
     set_error("gsb_init has not succeeded");
@@ -794,6 +802,7 @@ int gsb_device_count(uint32_t *n) {
 }
 
 int gsb_device_info_get(uint32_t idx, gsb_device_info *out) {
+  std::shared_lock<std::shared_mutex> api_lk(G.api_mu);
   if (!out) return GSB_ERR_INVALID_ARGUMENT;
   Device *d = device_at(idx);
   if (!d) return G.inited ? GSB_ERR_NO_DEVICE : GSB_ERR_NOT_INITIALIZED;
@@ -803,6 +812,7 @@ int gsb_device_info_get(uint32_t idx, gsb_device_info *out) {
 }
 
 int gsb_arena_create(uint32_t idx, uint64_t max_bytes, uint64_t keep_free_bytes, uint64_t *arena_bytes) {
+  std::shared_lock<std::shared_mutex> api_lk(G.api_mu);
   Device *d = device_at(idx);
   if (!d) return G.inited ? GSB_ERR_NO_DEVICE : GSB_ERR_NOT_INITIALIZED;
   std::lock_guard<std::mutex> lk(d->mu);
@@ -810,6 +820,7 @@ int gsb_arena_create(uint32_t idx, uint64_t max_bytes, uint64_t keep_free_bytes,
 }
 
 int gsb_arena_destroy(uint32_t idx) {
+  std::shared_lock<std::shared_mutex> api_lk(G.api_mu);
   Device *d = device_at(idx);
   if (!d) return G.inited ? GSB_ERR_NO_DEVICE : GSB_ERR_NOT_INITIALIZED;
   std::lock_guard<std::mutex> lk(d->mu);
@@ -817,6 +828,7 @@ int gsb_arena_destroy(uint32_t idx) {
 }
 
 int gsb_arena_bytes(uint32_t idx, uint64_t *arena_bytes) {
+  std::shared_lock<std::shared_mutex> api_lk(G.api_mu);
   Device *d = device_at(idx);
   if (!d || !arena_bytes) return G.inited ? GSB_ERR_NO_DEVICE : GSB_ERR_NOT_INITIALIZED;
   std::lock_guard<std::mutex> lk(d->mu);
@@ -825,6 +837,7 @@ int gsb_arena_bytes(uint32_t idx, uint64_t *arena_bytes) {
 }
 
 int gsb_probe(uint32_t idx, const gsb_probe_cfg *cfg, gsb_probe_result *out) {
+  std::shared_lock<std::shared_mutex> api_lk(G.api_mu);
   if (!cfg || !out) return GSB_ERR_INVALID_ARGUMENT;
   Device *d = device_at(idx);
   if (!d) {
@@ -900,6 +913,7 @@ int64_t gsb_cycle_all(uint32_t n, const uint32_t *idxs, uint64_t cycle_no, uint6
 }
 
 int gsb_arena_read(uint32_t idx, uint64_t offset, void *dst, uint64_t bytes) {
+  std::shared_lock<std::shared_mutex> api_lk(G.api_mu);
   Device *d = device_at(idx);
   if (!d || !dst) return GSB_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> lk(d->mu);
@@ -911,6 +925,7 @@ int gsb_arena_read(uint32_t idx, uint64_t offset, void *dst, uint64_t bytes) {
 }
 
 int gsb_arena_write(uint32_t idx, uint64_t offset, const void *src, uint64_t bytes) {
+  std::shared_lock<std::shared_mutex> api_lk(G.api_mu);
   Device *d = device_at(idx);
   if (!d || !src) return GSB_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> lk(d->mu);
@@ -923,6 +938,7 @@ int gsb_arena_write(uint32_t idx, uint64_t offset, const void *src, uint64_t byt
 
 int gsb_cycle(uint32_t idx, uint64_t cycle_no, uint64_t window_bytes, int unit_gib, uint32_t variant,
               uint8_t *lw_buf, size_t lw_cap, gsb_cycle_result *out) {
+  std::shared_lock<std::shared_mutex> api_lk(G.api_mu);
   if (!out) return GSB_ERR_INVALID_ARGUMENT;
   memset(out, 0, sizeof *out);
   Device *d = device_at(idx);
@@ -1030,6 +1046,7 @@ int gsb_health_wait(uint32_t timeout_ms, gsb_event *ev) {
 }
 
 int gsb_health_start(uint32_t probe_period_ms, uint64_t window_bytes) {
+  std::shared_lock<std::shared_mutex> api_lk(G.api_mu);
   if (!G.inited) return GSB_ERR_NOT_INITIALIZED;
   std::lock_guard<std::mutex> lk(G.mu);
   if (G.health_running) return GSB_OK;

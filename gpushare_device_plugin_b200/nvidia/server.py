@@ -197,6 +197,10 @@ class NvidiaDevicePlugin:
             self._cv.notify_all()
         self.server.stop(0)
         self.server = None
+        # the health thread may be in the middle of a start-up walk: let it finish before anyone shuts the
+        # device layer down or a new plugin starts its own health thread
+        if self._health_thread is not None and self._health_thread is not threading.current_thread():
+            self._health_thread.join(timeout=60)
         self.cleanup()
 
     def Register(self, kubeletEndpoint: str, resourceName: str) -> None:  # server.go:150-169
