@@ -206,3 +206,68 @@ def test_raw_frames_continuation_padding_priority(server):
                 done = True
     assert len(got) == 5 + 100000 and got[5:] == b"a" * 100000
     s.close()
+
+
+# ---- JSON reader of the native daemon vs Python's json ---------------------------------------------------
+
+import json as _json  # noqa: E402
+
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+_json_values = st.recursive(
+    st.none() | st.booleans() | st.integers(-2**53, 2**53) | st.text(max_size=20) |
+    st.floats(allow_nan=False, allow_infinity=False, width=32),
+    lambda kids: st.lists(kids, max_size=4) | st.dictionaries(st.text(max_size=8), kids, max_size=4), max_leaves=20)
+
+
+def native_json(text: bytes):
+    out = subprocess.run([BIN, "json"], input=text, capture_output=True, timeout=10)
+    return out.returncode, out.stdout
+
+
+@settings(max_examples=150, deadline=None)
+@given(doc=_json_values, ascii_only=st.booleans(), pretty=st.booleans())
+def test_json_reader_agrees_with_python(doc, ascii_only, pretty):
+    try:
+        text = _json.dumps(doc, ensure_ascii=ascii_only, indent=2 if pretty else None).encode("utf-8")
+    except UnicodeEncodeError:  # lone surrogates cannot be written as UTF-8
+        return
+    rc, out = native_json(text)
+    assert rc == 0
+    assert _json.loads(out.decode("utf-8", errors="surrogatepass")) == _json.loads(text)
+
+
+@pytest.mark.parametrize("bad", [b"", b"{", b'{"a":}', b"[1,]", b'{"a" 1}', b'"unterminated', b"tru", b'{"a":1}x',
+                                 b'"\\u12"', b'"\\q"', b"[" * 500 + b"]" * 500])
+def test_json_reader_rejects_malformed(bad):
+    rc, out = native_json(bad)
+    assert rc == 1 and out.strip() == b"INVALID"
+
+
+def test_server_survives_garbage_and_truncated_frames(server):
+    """Protocol violations close that connection only; the server keeps serving others."""
+    import random
+    import socket as _s
+    ch, sock_path, proc = server
+    rng = random.Random(7)
+    preface = b"PRI * HTTP/2.0\r\n\r\nSM\r\n\r\n"
+    blobs = [b"GET / HTTP/1.1\r\n\r\n", preface[:10], preface + b"\xff" * 64, preface + frame(1, 0x4, 1, b"\x80"),
+             preface + frame(1, 0x4, 2, b"\x82"), preface + frame(0, 0, 1, b"data before headers"),
+             preface + frame(9, 0x4, 1, b"orphan continuation"), preface + frame(4, 0, 0, b"\x00\x04\x00"),
+             preface + frame(1, 0x8 | 0x4, 1, b"\xff\x82"), preface + frame(1, 0x4, 1, b"\x3f\xff\xff\xff\xff\xff\xff\xff\xff\xff\x7f"),
+             preface + (200000).to_bytes(3, "big") + b"\x00\x00\x00\x00\x00\x01" + b"x" * 1000]
+    blobs += [preface + bytes(rng.randrange(256) for _ in range(rng.randrange(1, 400))) for _ in range(40)]
+    for b in blobs:
+        s = _s.socket(_s.AF_UNIX, _s.SOCK_STREAM)
+        s.settimeout(2)
+        s.connect(sock_path)
+        try:
+            s.sendall(b)
+            s.shutdown(_s.SHUT_WR)
+            while s.recv(65536):
+                pass
+        except OSError:
+            pass
+        s.close()
+        assert proc.poll() is None
+    assert ch.unary_unary("/test.Echo/Unary")(b"still alive", timeout=5) == b"still alive"
