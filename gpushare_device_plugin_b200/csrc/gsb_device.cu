@@ -155,6 +155,7 @@ struct Device {
   std::condition_variable wcv;
   std::function<void()> job;
   bool job_ready = false, job_done = false, worker_quit = false;
+  std::atomic<bool> job_flag{false}, done_flag{false}, quit_flag{false};  // lock-free mirrors for the spin phase
 };
 
 struct Global {
@@ -616,32 +617,47 @@ int query_info(Device *d, gsb_device_info *out) {
   return GSB_OK;
 }
 
-// run `fn` on the device's own persistent thread (created on first use)
+// run `fn` on the device's own persistent thread (created on first use). Hand-off is spin-then-block in
+// both directions: a node cycle every few hundred microseconds never pays a futex wake-up (tens of us per
+// hop, a tenth of a 1 GiB-window cycle), an idle daemon's workers park after ~200 us.
+constexpr uint64_t kSpinNs = 200000;
+
 void worker_submit(Device *d, std::function<void()> fn) {
   std::unique_lock<std::mutex> lk(d->wmu);
   if (!d->worker.joinable()) {
     d->worker = std::thread([d] {
-      std::unique_lock<std::mutex> wl(d->wmu);
       for (;;) {
+        // spin for a job first
+        const uint64_t until = now_ns() + kSpinNs;
+        while (!d->job_flag.load(std::memory_order_acquire) && !d->quit_flag.load(std::memory_order_acquire) &&
+               now_ns() < until)
+          __builtin_ia32_pause();
+        std::unique_lock<std::mutex> wl(d->wmu);
         d->wcv.wait(wl, [d] { return d->job_ready || d->worker_quit; });
         if (d->worker_quit) return;
         d->job_ready = false;
+        d->job_flag.store(false, std::memory_order_relaxed);
         std::function<void()> f = std::move(d->job);
         wl.unlock();
         f();
         wl.lock();
         d->job_done = true;
+        d->done_flag.store(true, std::memory_order_release);
         d->wcv.notify_all();
       }
     });
   }
   d->job = std::move(fn);
   d->job_done = false;
+  d->done_flag.store(false, std::memory_order_relaxed);
   d->job_ready = true;
+  d->job_flag.store(true, std::memory_order_release);
   d->wcv.notify_all();
 }
 
 void worker_wait(Device *d) {
+  const uint64_t until = now_ns() + 5 * kSpinNs;
+  while (!d->done_flag.load(std::memory_order_acquire) && now_ns() < until) __builtin_ia32_pause();
   std::unique_lock<std::mutex> lk(d->wmu);
   d->wcv.wait(lk, [d] { return d->job_done; });
 }
@@ -650,6 +666,7 @@ void worker_stop(Device *d) {
   {
     std::lock_guard<std::mutex> lk(d->wmu);
     d->worker_quit = true;
+    d->quit_flag.store(true, std::memory_order_release);
   }
   d->wcv.notify_all();
   if (d->worker.joinable()) d->worker.join();
