@@ -620,7 +620,11 @@ int query_info(Device *d, gsb_device_info *out) {
 // run `fn` on the device's own persistent thread (created on first use). Hand-off is spin-then-block in
 // both directions: a node cycle every few hundred microseconds never pays a futex wake-up (tens of us per
 // hop, a tenth of a 1 GiB-window cycle), an idle daemon's workers park after ~200 us.
-constexpr uint64_t kSpinNs = 200000;
+// knob GSB_WORKER_SPIN_US (default 200; 0 = pure condition-variable hand-off)
+const uint64_t kSpinNs = [] {
+  const char *e = getenv("GSB_WORKER_SPIN_US");
+  return (uint64_t)(e ? atoi(e) : 200) * 1000ull;
+}();
 
 void worker_submit(Device *d, std::function<void()> fn) {
   std::unique_lock<std::mutex> lk(d->wmu);
