@@ -294,7 +294,7 @@ def bench_reference(args) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    if not args.no_allocate:
+    if not args.no_allocate and int(os.environ.get("WORLD_SIZE", 1)) == 1:  # host-only leg: N = 1 runs only
         try:
             line["allocate"] = bench_allocate("reference", args.quick_allocate)
         except Exception as e:  # noqa: BLE001
