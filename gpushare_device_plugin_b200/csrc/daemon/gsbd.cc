@@ -181,31 +181,55 @@ struct Kube {
     if (!f.kube_api_url.empty()) return api.configure(f.kube_api_url, "", "", true, 30, err);
     const char *kc = getenv("KUBECONFIG");
     if (kc && file_exists(kc)) {
-      // first cluster / first user of the kubeconfig: server, token, CA, insecure-skip-tls-verify
+      // first cluster / first user of the kubeconfig: server, token, CA (file or *-data), client cert/key
+      // (file or *-data), insecure-skip-tls-verify — the forms kubeadm / cloud kubeconfigs use
       std::string server, token, ca;
+      http::Client::TlsExtra extra;
       bool insecure = false;
       std::istringstream in(read_file(kc));
       std::string line;
       auto val = [](const std::string &l) {
         size_t c = l.find(':');
         std::string v = l.substr(c + 1);
-        while (!v.empty() && (v.front() == ' ' || v.front() == '"')) v.erase(0, 1);
-        while (!v.empty() && (v.back() == ' ' || v.back() == '"' || v.back() == '\r')) v.pop_back();
+        while (!v.empty() && (v.front() == ' ' || v.front() == '"' || v.front() == '\'')) v.erase(0, 1);
+        while (!v.empty() && (v.back() == ' ' || v.back() == '"' || v.back() == '\'' || v.back() == '\r')) v.pop_back();
         return v;
       };
+      auto b64 = [](const std::string &in) {
+        std::string out;
+        int acc = 0, bits = -8;
+        for (unsigned char c : in) {
+          int d = c >= 'A' && c <= 'Z' ? c - 'A' : c >= 'a' && c <= 'z' ? c - 'a' + 26 : c >= '0' && c <= '9' ? c - '0' + 52
+                  : c == '+' ? 62 : c == '/' ? 63 : -1;
+          if (d < 0) continue;
+          acc = (acc << 6) | d;
+          bits += 6;
+          if (bits >= 0) {
+            out.push_back((char)((acc >> bits) & 0xFF));
+            bits -= 8;
+          }
+        }
+        return out;
+      };
+      auto starts = [](const std::string &t, const char *k) { return t.compare(0, strlen(k), k) == 0; };
       while (std::getline(in, line)) {
         std::string t = line;
         t.erase(0, t.find_first_not_of(" -"));
-        if (t.compare(0, 7, "server:") == 0 && server.empty()) server = val(t);
-        else if (t.compare(0, 6, "token:") == 0 && token.empty()) token = val(t);
-        else if (t.compare(0, 22, "certificate-authority:") == 0 && ca.empty()) ca = val(t);
-        else if (t.compare(0, 25, "insecure-skip-tls-verify:") == 0) insecure = val(t) == "true";
+        if (starts(t, "server:") && server.empty()) server = val(t);
+        else if (starts(t, "token:") && token.empty()) token = val(t);
+        else if (starts(t, "certificate-authority-data:") && extra.ca_pem.empty()) extra.ca_pem = b64(val(t));
+        else if (starts(t, "certificate-authority:") && ca.empty()) ca = val(t);
+        else if (starts(t, "client-certificate-data:") && extra.cert_pem.empty()) extra.cert_pem = b64(val(t));
+        else if (starts(t, "client-key-data:") && extra.key_pem.empty()) extra.key_pem = b64(val(t));
+        else if (starts(t, "client-certificate:") && extra.cert_file.empty()) extra.cert_file = val(t);
+        else if (starts(t, "client-key:") && extra.key_file.empty()) extra.key_file = val(t);
+        else if (starts(t, "insecure-skip-tls-verify:")) insecure = val(t) == "true";
       }
       if (server.empty()) {
         *err = std::string("no cluster server in ") + kc;
         return false;
       }
-      return api.configure(server, token, ca, insecure, 30, err);
+      return api.configure(server, token, ca, insecure, 30, err, &extra);
     }
     const char *h = getenv("KUBERNETES_SERVICE_HOST"), *p = getenv("KUBERNETES_SERVICE_PORT");
     if (!h || !p) {

@@ -8,6 +8,8 @@
 #include <netinet/in.h>
 #include <netinet/tcp.h>
 #include <openssl/err.h>
+#include <openssl/pem.h>
+#include <openssl/x509v3.h>
 #include <openssl/ssl.h>
 #include <string.h>
 #include <sys/socket.h>
@@ -29,7 +31,8 @@ struct Response {
 class Conn {
  public:
   ~Conn() { close(); }
-  bool open(const std::string &host, int port, SSL_CTX *tls, const std::string &sni, int timeout_s, std::string *err) {
+  bool open(const std::string &host, int port, SSL_CTX *tls, const std::string &sni, int timeout_s, std::string *err,
+            bool verify_name = true) {
     addrinfo hints, *res = nullptr;
     memset(&hints, 0, sizeof hints);
     hints.ai_socktype = SOCK_STREAM;
@@ -57,9 +60,19 @@ class Conn {
     if (tls) {
       ssl_ = SSL_new(tls);
       SSL_set_fd(ssl_, fd_);
-      if (!sni.empty()) SSL_set_tlsext_host_name(ssl_, sni.c_str());
+      // the certificate must be FOR the endpoint we dialled: DNS name or (in-cluster: 10.x service IP) IP SAN
+      unsigned char ipbuf[16];
+      const bool is_ip = inet_pton(AF_INET, sni.c_str(), ipbuf) == 1 || inet_pton(AF_INET6, sni.c_str(), ipbuf) == 1;
+      if (!sni.empty() && !is_ip) SSL_set_tlsext_host_name(ssl_, sni.c_str());
+      if (verify_name && !sni.empty()) {
+        X509_VERIFY_PARAM *vp = SSL_get0_param(ssl_);
+        if (is_ip) X509_VERIFY_PARAM_set1_ip_asc(vp, sni.c_str());
+        else X509_VERIFY_PARAM_set1_host(vp, sni.c_str(), 0);
+      }
       if (SSL_connect(ssl_) != 1) {
-        *err = "tls handshake with " + host + " failed";
+        const long vr = SSL_get_verify_result(ssl_);
+        *err = "tls handshake with " + host + " failed" +
+               (vr != X509_V_OK ? std::string(": x509: ") + X509_verify_cert_error_string(vr) : std::string());
         close();
         return false;
       }
@@ -155,10 +168,15 @@ class Conn {
 class Client {
  public:
   // base_url: http://host:port or https://host:port
+  // optional TLS material given as PEM text (kubeconfig *-data fields) or files (client cert for mTLS)
+  struct TlsExtra {
+    std::string ca_pem, cert_pem, key_pem, cert_file, key_file;
+  };
   bool configure(const std::string &base_url, const std::string &token, const std::string &ca_file, bool insecure,
-                 int timeout_s, std::string *err) {
+                 int timeout_s, std::string *err, const TlsExtra *extra = nullptr) {
     token_ = token;
     timeout_s_ = timeout_s;
+    insecure_ = insecure;
     std::string rest;
     if (base_url.compare(0, 8, "https://") == 0) {
       tls_ = true;
@@ -184,13 +202,49 @@ class Client {
         SSL_CTX_set_verify(ctx_, SSL_VERIFY_NONE, nullptr);
       } else {
         SSL_CTX_set_verify(ctx_, SSL_VERIFY_PEER, nullptr);
-        if (!ca_file.empty()) {
+        if (extra && !extra->ca_pem.empty()) {
+          BIO *bio = BIO_new_mem_buf(extra->ca_pem.data(), (int)extra->ca_pem.size());
+          X509 *x = nullptr;
+          int n = 0;
+          while ((x = PEM_read_bio_X509(bio, nullptr, nullptr, nullptr)) != nullptr) {
+            X509_STORE_add_cert(SSL_CTX_get_cert_store(ctx_), x);
+            X509_free(x);
+            n++;
+          }
+          BIO_free(bio);
+          ERR_clear_error();
+          if (n == 0) {
+            *err = "certificate-authority-data holds no PEM certificate";
+            return false;
+          }
+        } else if (!ca_file.empty()) {
           if (SSL_CTX_load_verify_locations(ctx_, ca_file.c_str(), nullptr) != 1) {
             *err = "cannot load CA " + ca_file;
             return false;
           }
         } else {
           SSL_CTX_set_default_verify_paths(ctx_);
+        }
+      }
+      if (extra && (!extra->cert_pem.empty() || !extra->cert_file.empty())) {  // client certificate (mTLS)
+        bool ok = true;
+        if (!extra->cert_pem.empty()) {
+          BIO *cb = BIO_new_mem_buf(extra->cert_pem.data(), (int)extra->cert_pem.size());
+          X509 *x = PEM_read_bio_X509(cb, nullptr, nullptr, nullptr);
+          BIO_free(cb);
+          BIO *kb = BIO_new_mem_buf(extra->key_pem.data(), (int)extra->key_pem.size());
+          EVP_PKEY *k = PEM_read_bio_PrivateKey(kb, nullptr, nullptr, nullptr);
+          BIO_free(kb);
+          ok = x && k && SSL_CTX_use_certificate(ctx_, x) == 1 && SSL_CTX_use_PrivateKey(ctx_, k) == 1;
+          if (x) X509_free(x);
+          if (k) EVP_PKEY_free(k);
+        } else {
+          ok = SSL_CTX_use_certificate_chain_file(ctx_, extra->cert_file.c_str()) == 1 &&
+               SSL_CTX_use_PrivateKey_file(ctx_, extra->key_file.c_str(), SSL_FILETYPE_PEM) == 1;
+        }
+        if (!ok) {
+          *err = "cannot load the client certificate / key";
+          return false;
         }
       }
     }
@@ -212,7 +266,7 @@ class Client {
       const bool pooled = c != nullptr;
       if (!c) {
         c.reset(new Conn());
-        if (!c->open(host_, port_, ctx_, host_, timeout_s_, err)) return false;
+        if (!c->open(host_, port_, ctx_, host_, timeout_s_, err, !insecure_)) return false;
       }
       bool keep = false;
       if (c->write_all(req) && c->read_response(out, &keep)) {
@@ -242,7 +296,7 @@ class Client {
   }
   std::string host_, token_;
   int port_ = 0, timeout_s_ = 30;
-  bool tls_ = false;
+  bool tls_ = false, insecure_ = false;
   SSL_CTX *ctx_ = nullptr;
   std::mutex mu_;
   std::vector<std::unique_ptr<Conn>> idle_;

@@ -28,13 +28,18 @@ class ApiError(Exception):
 
 class Clientset:
     def __init__(self, server: str, token: str = "", ca_file: Optional[str] = None, insecure: bool = False,
-                 cert: Optional[Tuple[str, str]] = None, timeout: float = 30.0):
+                 cert: Optional[Tuple[str, str]] = None, timeout: float = 30.0, ca_data: Optional[str] = None):
         u = urllib.parse.urlparse(server)
         self.scheme, self.host, self.port = u.scheme, u.hostname, u.port or (443 if u.scheme == "https" else 80)
         self.token, self.timeout = token, timeout
         self.ctx = None
         if self.scheme == "https":
-            self.ctx = ssl.create_default_context(cafile=ca_file) if ca_file and not insecure else ssl.create_default_context()
+            if ca_data and not insecure:
+                self.ctx = ssl.create_default_context(cadata=ca_data)
+            elif ca_file and not insecure:
+                self.ctx = ssl.create_default_context(cafile=ca_file)
+            else:
+                self.ctx = ssl.create_default_context()
             if insecure:
                 self.ctx.check_hostname = False
                 self.ctx.verify_mode = ssl.CERT_NONE
@@ -110,9 +115,22 @@ def from_environment() -> Clientset:
             cfg["contexts"][0]["context"]
         cluster = next(c["cluster"] for c in cfg["clusters"] if c["name"] == ctx["cluster"])
         user = next((u["user"] for u in cfg.get("users", []) if u["name"] == ctx.get("user")), {}) or {}
+        import base64
+        import tempfile
         cert = (user["client-certificate"], user["client-key"]) if "client-certificate" in user else None
+        if "client-certificate-data" in user:  # ssl wants files: materialise the embedded PEMs privately
+            files = []
+            for key in ("client-certificate-data", "client-key-data"):
+                f = tempfile.NamedTemporaryFile("wb", suffix=".pem", delete=False)
+                os.chmod(f.name, 0o600)
+                f.write(base64.b64decode(user[key]))
+                f.close()
+                files.append(f.name)
+            cert = (files[0], files[1])
+        ca_data = cluster.get("certificate-authority-data")
         return Clientset(cluster["server"], token=user.get("token", ""), ca_file=cluster.get("certificate-authority"),
-                         insecure=bool(cluster.get("insecure-skip-tls-verify")), cert=cert)
+                         insecure=bool(cluster.get("insecure-skip-tls-verify")), cert=cert,
+                         ca_data=base64.b64decode(ca_data).decode() if ca_data else None)
     host, port = os.environ.get("KUBERNETES_SERVICE_HOST"), os.environ.get("KUBERNETES_SERVICE_PORT")
     if not host or not port:
         raise RuntimeError("unable to load in-cluster configuration, KUBERNETES_SERVICE_HOST and "

@@ -56,8 +56,10 @@ def config4_pods(node: str = "b200-0", n: int = 64, per_gpu: int = 8, mod: bool 
 
 
 class MockKube:
-    def __init__(self, node: dict, pods: List[dict], chunked_lists: bool = False):
+    def __init__(self, node: dict, pods: List[dict], chunked_lists: bool = False, tls=None, client_ca=None):
+        """tls = (certfile, keyfile) serves HTTPS; client_ca = CA file makes a client certificate mandatory."""
         self.chunked_lists = chunked_lists  # answer pod LISTs with Transfer-Encoding: chunked, like the apiserver
+        self.auth_headers: List[Optional[str]] = []
         self.lock = threading.Lock()
         self.nodes: Dict[str, dict] = {node["metadata"]["name"]: node}
         self.pods: Dict[tuple, dict] = {(p["metadata"]["namespace"], p["metadata"]["name"]): p for p in pods}
@@ -96,6 +98,7 @@ class MockKube:
                                   "code": code})
 
             def do_GET(self):
+                mock.auth_headers.append(self.headers.get("Authorization"))
                 u = urllib.parse.urlparse(self.path)
                 parts = [p for p in u.path.split("/") if p]
                 with mock.lock:
@@ -159,9 +162,19 @@ class MockKube:
             request_queue_size = 1024  # default 5: a burst of new client connections would hit SYN retransmits (1 s)
 
         self.httpd = Server(("127.0.0.1", 0), H)
+        self.scheme = "http"
+        if tls is not None:
+            import ssl
+            ctx = ssl.SSLContext(ssl.PROTOCOL_TLS_SERVER)
+            ctx.load_cert_chain(*tls)
+            if client_ca is not None:
+                ctx.verify_mode = ssl.CERT_REQUIRED
+                ctx.load_verify_locations(client_ca)
+            self.httpd.socket = ctx.wrap_socket(self.httpd.socket, server_side=True)
+            self.scheme = "https"
         self.httpd.daemon_threads = True
         self.port = self.httpd.server_address[1]
-        self.url = f"http://127.0.0.1:{self.port}"
+        self.url = f"{self.scheme}://127.0.0.1:{self.port}"
         self.thread = threading.Thread(target=self.httpd.serve_forever, name="mock-kube", daemon=True)
         self.thread.start()
 

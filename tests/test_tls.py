@@ -1,0 +1,135 @@
+"""The deployment path only CPU tests can cover: HTTPS to the apiserver with CA verification, name/IP
+check, bearer token, client certificates and the kubeconfig forms clusters really use (file paths and
+base64 *-data fields) — for the native daemon's OpenSSL client and for the Python kube client."""
+import base64
+import os
+import subprocess
+
+import pytest
+
+from gpushare_device_plugin_b200.nvidia import kubeclient
+from gpushare_device_plugin_b200.testing.fake_kubelet import FakeKubelet
+from gpushare_device_plugin_b200.testing.mock_kube import MockKube, config4_pods, make_node
+from oracle import wire_oracle as wo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GSBD = os.path.join(ROOT, "gpushare_device_plugin_b200", "gsbd")
+NODE = "b200-0"
+
+
+def sh(*a, cwd):
+    subprocess.run(a, cwd=cwd, check=True, capture_output=True)
+
+
+@pytest.fixture(scope="module")
+def pki(tmp_path_factory):
+    d = tmp_path_factory.mktemp("pki")
+    sh("openssl", "req", "-x509", "-newkey", "rsa:2048", "-nodes", "-keyout", "ca.key", "-out", "ca.crt", "-subj", "/CN=test-ca",
+       "-days", "2", cwd=d)
+    for name, san in (("server", "IP:127.0.0.1"), ("wrongname", "DNS:not-this-host"), ("client", "DNS:client")):
+        sh("openssl", "req", "-newkey", "rsa:2048", "-nodes", "-keyout", f"{name}.key", "-out", f"{name}.csr", "-subj", f"/CN={name}", cwd=d)
+        (d / f"{name}.ext").write_text(f"subjectAltName={san}\n")
+        sh("openssl", "x509", "-req", "-in", f"{name}.csr", "-CA", "ca.crt", "-CAkey", "ca.key", "-CAcreateserial", "-out",
+           f"{name}.crt", "-days", "2", "-extfile", f"{name}.ext", cwd=d)
+    sh("openssl", "req", "-x509", "-newkey", "rsa:2048", "-nodes", "-keyout", "other.key", "-out", "other-ca.crt", "-subj",
+       "/CN=other-ca", "-days", "2", cwd=d)
+    return d
+
+
+def kubeconfig(path, server, cluster_lines, user_lines):
+    path.write_text("apiVersion: v1\nkind: Config\ncurrent-context: c\nclusters:\n- name: k\n  cluster:\n"
+                    f"    server: {server}\n" + "".join(f"    {l}\n" for l in cluster_lines) +
+                    "contexts:\n- name: c\n  context:\n    cluster: k\n    user: u\nusers:\n- name: u\n  user:\n" +
+                    "".join(f"    {l}\n" for l in user_lines))
+    return str(path)
+
+
+def run_gsbd(tmp_path, kc, expect_register=True):
+    kubelet = FakeKubelet(str(tmp_path))
+    env = dict(os.environ, NODE_NAME=NODE, KUBECONFIG=kc, GPUSHARE_PLUGIN_DIR=str(tmp_path) + "/", GPUSHARE_RETRY_SLEEP_MS="1")
+    log = open(tmp_path / "gsbd.log", "w")
+    p = subprocess.Popen([GSBD, "--v=5", "--fake-inventory", "8"], env=env, stderr=log, stdout=log)
+    try:
+        if expect_register:
+            kubelet.register_requests.get(timeout=20)
+            ch = kubelet.channel("aliyungpushare.sock")
+            envs = wo.unmarshal_AllocateResponse(kubelet.allocate(ch, wo.marshal_AllocateRequest([["a", "b", "c", "d"]])))
+            ch.close()
+            return envs
+        return p.wait(timeout=20), open(tmp_path / "gsbd.log").read()
+    finally:
+        if p.poll() is None:
+            p.terminate()
+            p.wait(timeout=10)
+        log.close()
+        kubelet.stop()
+
+
+def b64file(p):
+    return base64.b64encode(open(p, "rb").read()).decode()
+
+
+@pytest.mark.skipif(not os.access(GSBD, os.X_OK), reason="gsbd not built")
+class TestNativeDaemonTls:
+    def test_ca_file_and_token(self, pki, tmp_path):
+        kube = MockKube(make_node(NODE), config4_pods(NODE), tls=(str(pki / "server.crt"), str(pki / "server.key")))
+        try:
+            kc = kubeconfig(tmp_path / "kc", kube.url, [f"certificate-authority: {pki / 'ca.crt'}"], ["token: s3cr3t-token"])
+            envs = run_gsbd(tmp_path, kc)
+            assert envs[0]["ALIYUN_COM_GPU_MEM_IDX"] == "0"
+            assert "Bearer s3cr3t-token" in kube.auth_headers
+            assert kube.pod("pod-00")["metadata"]["annotations"]["ALIYUN_COM_GPU_MEM_ASSIGNED"] == "true"
+        finally:
+            kube.close()
+
+    def test_embedded_data_fields_and_client_certificate(self, pki, tmp_path):
+        kube = MockKube(make_node(NODE), config4_pods(NODE), tls=(str(pki / "server.crt"), str(pki / "server.key")),
+                        client_ca=str(pki / "ca.crt"))
+        try:
+            kc = kubeconfig(tmp_path / "kc", kube.url, [f"certificate-authority-data: {b64file(pki / 'ca.crt')}"],
+                            [f"client-certificate-data: {b64file(pki / 'client.crt')}",
+                             f"client-key-data: {b64file(pki / 'client.key')}"])
+            assert run_gsbd(tmp_path, kc)[0]["ALIYUN_COM_GPU_MEM_IDX"] == "0"
+            # same server, no client certificate: the handshake is refused, the daemon exits 1 (gpumanager.go:73)
+            kc2 = kubeconfig(tmp_path / "kc2", kube.url, [f"certificate-authority: {pki / 'ca.crt'}"], ["token: t"])
+            rc, log = run_gsbd(tmp_path, kc2, expect_register=False)
+            assert rc == 1 and "Failed to get device plugin" in log
+        finally:
+            kube.close()
+
+    def test_wrong_ca_and_wrong_name_are_refused_unless_insecure(self, pki, tmp_path):
+        kube = MockKube(make_node(NODE), config4_pods(NODE), tls=(str(pki / "server.crt"), str(pki / "server.key")))
+        try:
+            kc = kubeconfig(tmp_path / "kc", kube.url, [f"certificate-authority: {pki / 'other-ca.crt'}"], ["token: t"])
+            rc, log = run_gsbd(tmp_path, kc, expect_register=False)
+            assert rc == 1 and "x509" in log
+            kc = kubeconfig(tmp_path / "kc3", kube.url, ["insecure-skip-tls-verify: true"], ["token: t"])
+            assert run_gsbd(tmp_path, kc)[0]["ALIYUN_COM_GPU_MEM_IDX"] == "0"
+        finally:
+            kube.close()
+        kube = MockKube(make_node(NODE), config4_pods(NODE), tls=(str(pki / "wrongname.crt"), str(pki / "wrongname.key")))
+        try:  # right CA, but the certificate is for another host
+            kc = kubeconfig(tmp_path / "kc4", kube.url, [f"certificate-authority: {pki / 'ca.crt'}"], ["token: t"])
+            rc, log = run_gsbd(tmp_path, kc, expect_register=False)
+            assert rc == 1 and "x509" in log
+        finally:
+            kube.close()
+
+
+def test_python_kube_client_tls_forms(pki, tmp_path, monkeypatch):
+    kube = MockKube(make_node(NODE), config4_pods(NODE), tls=(str(pki / "server.crt"), str(pki / "server.key")),
+                    client_ca=str(pki / "ca.crt"))
+    try:
+        kc = kubeconfig(tmp_path / "kc", kube.url, [f"certificate-authority-data: {b64file(pki / 'ca.crt')}"],
+                        [f"client-certificate-data: {b64file(pki / 'client.crt')}", f"client-key-data: {b64file(pki / 'client.key')}",
+                         "token: tok"])
+        monkeypatch.setenv("KUBECONFIG", kc)
+        cs = kubeclient.from_environment()
+        assert cs.get_node(NODE)["metadata"]["name"] == NODE and "Bearer tok" in kube.auth_headers
+        kc = kubeconfig(tmp_path / "kc2", kube.url, [f"certificate-authority: {pki / 'other-ca.crt'}"],
+                        [f"client-certificate: {pki / 'client.crt'}", f"client-key: {pki / 'client.key'}"])
+        monkeypatch.setenv("KUBECONFIG", kc)
+        with pytest.raises(Exception):
+            kubeclient.from_environment().get_node(NODE)
+    finally:
+        kube.close()
