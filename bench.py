@@ -247,9 +247,15 @@ def bench_allocate(impl: str, quick: bool = False) -> dict:
             shutil.rmtree(tmp, ignore_errors=True)
         return sock, close
 
-    def load(sock, c, total):  # clients in their own process too
-        o = subprocess.run([sys.executable, "-m", "gpushare_device_plugin_b200.testing.allocate_load", sock, str(c),
-                            str(total), ",".join(UUIDS8)], capture_output=True, text=True, cwd=ROOT, timeout=900)
+    native_client = os.path.join(ROOT, "gpushare_device_plugin_b200", "gsb_alloc_load")
+    out["client"] = "native HTTP/2 client (csrc/daemon/alloc_load.cc), one persistent connection per client thread" \
+        if os.access(native_client, os.X_OK) else "grpcio (Python) client threads"
+
+    def load(sock, c, total):  # clients in their own process too; the same generator for every arm
+        argv = [native_client] if os.access(native_client, os.X_OK) else \
+            [sys.executable, "-m", "gpushare_device_plugin_b200.testing.allocate_load"]
+        o = subprocess.run(argv + [sock, str(c), str(total), ",".join(UUIDS8)], capture_output=True, text=True, cwd=ROOT,
+                           timeout=900)
         if o.returncode:
             raise RuntimeError(o.stderr[-400:])
         return json.loads(o.stdout.strip().splitlines()[-1])

@@ -17,5 +17,6 @@ echo "built $OUT"
 # native daemon (C++ host side: HTTP/2 + HPACK gRPC front end, kube client, manager loop) + its h2 self-test
 g++ -O2 -std=c++17 -Wall -pthread -o $PKG/gsbd $SRC/daemon/gsbd.cc -L$PKG -lgpushare_b200 -lssl -lcrypto -ldl -Wl,-rpath,'$ORIGIN'
 g++ -O2 -std=c++17 -Wall -pthread -o build/h2_selftest $SRC/daemon/h2_selftest.cc
+g++ -O2 -std=c++17 -Wall -pthread -o $PKG/gsb_alloc_load $SRC/daemon/alloc_load.cc
 echo "built $PKG/gsbd"
 if [ -f oracle/Makefile ]; then make -s -C oracle; fi

@@ -317,3 +317,22 @@ def test_native_optional_recovery(world):
     d2.inject(ch, fakes.UUIDS[1], 0x100, 3)
     assert next_frame(it) == first
     ch.close()
+
+
+def test_native_load_generator_drives_config4(world):
+    """csrc/daemon/alloc_load.cc (persistent HTTP/2 client) against gsbd: 64 requests, 64 distinct pods claimed."""
+    lg = os.path.join(ROOT, "gpushare_device_plugin_b200", "gsb_alloc_load")
+    if not os.access(lg, os.X_OK):
+        pytest.skip("gsb_alloc_load not built")
+    d = world.start("--pod-cache-ttl", "60")
+    out = subprocess.run([lg, str(world.dir / "aliyungpushare.sock"), "4", "64", ",".join(fakes.UUIDS)],
+                         capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    r = json.loads(out.stdout)
+    assert (r["requests"], r["error_responses"], r["rpc_failures"], r["client"]) == (64, 0, 0, "native")
+    assert 0 < r["p50_us"] < r["p99_us"]
+    patched = [x[1] for x in world.kube.requests if x[0] == "PATCH" and "/pods/" in x[1]]
+    assert len(patched) == 64 and len(set(patched)) == 64
+    out = subprocess.run([lg, str(world.dir / "aliyungpushare.sock"), "1", "3", ",".join(fakes.UUIDS)],
+                         capture_output=True, text=True, timeout=60)
+    assert json.loads(out.stdout)["error_responses"] == 3  # nothing left to assign: poison envs, still grpc OK
