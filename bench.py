@@ -214,7 +214,8 @@ def bench_allocate(impl: str, quick: bool = False) -> dict:
         if impl == "ours":  # the native daemon (gsbd): C++ HTTP/2 front end + C ABI, no interpreter on the RPC path
             from gpushare_device_plugin_b200.testing.fake_kubelet import FakeKubelet
             kubelet = FakeKubelet(tmp)
-            env = dict(os.environ, NODE_NAME=node, GPUSHARE_PLUGIN_DIR=tmp + "/", GPUSHARE_DUMP_DIR=tmp)
+            env = dict(os.environ, NODE_NAME=node, GPUSHARE_PLUGIN_DIR=tmp + "/", GPUSHARE_DUMP_DIR=tmp,
+                       GSBD_ALLOW_FAKE_INVENTORY="1")
             env.pop("KUBECONFIG", None)
             proc = subprocess.Popen([os.path.join(ROOT, "gpushare_device_plugin_b200", "gsbd"), "--fake-inventory", "8",
                                      "--kube-api-url", url], env=env, stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL)

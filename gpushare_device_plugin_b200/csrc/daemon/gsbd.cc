@@ -800,6 +800,16 @@ int main(int argc, char **argv) {
     WARN("Unsupported memory unit: %s, use memoryUnit Gi as default", f.memory_unit.c_str());
     f.memory_unit = "GiB";
   }
+  if (f.fake_inventory > 0) {
+    // test hook only: a synthetic node so the RPC surface can be exercised on a GPU-less builder. It never runs a
+    // probe and never stands in for a GPU; refuse it unless the caller says so twice.
+    const char *ok = getenv("GSBD_ALLOW_FAKE_INVENTORY");
+    if (!ok || strcmp(ok, "1") != 0) {
+      fprintf(stderr, "--fake-inventory is a test hook; set GSBD_ALLOW_FAKE_INVENTORY=1 to use it\n");
+      return 2;
+    }
+    WARN("TEST MODE: advertising %d synthetic GPUs, no driver, no HBM probe", f.fake_inventory);
+  }
   VLOG(1, "Start gpushare device plugin");
   const char *pd = getenv("GPUSHARE_PLUGIN_DIR");
   std::string plugin_dir = pd ? pd : kDevicePluginPath;

@@ -33,7 +33,7 @@ class Daemon:
         self.dir = tmp_path
         self.kubelet = kubelet or FakeKubelet(str(tmp_path))
         env = dict(os.environ, NODE_NAME=NODE, GPUSHARE_PLUGIN_DIR=str(tmp_path) + "/", GPUSHARE_DUMP_DIR=str(tmp_path),
-                   GPUSHARE_RETRY_SLEEP_MS="1")
+                   GPUSHARE_RETRY_SLEEP_MS="1", GSBD_ALLOW_FAKE_INVENTORY="1")
         env.pop("KUBECONFIG", None)
         self.log = open(tmp_path / "gsbd.log", "w")
         self.proc = subprocess.Popen([GSBD, "-logtostderr", "--v=5", "--memory-unit=GiB", "--health-check",
@@ -258,10 +258,14 @@ def test_lifecycle_restart_dump_and_exit_codes(world, tmp_path):
     assert d2.proc.wait(timeout=20) == 2
     d2.log.close()
     # NODE_NAME missing: fatal at kubeInit
-    env = dict(os.environ)
+    env = dict(os.environ, GSBD_ALLOW_FAKE_INVENTORY="1")
     env.pop("NODE_NAME", None)
     p = subprocess.run([GSBD, "--fake-inventory", "1", "--kube-api-url", world.kube.url], env=env, capture_output=True, text=True)
     assert p.returncode != 0 and "Please set env NODE_NAME" in p.stderr
+    env = dict(os.environ, NODE_NAME=NODE)
+    env.pop("GSBD_ALLOW_FAKE_INVENTORY", None)  # the synthetic-inventory hook cannot be switched on by the flag alone
+    p = subprocess.run([GSBD, "--fake-inventory", "1", "--kube-api-url", world.kube.url], env=env, capture_output=True, text=True)
+    assert p.returncode == 2 and "test hook" in p.stderr
     p = subprocess.run([GSBD, "--no-such-flag"], capture_output=True, text=True)
     assert p.returncode == 2 and "flag provided but not defined" in p.stderr
 

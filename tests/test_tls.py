@@ -46,7 +46,8 @@ def kubeconfig(path, server, cluster_lines, user_lines):
 
 def run_gsbd(tmp_path, kc, expect_register=True):
     kubelet = FakeKubelet(str(tmp_path))
-    env = dict(os.environ, NODE_NAME=NODE, KUBECONFIG=kc, GPUSHARE_PLUGIN_DIR=str(tmp_path) + "/", GPUSHARE_RETRY_SLEEP_MS="1")
+    env = dict(os.environ, NODE_NAME=NODE, KUBECONFIG=kc, GPUSHARE_PLUGIN_DIR=str(tmp_path) + "/", GPUSHARE_RETRY_SLEEP_MS="1",
+               GSBD_ALLOW_FAKE_INVENTORY="1")
     log = open(tmp_path / "gsbd.log", "w")
     p = subprocess.Popen([GSBD, "--v=5", "--fake-inventory", "8"], env=env, stderr=log, stdout=log)
     try:
