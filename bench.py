@@ -200,7 +200,7 @@ def bench_allocate(impl: str, quick: bool = False) -> dict:
     logging.getLogger("gpushare").setLevel(logging.WARNING)
     logging.getLogger("gpushare.nvidia").setLevel(logging.WARNING)
     node = "b200-0"
-    out = {"impl": impl, "transport": "grpcio over unix socket (both arms)", "mock": "loopback Python apiserver (own process), clients in a third process",
+    out = {"impl": impl, "transport": "gRPC (HTTP/2) over a unix socket; the server is the arm under test", "mock": "loopback Python apiserver (own process), clients in a third process",
            "sweep": []}
 
     def start(n_pods, mod):
