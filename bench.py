@@ -266,10 +266,10 @@ def bench_allocate(impl: str, quick: bool = False) -> dict:
     r = load(sock, 1, 64)
     close()
     out["config4"] = {k: r[k] for k in ("p50_us", "p99_us", "mean_us", "req_per_s", "error_responses")}
-    # config 5: 1024 pending pods, concurrency sweep (bounded: 256 requests per point)
-    for c in ((1, 16) if quick else (1, 4, 16, 64, 256)):
+    # config 5: 1024 pending pods, concurrency sweep 1..1024 (bounded: max(256, c) requests per point)
+    for c in ((1, 16) if quick else (1, 4, 16, 64, 256, 1024)):
         sock, close = start(1024, True)
-        r = load(sock, c, 64 if quick else 256)
+        r = load(sock, c, 64 if quick else max(256, c))
         close()
         out["sweep"].append(r)
     out["p50_us"] = out["config4"]["p50_us"]
