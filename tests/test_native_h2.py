@@ -271,3 +271,25 @@ def test_server_survives_garbage_and_truncated_frames(server):
         s.close()
         assert proc.poll() is None
     assert ch.unary_unary("/test.Echo/Unary")(b"still alive", timeout=5) == b"still alive"
+
+
+def test_interop_with_curl_nghttp2(server, tmp_path):
+    """A third HTTP/2 stack: curl + nghttp2 (h2c prior knowledge over the unix socket). nghttp2's HPACK encoder
+    Huffman-codes and indexes differently from grpc's C-core."""
+    import shutil
+    if not shutil.which("curl") or "nghttp2" not in subprocess.run(["curl", "--version"], capture_output=True, text=True).stdout:
+        pytest.skip("curl without nghttp2")
+    _, sock_path, _ = server
+    msg = b"hello from nghttp2 " * 50
+    req = tmp_path / "req.bin"
+    req.write_bytes(b"\0" + len(msg).to_bytes(4, "big") + msg)
+    for _ in range(2):
+        out = subprocess.run(["curl", "-sS", "--unix-socket", sock_path, "--http2-prior-knowledge", "-X", "POST",
+                              "-H", "content-type: application/grpc", "-H", "te: trailers", "--data-binary", f"@{req}",
+                              "-D", str(tmp_path / "hdr.txt"), "-o", str(tmp_path / "body.bin"),
+                              "http://localhost/test.Echo/Unary"], capture_output=True, text=True, timeout=20)
+        assert out.returncode == 0, out.stderr
+        body = (tmp_path / "body.bin").read_bytes()
+        assert body == b"\0" + len(msg).to_bytes(4, "big") + msg
+        hdr = (tmp_path / "hdr.txt").read_text().lower()
+        assert "http/2 200" in hdr and "content-type: application/grpc" in hdr and "grpc-status: 0" in hdr
