@@ -30,6 +30,7 @@
 #include <fstream>
 #include <memory>
 #include <mutex>
+#include <set>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -92,7 +93,7 @@ struct Flags {
   // additions (active probe, test hooks); none changes the wire contract
   int probe_period_ms = 1000, probe_window_mib = 1024, probe_arena_mib = 4096, fake_inventory = 0;
   int health_recovery_cycles = 0;  // 0 = the reference's sticky Unhealthy
-  bool startup_full_walk = false, coalesce_health = true;
+  bool startup_full_walk = false, coalesce_health = true, pod_informer = true;
   double pod_cache_ttl = 1.0;
   std::string kube_api_url, kubelet_scheme = "https";
 };
@@ -128,6 +129,7 @@ bool parse_flags(int argc, char **argv, Flags *f) {
     else if (name == "query-kubelet") boolean(&f->query_kubelet);
     else if (name == "startup-full-walk") boolean(&f->startup_full_walk);
     else if (name == "coalesce-health") boolean(&f->coalesce_health);
+    else if (name == "pod-informer") boolean(&f->pod_informer);
     else if (name == "logtostderr" || name == "alsologtostderr") { bool ignored; boolean(&ignored); }
     else if (name == "memory-unit") { if (!need()) return false; f->memory_unit = val; }
     else if (name == "kubelet-address") { if (!need()) return false; f->kubelet_address = val; }
@@ -315,6 +317,47 @@ bool parse_uint64(const std::string &s, uint64_t *out) {  // strconv.ParseUint(s
   return true;
 }
 
+// one v1.Pod JSON object -> (PodRec, gsb_pod) with the fields the reference reads (podutils.go:37-131)
+void pod_row(const json::Value &p, const std::string &node, PodRec *r, gsb_pod *g) {
+  const json::Value *md = p.get("metadata");
+  if (md) {
+    if (auto *v = md->get("name")) r->name = v->str();
+    if (auto *v = md->get("namespace")) r->ns = v->str();
+    if (auto *v = md->get("uid")) r->uid = v->str();
+  }
+  memset(g, 0, sizeof *g);
+  g->gpu_idx = -1;
+  if (const json::Value *cs = p.path({"spec", "containers"}))  // podutils.go:122-131: spec.containers only
+    for (const json::Value &c : cs->arr)
+      if (const json::Value *lim = c.path({"resources", "limits", kResourceName})) g->gpu_mem_limit += quantity_value(*lim);
+  const json::Value *ann = md ? md->get("annotations") : nullptr;
+  if (ann && ann->type == json::Value::Object) {
+    if (auto *v = ann->get(kEnvResourceIndex)) {
+      long long id;
+      if (atoi_strict(v->str(), &id) && id >= -2147483648LL && id <= 2147483647LL) g->gpu_idx = id < 0 ? -1 : (int32_t)id;
+    }
+    if (auto *v = ann->get(kEnvResourceAssumeTime)) {
+      g->has_assume_time = 1;
+      uint64_t at;
+      if (parse_uint64(v->str(), &at)) g->assume_time = at;
+    }
+    if (auto *v = ann->get(kEnvAssignedFlag)) {
+      g->has_assigned = 1;
+      g->assigned_is_false = v->str() == "false";
+    }
+  }
+  const json::Value *nn = p.path({"spec", "nodeName"});
+  g->on_node = nn && nn->str() == node;
+}
+
+void fix_pointers(PodTable *t) {  // only after recs stopped changing
+  for (size_t i = 0; i < t->recs.size(); i++) {
+    t->pods[i].name = t->recs[i].name.c_str();
+    t->pods[i].ns = t->recs[i].ns.c_str();
+    t->pods[i].uid = t->recs[i].uid.c_str();
+  }
+}
+
 // v1.PodList JSON -> table; `pending_only` = the kubelet path's phase filter (podmanager.go:101-123)
 void build_table(const json::Value &list, const std::string &node, bool pending_only, PodTable *t) {
   t->recs.clear();
@@ -328,44 +371,12 @@ void build_table(const json::Value &list, const std::string &node, bool pending_
       if (!ph || ph->str() != "Pending") continue;
     }
     PodRec r;
-    const json::Value *md = p.get("metadata");
-    if (md) {
-      if (auto *v = md->get("name")) r.name = v->str();
-      if (auto *v = md->get("namespace")) r.ns = v->str();
-      if (auto *v = md->get("uid")) r.uid = v->str();
-    }
     gsb_pod g;
-    memset(&g, 0, sizeof g);
-    g.gpu_idx = -1;
-    if (const json::Value *cs = p.path({"spec", "containers"}))  // podutils.go:122-131: spec.containers only
-      for (const json::Value &c : cs->arr)
-        if (const json::Value *lim = c.path({"resources", "limits", kResourceName})) g.gpu_mem_limit += quantity_value(*lim);
-    const json::Value *ann = md ? md->get("annotations") : nullptr;
-    if (ann && ann->type == json::Value::Object) {
-      if (auto *v = ann->get(kEnvResourceIndex)) {
-        long long id;
-        if (atoi_strict(v->str(), &id) && id >= -2147483648LL && id <= 2147483647LL) g.gpu_idx = id < 0 ? -1 : (int32_t)id;
-      }
-      if (auto *v = ann->get(kEnvResourceAssumeTime)) {
-        g.has_assume_time = 1;
-        uint64_t at;
-        if (parse_uint64(v->str(), &at)) g.assume_time = at;
-      }
-      if (auto *v = ann->get(kEnvAssignedFlag)) {
-        g.has_assigned = 1;
-        g.assigned_is_false = v->str() == "false";
-      }
-    }
-    const json::Value *nn = p.path({"spec", "nodeName"});
-    g.on_node = nn && nn->str() == node;
+    pod_row(p, node, &r, &g);
     t->recs.push_back(std::move(r));
     t->pods.push_back(g);
   }
-  for (size_t i = 0; i < t->recs.size(); i++) {  // pointers only after recs stopped growing
-    t->pods[i].name = t->recs[i].name.c_str();
-    t->pods[i].ns = t->recs[i].ns.c_str();
-    t->pods[i].uid = t->recs[i].uid.c_str();
-  }
+  fix_pointers(t);
 }
 
 // ---------------------------------------------------------------- the plugin (server.go)
@@ -459,6 +470,7 @@ class Plugin {
     }
     if (!srv_->start(socket_, err)) return false;
     health_thread_ = std::thread([this] { healthcheck(); });
+    if (f_.pod_informer && !f_.query_kubelet) informer_thread_ = std::thread([this] { informer(); });
     return true;
   }
 
@@ -470,9 +482,14 @@ class Plugin {
       std::lock_guard<std::mutex> lk(hmu_);
       hcv_.notify_all();
     }
+    {
+      std::lock_guard<std::mutex> lk(wmu_);
+      if (watch_conn_) watch_conn_->abort();
+    }
     srv_->stop();
     srv_.reset();
     if (health_thread_.joinable()) health_thread_.join();
+    if (informer_thread_.joinable()) informer_thread_.join();
     ::unlink(socket_.c_str());
   }
 
@@ -624,6 +641,98 @@ class Plugin {
     if (f_.fake_inventory == 0) gsb_health_stop();
   }
 
+  // ---- pending-pod informer (second step): LIST once, then follow the apiserver's watch
+  // stream so the table is current without a LIST per call or per TTL. Optimistic like the TTL cache: a request
+  // that finds no candidate still re-LISTs, a failed PATCH forces a resync. Falls back to the TTL cache whenever
+  // the watch cannot be established (synced_ == false).
+  void informer() {
+    const std::string sel = "fieldSelector=spec.nodeName%3D" + kube_->node_name + "%2Cstatus.phase%3DPending";
+    while (!stopping_) {
+      std::string err, rv;
+      json::Value list;
+      if (!kube_->call("GET", "/api/v1/pods?" + sel, "", "", &list, &err)) {
+        for (int i = 0; i < 20 && !stopping_; i++) std::this_thread::sleep_for(std::chrono::milliseconds(50));
+        continue;
+      }
+      if (const json::Value *v = list.path({"metadata", "resourceVersion"})) rv = v->str();
+      {
+        std::lock_guard<std::mutex> lk(amu_);
+        build_table(list, kube_->node_name, false, &table_);
+        table_.stamp = std::chrono::steady_clock::now();
+        table_.valid = true;
+        resync_ = false;
+      }
+      std::unique_ptr<http::Conn> conn = kube_->api.open_stream("/api/v1/pods?watch=true&" + sel + "&resourceVersion=" + rv, 300, &err);
+      if (!conn) {
+        synced_ = false;
+        for (int i = 0; i < 20 && !stopping_; i++) std::this_thread::sleep_for(std::chrono::milliseconds(50));
+        continue;
+      }
+      {
+        std::lock_guard<std::mutex> lk(wmu_);
+        watch_conn_ = conn.get();
+        // a stop or a resync request that arrived while the stream was being opened found nothing to abort
+        if (stopping_ || resync_) conn->abort();
+      }
+      int status = 0;
+      conn->read_stream(&status, [&](int st) { synced_ = st == 200; },  // stream is up: table kept current from here on
+                        [&](const std::string &line) -> bool {
+        if (status >= 400) return false;
+        json::Value ev;
+        if (!json::parse(line, &ev)) return true;
+        const json::Value *type = ev.get("type"), *obj = ev.get("object");
+        if (!type || !obj) return true;
+        if (type->str() == "ERROR") return false;  // e.g. 410 Gone (resourceVersion too old): start over from a LIST
+        apply_event(type->str(), *obj);
+        return !stopping_ && !resync_;
+      });
+      {
+        std::lock_guard<std::mutex> lk(wmu_);
+        watch_conn_ = nullptr;
+      }
+      synced_ = false;  // until the next LIST + watch are in place the TTL path answers
+    }
+    synced_ = false;
+  }
+
+  void apply_event(const std::string &type, const json::Value &obj) {
+    PodRec r;
+    gsb_pod g;
+    pod_row(obj, kube_->node_name, &r, &g);
+    std::lock_guard<std::mutex> lk(amu_);
+    size_t at = table_.recs.size();
+    for (size_t i = 0; i < table_.recs.size(); i++)
+      if (table_.recs[i].uid == r.uid) {
+        at = i;
+        break;
+      }
+    if (type == "DELETED") {
+      if (at < table_.recs.size()) {
+        table_.recs.erase(table_.recs.begin() + (long)at);
+        table_.pods.erase(table_.pods.begin() + (long)at);
+      }
+    } else if (type == "ADDED" || type == "MODIFIED") {
+      // a pod this daemon has claimed (PATCH possibly still in flight) stays hidden until the apiserver's copy
+      // itself stops saying assigned == "false"
+      auto c = claimed_.find(r.uid);
+      if (c != claimed_.end()) {
+        if (g.has_assigned && !g.assigned_is_false) claimed_.erase(c);
+        else g.assigned_is_false = 0;
+      }
+      if (at < table_.recs.size()) {
+        table_.recs[at] = std::move(r);
+        table_.pods[at] = g;
+      } else {
+        table_.recs.push_back(std::move(r));
+        table_.pods.push_back(g);
+      }
+    } else {
+      return;  // BOOKMARK / ERROR: nothing to apply (an ERROR ends the stream on the server side)
+    }
+    fix_pointers(&table_);
+    table_.stamp = std::chrono::steady_clock::now();
+  }
+
   // ---- Allocate
   bool load_pods(std::string *err) {
     json::Value list;
@@ -666,6 +775,7 @@ class Plugin {
     return true;
   }
   bool cache_fresh() const {
+    if (synced_ && table_.valid && !resync_) return true;  // kept current by the watch stream
     return table_.valid && f_.pod_cache_ttl > 0 &&
            std::chrono::duration<double>(std::chrono::steady_clock::now() - table_.stamp).count() < f_.pod_cache_ttl;
   }
@@ -717,6 +827,7 @@ class Plugin {
         name = table_.recs[pidx].name;
         ns = table_.recs[pidx].ns;
         table_.pods[pidx].assigned_is_false = 0;  // claimed: hidden from the next request
+        claimed_.insert(table_.recs[pidx].uid);
       }
     }
     if (kind == GSB_ALLOC_MATCHED) {
@@ -733,6 +844,12 @@ class Plugin {
         WARN("Failed due to %s", err.c_str());
         std::lock_guard<std::mutex> lk(amu_);
         table_.valid = false;  // drop the cache: it no longer reflects the apiserver
+        claimed_.clear();
+        resync_ = true;        // and make the informer start over from a fresh LIST
+        {
+          std::lock_guard<std::mutex> wl(wmu_);
+          if (watch_conn_) watch_conn_->abort();
+        }
         return err_response(req);
       }
       VLOG(1, "----Allocating GPU for gpu mem for %s is ended----", name.c_str());
@@ -787,6 +904,11 @@ class Plugin {
   // Allocate
   std::mutex amu_;
   PodTable table_;
+  std::thread informer_thread_;
+  std::atomic<bool> synced_{false}, resync_{false};
+  std::set<std::string> claimed_;  // uids claimed here whose assigned="true" has not come back on the watch yet
+  std::mutex wmu_;
+  http::Conn *watch_conn_ = nullptr;
   int retry_sleep_ms_ = 1000;
 };
 

@@ -123,6 +123,68 @@ class Conn {
     buf_.erase(0, n);
     return true;
   }
+  // Streaming variant for watches: parses the status line + headers, then hands every '\n'-terminated line of
+  // the (chunked or close-delimited) body to `on_line` as it arrives. Returns when the server ends the stream,
+  // the connection drops, on_line returns false, or abort() is called from another thread.
+  template <typename F, typename H>
+  bool read_stream(int *status, H on_headers, F on_line) {
+    std::string line;
+    if (!read_line(&line) || line.size() < 12) return false;
+    *status = atoi(line.c_str() + 9);
+    bool chunked = false;
+    while (read_line(&line)) {
+      if (line.empty()) break;
+      std::string lower = line;
+      for (auto &c : lower) c = (char)tolower((unsigned char)c);
+      if (lower.compare(0, 18, "transfer-encoding:") == 0 && lower.find("chunked") != std::string::npos) chunked = true;
+    }
+    on_headers(*status);
+    std::string pending;
+    auto feed = [&](const std::string &data) -> bool {
+      pending += data;
+      size_t nl;
+      while ((nl = pending.find('\n')) != std::string::npos) {
+        std::string one = pending.substr(0, nl);
+        pending.erase(0, nl + 1);
+        if (!one.empty() && !on_line(one)) return false;
+      }
+      return true;
+    };
+    if (*status >= 400) {  // error body: small, read what is there
+      std::string body;
+      while (fill()) {
+      }
+      body.swap(buf_);
+      on_line(body);
+      return false;
+    }
+    if (chunked) {
+      for (;;) {
+        if (!read_line(&line)) return false;
+        const size_t n = (size_t)strtoul(line.c_str(), nullptr, 16);
+        if (n == 0) return true;
+        std::string chunk;
+        if (!read_n(n, &chunk) || !read_line(&line)) return false;
+        if (!feed(chunk)) return true;
+      }
+    }
+    for (;;) {
+      if (!buf_.empty()) {
+        std::string chunk;
+        chunk.swap(buf_);
+        if (!feed(chunk)) return true;
+      }
+      if (!fill()) return true;
+    }
+  }
+  void abort() {  // from another thread: wakes a blocked read
+    if (fd_ >= 0) ::shutdown(fd_, SHUT_RDWR);
+  }
+  void set_read_timeout(int seconds) {
+    timeval tv{seconds, 0};
+    if (fd_ >= 0) setsockopt(fd_, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof tv);
+  }
+
   bool read_response(Response *r, bool *keep_alive) {
     std::string line;
     if (!read_line(&line) || line.size() < 12) return false;
@@ -249,6 +311,21 @@ class Client {
       }
     }
     return true;
+  }
+
+  // A dedicated connection for a long-lived GET (watch): returns the connection with the request already sent.
+  std::unique_ptr<Conn> open_stream(const std::string &path, int read_timeout_s, std::string *err) {
+    std::unique_ptr<Conn> c(new Conn());
+    if (!c->open(host_, port_, ctx_, host_, timeout_s_, err, !insecure_)) return nullptr;
+    c->set_read_timeout(read_timeout_s);
+    std::string req = "GET " + path + " HTTP/1.1\r\nHost: " + host_ + "\r\nAccept: application/json\r\n";
+    if (!token_.empty()) req += "Authorization: Bearer " + token_ + "\r\n";
+    req += "\r\n";
+    if (!c->write_all(req)) {
+      *err = "GET " + path + ": connection failed";
+      return nullptr;
+    }
+    return c;
   }
 
   // One request; a stale pooled connection is retried once on a fresh one.

@@ -60,6 +60,12 @@ class MockKube:
         """tls = (certfile, keyfile) serves HTTPS; client_ca = CA file makes a client certificate mandatory."""
         self.chunked_lists = chunked_lists  # answer pod LISTs with Transfer-Encoding: chunked, like the apiserver
         self.auth_headers: List[Optional[str]] = []
+        self.rv = 1000                      # cluster resourceVersion
+        self.events: List[tuple] = []       # (rv, type, pod snapshot) — the watch cache
+        self.watch_cv = threading.Condition()
+        self.closing = False
+        self.watches_served = 0
+        self.enable_watch = True
         self.lock = threading.Lock()
         self.nodes: Dict[str, dict] = {node["metadata"]["name"]: node}
         self.pods: Dict[tuple, dict] = {(p["metadata"]["namespace"], p["metadata"]["name"]): p for p in pods}
@@ -112,7 +118,17 @@ class MockKube:
                     if parts[:3] == ["api", "v1", "nodes"] and len(parts) == 4:
                         n = mock.nodes.get(parts[3])
                         return self._send(200, n) if n else self._status(404, f'nodes "{parts[3]}" not found')
-                    if parts[:3] == ["api", "v1", "pods"]:
+                    if parts[:3] == ["api", "v1", "pods"] and urllib.parse.parse_qs(u.query).get("watch", ["0"])[0] in ("1", "true"):
+                        if not mock.enable_watch:
+                            return self._status(400, "watch is disabled on this mock")
+                        q = urllib.parse.parse_qs(u.query)
+                        sel = dict(kv.split("=", 1) for kv in q.get("fieldSelector", [""])[0].split(",") if "=" in kv)
+                        since = int(q.get("resourceVersion", ["0"])[0] or 0)
+                        mock.watches_served += 1
+                        watch_args = (sel, since)
+                    else:
+                        watch_args = None
+                    if watch_args is None and parts[:3] == ["api", "v1", "pods"]:
                         if mock.fail_lists > 0:
                             mock.fail_lists -= 1
                             return self._status(500, "etcdserver: request timed out")
@@ -126,9 +142,49 @@ class MockKube:
                             if "status.phase" in sel and p["status"].get("phase") != sel["status.phase"]:
                                 continue
                             items.append(copy.deepcopy(p))
-                        return self._send(200, {"kind": "PodList", "apiVersion": "v1", "items": items},
+                        return self._send(200, {"kind": "PodList", "apiVersion": "v1",
+                                                "metadata": {"resourceVersion": str(mock.rv)}, "items": items},
                                           chunked=mock.chunked_lists)
+                if watch_args is not None:
+                    return self._watch(*watch_args)
                 self._status(404, "not found")
+
+            def _watch(self, sel, since):
+                """GET /api/v1/pods?watch=true: chunked stream of {"type","object"} lines from resourceVersion `since`.
+                A pod that stops matching the field selector is reported as DELETED, as the apiserver does."""
+                def matches(p):
+                    return (("spec.nodeName" not in sel or p["spec"].get("nodeName") == sel["spec.nodeName"]) and
+                            ("status.phase" not in sel or p["status"].get("phase") == sel["status.phase"]))
+                try:
+                    self.wfile.write(b"HTTP/1.1 200 OK\r\nContent-Type: application/json\r\nTransfer-Encoding: chunked\r\n\r\n")
+                    self.wfile.flush()
+                    cursor = 0
+                    while True:
+                        with mock.watch_cv:
+                            while cursor >= len(mock.events) and not mock.closing:
+                                mock.watch_cv.wait(0.2)
+                            if mock.closing:
+                                break
+                            batch = mock.events[cursor:]
+                            cursor = len(mock.events)
+                        for rv, etype, pod in batch:
+                            if rv <= since:
+                                continue
+                            if etype == "ERROR":  # e.g. 410 Gone: one Status line, then the server ends the stream
+                                line = json.dumps({"type": "ERROR", "object": pod}, separators=(",", ":")).encode() + b"\n"
+                                self.wfile.write(b"%x\r\n" % len(line) + line + b"\r\n0\r\n\r\n")
+                                self.wfile.flush()
+                                self.close_connection = True
+                                return
+                            if not matches(pod):
+                                etype = "DELETED"
+                            line = json.dumps({"type": etype, "object": pod}, separators=(",", ":")).encode() + b"\n"
+                            self.wfile.write(b"%x\r\n" % len(line) + line + b"\r\n")
+                            self.wfile.flush()
+                    self.wfile.write(b"0\r\n\r\n")
+                except OSError:
+                    pass
+                self.close_connection = True
 
             def do_PATCH(self):
                 u = urllib.parse.urlparse(self.path)
@@ -155,6 +211,7 @@ class MockKube:
                             return self._status(404, f'pods "{parts[5]}" not found')
                         p["metadata"].setdefault("annotations", {}).update(
                             (patch.get("metadata") or {}).get("annotations") or {})
+                        mock._emit("MODIFIED", p)
                         return self._send(200, p)
                 self._status(404, "not found")
 
@@ -178,6 +235,37 @@ class MockKube:
         self.thread = threading.Thread(target=self.httpd.serve_forever, name="mock-kube", daemon=True)
         self.thread.start()
 
+    def _emit(self, etype: str, pod: dict):
+        """caller holds self.lock"""
+        self.rv += 1
+        pod.setdefault("metadata", {})["resourceVersion"] = str(self.rv)
+        with self.watch_cv:
+            self.events.append((self.rv, etype, copy.deepcopy(pod)))
+            self.watch_cv.notify_all()
+
+    def add_pod(self, pod: dict):
+        with self.lock:
+            key = (pod["metadata"]["namespace"], pod["metadata"]["name"])
+            self.pods[key] = pod
+            self.order.append(key)
+            self._emit("ADDED", pod)
+
+    def delete_pod(self, name: str, namespace: str = "default"):
+        with self.lock:
+            pod = self.pods.pop((namespace, name))
+            self.order.remove((namespace, name))
+            self._emit("DELETED", pod)
+
+    def expire_watches(self):
+        """Every open watch gets an ERROR event (410 Gone, "too old resource version") and is closed by the server."""
+        with self.lock:
+            self.rv += 1
+            status = {"kind": "Status", "apiVersion": "v1", "status": "Failure", "reason": "Expired", "code": 410,
+                      "message": "too old resource version"}
+            with self.watch_cv:
+                self.events.append((self.rv, "ERROR", status))
+                self.watch_cv.notify_all()
+
     def fail_next_patch(self, message: str, times: int = 1):
         with self.lock:
             self._fail_patch.extend([message] * times)
@@ -187,6 +275,9 @@ class MockKube:
             return copy.deepcopy(self.pods[(namespace, name)])
 
     def close(self):
+        with self.watch_cv:
+            self.closing = True
+            self.watch_cv.notify_all()
         self.httpd.shutdown()
         self.httpd.server_close()
 

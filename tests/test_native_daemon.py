@@ -157,7 +157,7 @@ def test_allocate_config4_end_to_end(world):
 
 
 def test_allocate_failure_paths_and_cache(world):
-    d = world.start("--pod-cache-ttl", "60")
+    d = world.start("--pod-cache-ttl", "60", "--pod-informer=false")  # the TTL cache alone (LIST failures are injected)
     ch = d.channel()
     req = wo.marshal_AllocateRequest([["a", "b", "c", "d"]])
     err = [KAT["err_response"]["envs"]]
@@ -340,3 +340,79 @@ def test_native_load_generator_drives_config4(world):
     out = subprocess.run([lg, str(world.dir / "aliyungpushare.sock"), "1", "3", ",".join(fakes.UUIDS)],
                          capture_output=True, text=True, timeout=60)
     assert json.loads(out.stdout)["error_responses"] == 3  # nothing left to assign: poison envs, still grpc OK
+
+
+def _count(world, kind, sub):
+    return len([r for r in world.kube.requests if r[0] == kind and sub in r[1]])
+
+
+def test_informer_keeps_the_table_current_without_lists(world):
+    d = world.start("--pod-cache-ttl", "0")  # no TTL cache at all: only the watch stream can avoid a LIST per call
+    ch = d.channel()
+    req = wo.marshal_AllocateRequest([["a", "b", "c", "d"]])
+    deadline = time.time() + 5
+    while world.kube.watches_served == 0 and time.time() < deadline:
+        time.sleep(0.05)
+    assert world.kube.watches_served >= 1
+    time.sleep(0.2)
+    lists0 = _count(world, "GET", "/api/v1/pods?fieldSelector")
+    for i in range(64):
+        assert wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, req))[0]["ALIYUN_COM_GPU_MEM_IDX"] == str(i // 8)
+    assert _count(world, "GET", "/api/v1/pods?fieldSelector") == lists0  # not one LIST for 64 requests
+    # a pod bound after start-up arrives as an ADDED event: found without a LIST
+    world.kube.add_pod(make_pod(99, NODE, gpu_mem=2, idx=5, assume_time=1_800_000_000_000_000_000))
+    time.sleep(0.3)
+    envs = wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, wo.marshal_AllocateRequest([["a", "b"]])))
+    assert envs[0]["ALIYUN_COM_GPU_MEM_IDX"] == "5" and _count(world, "GET", "/api/v1/pods?fieldSelector") == lists0
+    # a deleted pod disappears from the table; the miss is confirmed by one authoritative LIST
+    world.kube.add_pod(make_pod(98, NODE, gpu_mem=3, idx=6, assume_time=1_800_000_000_000_000_001))
+    time.sleep(0.2)
+    world.kube.delete_pod("pod-98")
+    time.sleep(0.3)
+    envs = wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, wo.marshal_AllocateRequest([["a", "b", "c"]])))
+    assert envs[0]["ALIYUN_COM_GPU_MEM_IDX"] == "-1" and _count(world, "GET", "/api/v1/pods?fieldSelector") == lists0 + 1
+    # a failed PATCH forces a resync (fresh LIST + new watch); service continues
+    world.kube.add_pod(make_pod(97, NODE, gpu_mem=5, idx=2, assume_time=1_800_000_000_000_000_002))
+    time.sleep(0.3)
+    world.kube.fail_next_patch("pods is forbidden", 1)
+    w0 = world.kube.watches_served
+    five = wo.marshal_AllocateRequest([["a"] * 5])
+    assert wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, five))[0]["ALIYUN_COM_GPU_MEM_IDX"] == "-1"
+    deadline = time.time() + 5
+    while world.kube.watches_served == w0 and time.time() < deadline:
+        time.sleep(0.05)
+    assert world.kube.watches_served > w0
+    assert wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, five))[0]["ALIYUN_COM_GPU_MEM_IDX"] == "2"
+    # the apiserver expires the stream (ERROR event, 410 Gone): the informer starts over from a LIST
+    w0 = world.kube.watches_served
+    world.kube.expire_watches()
+    deadline = time.time() + 5
+    while world.kube.watches_served == w0 and time.time() < deadline:
+        time.sleep(0.05)
+    assert world.kube.watches_served > w0
+    world.kube.add_pod(make_pod(96, NODE, gpu_mem=7, idx=3, assume_time=1_800_000_000_000_000_003))
+    time.sleep(0.3)
+    seven = wo.marshal_AllocateRequest([["a"] * 7])
+    assert wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, seven))[0]["ALIYUN_COM_GPU_MEM_IDX"] == "3"
+    ch.close()
+
+
+def test_informer_falls_back_to_the_ttl_cache_when_watch_is_refused(world):
+    world.kube.enable_watch = False
+    d = world.start("--pod-cache-ttl", "60")
+    ch = d.channel()
+    req = wo.marshal_AllocateRequest([["a", "b", "c", "d"]])
+    for i in range(16):
+        assert wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, req))[0]["ALIYUN_COM_GPU_MEM_IDX"] == str(i // 8)
+    ch.close()
+    assert world.kube.watches_served == 0
+
+
+def test_reference_exact_mode_lists_on_every_call(world):
+    d = world.start("--pod-informer=false", "--pod-cache-ttl", "0")
+    ch = d.channel()
+    req = wo.marshal_AllocateRequest([["a", "b", "c", "d"]])
+    for i in range(10):
+        assert wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, req))[0]["ALIYUN_COM_GPU_MEM_IDX"] == str(i // 8)
+    assert _count(world, "GET", "/api/v1/pods?fieldSelector") == 10 and world.kube.watches_served == 0
+    ch.close()
