@@ -200,14 +200,18 @@ def bench_allocate(impl: str, quick: bool = False) -> dict:
     logging.getLogger("gpushare").setLevel(logging.WARNING)
     logging.getLogger("gpushare.nvidia").setLevel(logging.WARNING)
     node = "b200-0"
-    out = {"impl": impl, "transport": "gRPC (HTTP/2) over a unix socket; the server is the arm under test", "mock": "loopback Python apiserver (own process), clients in a third process",
+    native_mock = os.path.join(ROOT, "gpushare_device_plugin_b200", "gsb_mock_kube")
+    use_native_mock = os.access(native_mock, os.X_OK) and os.environ.get("GSB_BENCH_MOCK", "native") == "native"
+    mock_argv = [native_mock] if use_native_mock else [sys.executable, "-m", "gpushare_device_plugin_b200.testing.mock_kube"]
+    out = {"impl": impl, "transport": "gRPC (HTTP/2) over a unix socket; the server is the arm under test",
+           "mock": ("loopback compiled apiserver stand-in (csrc/daemon/mock_kube.cc)" if use_native_mock else
+                    "loopback Python apiserver") + ", own process; clients in a third process",
            "sweep": []}
 
-    def start(n_pods, mod):
+    def start(n_pods, mod, gsbd_extra=()):
         tmp = tempfile.mkdtemp(prefix="gsb-alloc-")
-        kube = subprocess.Popen([sys.executable, "-m", "gpushare_device_plugin_b200.testing.mock_kube", "--node", node,
-                                 "--pods", str(n_pods)] + (["--mod"] if mod else []), stdin=subprocess.PIPE,
-                                stdout=subprocess.PIPE, text=True, cwd=ROOT)
+        kube = subprocess.Popen(mock_argv + ["--node", node, "--pods", str(n_pods)] + (["--mod"] if mod else []),
+                                stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, cwd=ROOT)
         url = f"http://127.0.0.1:{int(kube.stdout.readline())}"
         sock = os.path.join(tmp, "aliyungpushare.sock")
         minors = {u: i for i, u in enumerate(UUIDS8)}
@@ -218,8 +222,9 @@ def bench_allocate(impl: str, quick: bool = False) -> dict:
                        GSBD_ALLOW_FAKE_INVENTORY="1")
             env.pop("KUBECONFIG", None)
             proc = subprocess.Popen([os.path.join(ROOT, "gpushare_device_plugin_b200", "gsbd"), "--fake-inventory", "8",
-                                     "--kube-api-url", url], env=env, stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL)
+                                     "--kube-api-url", url] + list(gsbd_extra) + os.environ.get("GSBD_EXTRA", "").split(), env=env, stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL)
             kubelet.register_requests.get(timeout=30)
+            time.sleep(0.3)  # let the pod informer finish its first LIST + watch (the kubelet calls Allocate much later)
 
             def stop():
                 proc.terminate()
@@ -266,10 +271,19 @@ def bench_allocate(impl: str, quick: bool = False) -> dict:
     r = load(sock, 1, 64)
     close()
     out["config4"] = {k: r[k] for k in ("p50_us", "p99_us", "mean_us", "req_per_s", "error_responses")}
+    if impl == "ours":  # where the time goes: the same daemon with the pod source stepped back towards the reference's
+        out["config4_by_pod_source"] = {"watch_informer (default)": out["config4"]["p50_us"]}
+        for label, extra in (("ttl_cache (--pod-informer=false)", ("--pod-informer=false",)),
+                             ("list_per_call, as the reference (--pod-informer=false --pod-cache-ttl 0)",
+                              ("--pod-informer=false", "--pod-cache-ttl", "0"))):
+            sock, close = start(64, False, extra)
+            out["config4_by_pod_source"][label] = load(sock, 1, 64)["p50_us"]
+            close()
     # config 5: 1024 pending pods, concurrency sweep 1..1024 (bounded: max(256, c) requests per point)
     for c in ((1, 16) if quick else (1, 4, 16, 64, 256, 1024)):
         sock, close = start(1024, True)
-        r = load(sock, c, 64 if quick else max(256, c))
+        # each Allocate consumes one of the 1 024 pending pods; the reference arm (~40 req/s) gets a smaller sample
+        r = load(sock, c, 64 if quick else (max(256, c) if impl == "reference" else max(1000, c)))
         close()
         out["sweep"].append(r)
     out["p50_us"] = out["config4"]["p50_us"]

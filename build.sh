@@ -18,5 +18,6 @@ echo "built $OUT"
 g++ -O2 -std=c++17 -Wall -pthread -o $PKG/gsbd $SRC/daemon/gsbd.cc -L$PKG -lgpushare_b200 -lssl -lcrypto -ldl -Wl,-rpath,'$ORIGIN'
 g++ -O2 -std=c++17 -Wall -pthread -o build/h2_selftest $SRC/daemon/h2_selftest.cc
 g++ -O2 -std=c++17 -Wall -pthread -o $PKG/gsb_alloc_load $SRC/daemon/alloc_load.cc
+g++ -O2 -std=c++17 -Wall -pthread -o $PKG/gsb_mock_kube $SRC/daemon/mock_kube.cc
 echo "built $PKG/gsbd"
 if [ -f oracle/Makefile ]; then make -s -C oracle; fi

@@ -141,6 +141,7 @@ class AllocateCtx(C.Structure):
         ("slices", C.c_uint32),
         ("unit_gib", C.c_int32),
         ("disable_cgpu_isolation", C.c_int32),
+        ("pods_unique", C.c_int32),
     ]
 
 

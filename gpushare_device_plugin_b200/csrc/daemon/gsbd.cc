@@ -34,6 +34,7 @@
 #include <sstream>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../../include/gpushare_b200.h"
@@ -288,11 +289,65 @@ uint64_t quantity_value(const json::Value &q) {
 struct PodRec {
   std::string name, ns, uid;
 };
+// The pending-pod table gsb_allocate reads. Rows keep the order in which the apiserver listed (then streamed)
+// them; the strings a gsb_pod points at live in heap records that never move, so an upsert touches one row.
 struct PodTable {
-  std::vector<PodRec> recs;
+  std::vector<std::unique_ptr<PodRec>> recs;
   std::vector<gsb_pod> pods;
+  std::unordered_map<std::string, size_t> by_uid;  // live rows only
+  size_t dead = 0;      // rows deleted by a watch event: on_node = 0 makes gsb_allocate skip them entirely
+  bool unique = true;   // no two live rows share a uid (always true for a table the informer maintains)
   std::chrono::steady_clock::time_point stamp;
   bool valid = false;
+
+  void clear() {
+    recs.clear();
+    pods.clear();
+    by_uid.clear();
+    dead = 0;
+    unique = true;
+  }
+  void point(size_t i) {
+    pods[i].name = recs[i]->name.c_str();
+    pods[i].ns = recs[i]->ns.c_str();
+    pods[i].uid = recs[i]->uid.c_str();
+  }
+  void append(PodRec &&r, const gsb_pod &g) {
+    recs.emplace_back(new PodRec(std::move(r)));
+    pods.push_back(g);
+    point(recs.size() - 1);
+    if (!by_uid.emplace(recs.back()->uid, recs.size() - 1).second) unique = false;  // a LIST that repeats a uid
+  }
+  void upsert(PodRec &&r, const gsb_pod &g) {
+    auto it = by_uid.find(r.uid);
+    if (it == by_uid.end()) return append(std::move(r), g);
+    *recs[it->second] = std::move(r);
+    pods[it->second] = g;
+    point(it->second);
+  }
+  void remove(const std::string &uid) {
+    auto it = by_uid.find(uid);
+    if (it == by_uid.end()) return;
+    pods[it->second].on_node = 0;
+    by_uid.erase(it);
+    if (++dead > 64 && dead * 4 > recs.size()) compact();
+  }
+  void compact() {  // drop the tombstones, keeping the order of the live rows
+    size_t w = 0;
+    for (size_t i = 0; i < recs.size(); i++) {
+      auto it = by_uid.find(recs[i]->uid);
+      if (it == by_uid.end() || it->second != i) continue;
+      if (w != i) {
+        recs[w] = std::move(recs[i]);
+        pods[w] = pods[i];
+        it->second = w;
+      }
+      w++;
+    }
+    recs.resize(w);
+    pods.resize(w);
+    dead = 0;
+  }
 };
 
 bool atoi_strict(const std::string &s, long long *out) {  // strconv.Atoi
@@ -350,21 +405,14 @@ void pod_row(const json::Value &p, const std::string &node, PodRec *r, gsb_pod *
   g->on_node = nn && nn->str() == node;
 }
 
-void fix_pointers(PodTable *t) {  // only after recs stopped changing
-  for (size_t i = 0; i < t->recs.size(); i++) {
-    t->pods[i].name = t->recs[i].name.c_str();
-    t->pods[i].ns = t->recs[i].ns.c_str();
-    t->pods[i].uid = t->recs[i].uid.c_str();
-  }
-}
-
 // v1.PodList JSON -> table; `pending_only` = the kubelet path's phase filter (podmanager.go:101-123)
 void build_table(const json::Value &list, const std::string &node, bool pending_only, PodTable *t) {
-  t->recs.clear();
-  t->pods.clear();
+  t->clear();
   const json::Value *items = list.get("items");
   if (!items || items->type != json::Value::Array) return;
   t->recs.reserve(items->arr.size());
+  t->pods.reserve(items->arr.size());
+  t->by_uid.reserve(items->arr.size() * 2);
   for (const json::Value &p : items->arr) {
     if (pending_only) {
       const json::Value *ph = p.path({"status", "phase"});
@@ -373,10 +421,8 @@ void build_table(const json::Value &list, const std::string &node, bool pending_
     PodRec r;
     gsb_pod g;
     pod_row(p, node, &r, &g);
-    t->recs.push_back(std::move(r));
-    t->pods.push_back(g);
+    t->append(std::move(r), g);
   }
-  fix_pointers(t);
 }
 
 // ---------------------------------------------------------------- the plugin (server.go)
@@ -700,17 +746,9 @@ class Plugin {
     gsb_pod g;
     pod_row(obj, kube_->node_name, &r, &g);
     std::lock_guard<std::mutex> lk(amu_);
-    size_t at = table_.recs.size();
-    for (size_t i = 0; i < table_.recs.size(); i++)
-      if (table_.recs[i].uid == r.uid) {
-        at = i;
-        break;
-      }
     if (type == "DELETED") {
-      if (at < table_.recs.size()) {
-        table_.recs.erase(table_.recs.begin() + (long)at);
-        table_.pods.erase(table_.pods.begin() + (long)at);
-      }
+      claimed_.erase(r.uid);
+      table_.remove(r.uid);
     } else if (type == "ADDED" || type == "MODIFIED") {
       // a pod this daemon has claimed (PATCH possibly still in flight) stays hidden until the apiserver's copy
       // itself stops saying assigned == "false"
@@ -719,17 +757,10 @@ class Plugin {
         if (g.has_assigned && !g.assigned_is_false) claimed_.erase(c);
         else g.assigned_is_false = 0;
       }
-      if (at < table_.recs.size()) {
-        table_.recs[at] = std::move(r);
-        table_.pods[at] = g;
-      } else {
-        table_.recs.push_back(std::move(r));
-        table_.pods.push_back(g);
-      }
+      table_.upsert(std::move(r), g);
     } else {
-      return;  // BOOKMARK / ERROR: nothing to apply (an ERROR ends the stream on the server side)
+      return;  // BOOKMARK: nothing to apply
     }
-    fix_pointers(&table_);
     table_.stamp = std::chrono::steady_clock::now();
   }
 
@@ -782,6 +813,7 @@ class Plugin {
   int decide(const std::string &req, std::string *resp, int32_t *pod_index, uint32_t *pod_req) {
     resp->resize(1 << 16);
     size_t n = 0;
+    actx_.pods_unique = table_.unique;  // a uid-keyed table: podmanager.go's dedupe would be a no-op
     const int kind = gsb_allocate(&actx_, table_.pods.data(), (uint32_t)table_.pods.size(), (const uint8_t *)req.data(),
                                   req.size(), (uint8_t *)&(*resp)[0], resp->size(), &n, pod_index, pod_req);
     resp->resize(kind > 0 ? n : 0);
@@ -824,10 +856,10 @@ class Plugin {
       }
       VLOG(1, "RequestPodGPUs: %u", pod_req);
       if (kind == GSB_ALLOC_MATCHED) {
-        name = table_.recs[pidx].name;
-        ns = table_.recs[pidx].ns;
+        name = table_.recs[pidx]->name;
+        ns = table_.recs[pidx]->ns;
         table_.pods[pidx].assigned_is_false = 0;  // claimed: hidden from the next request
-        claimed_.insert(table_.recs[pidx].uid);
+        claimed_.insert(table_.recs[pidx]->uid);
       }
     }
     if (kind == GSB_ALLOC_MATCHED) {

@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <functional>
@@ -385,9 +386,51 @@ class Call {
 typedef std::function<int(Call &, const std::string &)> Handler;
 
 // state that outlives the Server object for as long as any connection thread still runs
+// Elastic worker pool for the RPC handlers: a call never waits behind another one (a streaming handler such as
+// ListAndWatch occupies its worker for the life of the stream), but unary calls reuse parked threads instead of
+// paying a thread creation + teardown each. A worker with nothing to do for 30 s exits.
+class WorkerPool : public std::enable_shared_from_this<WorkerPool> {
+ public:
+  void submit(std::function<void()> fn) {
+    std::unique_lock<std::mutex> lk(mu_);
+    q_.push_back(std::move(fn));
+    if (q_.size() > (size_t)idle_) {
+      auto self = shared_from_this();
+      lk.unlock();
+      std::thread([self] { self->run(); }).detach();
+    } else {
+      cv_.notify_one();
+    }
+  }
+
+ private:
+  void run() {
+    std::unique_lock<std::mutex> lk(mu_);
+    for (;;) {
+      if (q_.empty()) {
+        idle_++;
+        const bool got = cv_.wait_for(lk, std::chrono::seconds(30), [this] { return !q_.empty(); });
+        idle_--;
+        if (!got) return;
+      }
+      std::function<void()> fn = std::move(q_.front());
+      q_.pop_front();
+      lk.unlock();
+      fn();
+      fn = nullptr;  // drop the captures (connection, stream) before parking
+      lk.lock();
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<std::function<void()>> q_;
+  int idle_ = 0;
+};
+
 struct Shared {
   std::map<std::string, Handler> handlers;
   std::atomic<bool> stopping{false};
+  std::shared_ptr<WorkerPool> pool = std::make_shared<WorkerPool>();
 };
 
 class Connection : public std::enable_shared_from_this<Connection> {
@@ -566,7 +609,7 @@ class Connection : public std::enable_shared_from_this<Connection> {
 
   void dispatch(std::shared_ptr<Stream> s) {
     auto self = shared_from_this();
-    std::thread([self, s] {
+    sh_->pool->submit([self, s] {
       int status = 12;  // UNIMPLEMENTED
       std::string msg;
       bool ok_msg = false;
@@ -587,7 +630,7 @@ class Connection : public std::enable_shared_from_this<Connection> {
         status = it->second(call, msg);
       }
       self->finish(s, status);
-    }).detach();
+    });
   }
 
   bool send_headers_locked(Stream *s) {  // response HEADERS (wmu_ not held; sequence guarded by caller being the only writer of s)

@@ -88,35 +88,7 @@ int main(int argc, char **argv) {
       printf("INVALID\n");
       return 1;
     }
-    std::function<void(const json::Value &)> emit = [&](const json::Value &x) {
-      auto str = [&](const std::string &t) {
-        out.push_back('"');
-        for (unsigned char c : t) {
-          char e[8];
-          if (c == '"' || c == '\\') { out.push_back('\\'); out.push_back((char)c); }
-          else if (c < 0x20) { snprintf(e, sizeof e, "\\u%04x", c); out += e; }
-          else out.push_back((char)c);
-        }
-        out.push_back('"');
-      };
-      switch (x.type) {
-        case json::Value::Null: out += "null"; break;
-        case json::Value::Bool: out += x.b ? "true" : "false"; break;
-        case json::Value::Number: out += x.s; break;
-        case json::Value::String: str(x.s); break;
-        case json::Value::Array:
-          out.push_back('[');
-          for (size_t i = 0; i < x.arr.size(); i++) { if (i) out.push_back(','); emit(x.arr[i]); }
-          out.push_back(']');
-          break;
-        case json::Value::Object:
-          out.push_back('{');
-          for (size_t i = 0; i < x.obj.size(); i++) { if (i) out.push_back(','); str(x.obj[i].first); out.push_back(':'); emit(x.obj[i].second); }
-          out.push_back('}');
-          break;
-      }
-    };
-    emit(v);
+    json::dump(v, &out);
     fwrite(out.data(), 1, out.size(), stdout);
     return 0;
   }

@@ -213,4 +213,49 @@ class Parser {
 
 inline bool parse(const std::string &text, Value *out) { return Parser(text).parse(out); }
 
+// Compact serialisation (no whitespace, keys in stored order, numbers as their original text).
+inline void dump_string(const std::string &t, std::string *out) {
+  out->push_back('"');
+  for (unsigned char c : t) {
+    if (c == '"' || c == '\\') {
+      out->push_back('\\');
+      out->push_back((char)c);
+    } else if (c < 0x20) {
+      char e[8];
+      snprintf(e, sizeof e, "\\u%04x", c);
+      *out += e;
+    } else {
+      out->push_back((char)c);
+    }
+  }
+  out->push_back('"');
+}
+
+inline void dump(const Value &x, std::string *out) {
+  switch (x.type) {
+    case Value::Null: *out += "null"; break;
+    case Value::Bool: *out += x.b ? "true" : "false"; break;
+    case Value::Number: *out += x.s; break;
+    case Value::String: dump_string(x.s, out); break;
+    case Value::Array:
+      out->push_back('[');
+      for (size_t i = 0; i < x.arr.size(); i++) {
+        if (i) out->push_back(',');
+        dump(x.arr[i], out);
+      }
+      out->push_back(']');
+      break;
+    case Value::Object:
+      out->push_back('{');
+      for (size_t i = 0; i < x.obj.size(); i++) {
+        if (i) out->push_back(',');
+        dump_string(x.obj[i].first, out);
+        out->push_back(':');
+        dump(x.obj[i].second, out);
+      }
+      out->push_back('}');
+      break;
+  }
+}
+
 }  // namespace json

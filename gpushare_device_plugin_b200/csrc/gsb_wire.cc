@@ -335,43 +335,69 @@ int gsb_allocate(const gsb_allocate_ctx *ctx, const gsb_pod *pods, uint32_t n_po
   for (uint64_t n : per_container) pod_req += n;
   if (pod_req_gpu) *pod_req_gpu = (uint32_t)pod_req;
 
-  // getPendingPodsInNode's dedupe by UID (podmanager.go:162-212), then the candidate filter
+  // getPendingPodsInNode's dedupe by UID (podmanager.go:162-212: the first pod of a UID wins, whether or not it
+  // is a candidate), then the candidate filter. The set is an open-addressing table of (hash, index) kept
+  // across calls on this thread; a hash hit is confirmed on the bytes, so the result is exact.
   std::vector<uint32_t> cand;
-  {
-    std::unordered_set<std::string_view> seen;
-    seen.reserve(n_pods * 2);
+  if (ctx->pods_unique) {
+    cand.reserve(n_pods);
+    for (uint32_t i = 0; i < n_pods; i++)
+      if (pods[i].on_node && is_assumed(pods[i])) cand.push_back(i);
+  } else {
+    thread_local std::vector<uint64_t> slots;  // hash << 32 | (index + 1); 0 = empty
+    size_t cap = 64;
+    while (cap < (size_t)n_pods * 2) cap <<= 1;
+    slots.assign(cap, 0);
+    cand.reserve(n_pods);
     for (uint32_t i = 0; i < n_pods; i++) {
       if (!pods[i].on_node) continue;
-      if (!seen.insert(std::string_view(pods[i].uid ? pods[i].uid : "")).second) continue;
+      const char *u = pods[i].uid ? pods[i].uid : "";
+      uint64_t h = 1469598103934665603ull;  // FNV-1a
+      size_t len = 0;
+      for (; u[len]; len++) h = (h ^ (unsigned char)u[len]) * 1099511628211ull;
+      const uint32_t tag = (uint32_t)(h >> 32) | 1u;
+      size_t at = (size_t)h & (cap - 1);
+      bool dup = false;
+      while (slots[at]) {
+        if ((uint32_t)(slots[at] >> 32) == tag) {
+          const char *o = pods[(uint32_t)slots[at] - 1].uid;
+          if (strcmp(o ? o : "", u) == 0) {
+            dup = true;
+            break;
+          }
+        }
+        at = (at + 1) & (cap - 1);
+      }
+      if (dup) continue;
+      slots[at] = (uint64_t)tag << 32 | (uint64_t)(i + 1);
       if (is_assumed(pods[i])) cand.push_back(i);
     }
   }
-  // makePodOrderdByAge: sort.Sort with Less = (t[i] <= t[j])  (podmanager.go:241-262). Go 1.10's
-  // sort.Sort on <= 12 elements is one ShellSort pass with gap 6 followed by insertionSort; with the
-  // non-strict Less that is what decides the order of pods with EQUAL assume-times, so it is
-  // restated exactly. Beyond 12 elements Go's pivot code (standard library, not in the reference
-  // tree) decides tie order; the insertion rule alone is used there (deviations) — and an
-  // insertion sort with `<=` is the same permutation as sorting by (time ascending, arrival
-  // DEscending), which is what std::sort computes in O(n log n).
-  auto less = [&](size_t i, size_t j) { return pods[cand[i]].assume_time <= pods[cand[j]].assume_time; };
+  // makePodOrderdByAge: sort.Sort with Less = (t[i] <= t[j])  (podmanager.go:241-262), then the first pod in
+  // that order whose request equals this one (allocate.go:78-88). Go 1.10's sort.Sort on <= 12 elements is one
+  // ShellSort pass with gap 6 followed by insertionSort; with the non-strict Less that is what decides the
+  // order of pods with EQUAL assume-times, so it is restated exactly. Beyond 12 elements Go's pivot code
+  // (standard library, not in the reference tree) decides tie order; the insertion rule alone is used there
+  // (deviations) — an insertion sort with `<=` is the same permutation as sorting by (time
+  // ascending, arrival DEscending), a strict total order, so "first match in sorted order" is simply the
+  // minimum over the matching candidates: one O(n) pass, no sort.
+  int32_t found = -1;
   if (cand.size() <= 12) {
+    auto less = [&](size_t i, size_t j) { return pods[cand[i]].assume_time <= pods[cand[j]].assume_time; };
     if (cand.size() > 1)
       for (size_t i = 6; i < cand.size(); i++)
         if (less(i, i - 6)) std::swap(cand[i], cand[i - 6]);
     for (size_t i = 1; i < cand.size(); i++)
       for (size_t j = i; j > 0 && less(j, j - 1); j--) std::swap(cand[j], cand[j - 1]);
+    for (uint32_t c : cand)
+      if (pods[c].gpu_mem_limit == pod_req) {
+        found = (int32_t)c;
+        break;
+      }
   } else {
-    std::sort(cand.begin(), cand.end(), [&](uint32_t x, uint32_t y) {
-      if (pods[x].assume_time != pods[y].assume_time) return pods[x].assume_time < pods[y].assume_time;
-      return x > y;
-    });
-  }
-
-  int32_t found = -1;
-  for (uint32_t c : cand) {  // allocate.go:78-88
-    if (pods[c].gpu_mem_limit == pod_req) {
-      found = (int32_t)c;
-      break;
+    for (uint32_t c : cand) {  // cand is in arrival order: on equal times the later arrival wins
+      if (pods[c].gpu_mem_limit != pod_req) continue;
+      if (found < 0 || pods[c].assume_time <= pods[found].assume_time) found = (int32_t)c;
     }
   }
 

@@ -86,7 +86,8 @@ class MockKube:
                 self.request.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
 
             def _send(self, code: int, obj, chunked: bool = False):
-                body = json.dumps(obj, separators=(",", ":"), ensure_ascii=not chunked).encode()
+                body = obj if isinstance(obj, bytes) else \
+                    json.dumps(obj, separators=(",", ":"), ensure_ascii=not chunked).encode()
                 if chunked:
                     out = [b"HTTP/1.1 200 OK\r\nContent-Type: application/json\r\nTransfer-Encoding: chunked\r\n\r\n"]
                     for i in range(0, len(body), 1000):  # uneven chunks that split UTF-8 sequences and tokens
@@ -152,9 +153,9 @@ class MockKube:
             def _watch(self, sel, since):
                 """GET /api/v1/pods?watch=true: chunked stream of {"type","object"} lines from resourceVersion `since`.
                 A pod that stops matching the field selector is reported as DELETED, as the apiserver does."""
-                def matches(p):
-                    return (("spec.nodeName" not in sel or p["spec"].get("nodeName") == sel["spec.nodeName"]) and
-                            ("status.phase" not in sel or p["status"].get("phase") == sel["status.phase"]))
+                def matches(node, phase):
+                    return (("spec.nodeName" not in sel or node == sel["spec.nodeName"]) and
+                            ("status.phase" not in sel or phase == sel["status.phase"]))
                 try:
                     self.wfile.write(b"HTTP/1.1 200 OK\r\nContent-Type: application/json\r\nTransfer-Encoding: chunked\r\n\r\n")
                     self.wfile.flush()
@@ -167,18 +168,18 @@ class MockKube:
                                 break
                             batch = mock.events[cursor:]
                             cursor = len(mock.events)
-                        for rv, etype, pod in batch:
+                        for rv, etype, body, node, phase in batch:
                             if rv <= since:
                                 continue
                             if etype == "ERROR":  # e.g. 410 Gone: one Status line, then the server ends the stream
-                                line = json.dumps({"type": "ERROR", "object": pod}, separators=(",", ":")).encode() + b"\n"
+                                line = b'{"type":"ERROR","object":' + body + b"}\n"
                                 self.wfile.write(b"%x\r\n" % len(line) + line + b"\r\n0\r\n\r\n")
                                 self.wfile.flush()
                                 self.close_connection = True
                                 return
-                            if not matches(pod):
+                            if not matches(node, phase):
                                 etype = "DELETED"
-                            line = json.dumps({"type": etype, "object": pod}, separators=(",", ":")).encode() + b"\n"
+                            line = b'{"type":"' + etype.encode() + b'","object":' + body + b"}\n"
                             self.wfile.write(b"%x\r\n" % len(line) + line + b"\r\n")
                             self.wfile.flush()
                     self.wfile.write(b"0\r\n\r\n")
@@ -211,8 +212,7 @@ class MockKube:
                             return self._status(404, f'pods "{parts[5]}" not found')
                         p["metadata"].setdefault("annotations", {}).update(
                             (patch.get("metadata") or {}).get("annotations") or {})
-                        mock._emit("MODIFIED", p)
-                        return self._send(200, p)
+                        return self._send(200, mock._emit("MODIFIED", p))
                 self._status(404, "not found")
 
         class Server(ThreadingHTTPServer):
@@ -235,13 +235,16 @@ class MockKube:
         self.thread = threading.Thread(target=self.httpd.serve_forever, name="mock-kube", daemon=True)
         self.thread.start()
 
-    def _emit(self, etype: str, pod: dict):
-        """caller holds self.lock"""
+    def _emit(self, etype: str, pod: dict) -> bytes:
+        """caller holds self.lock; the object is serialised once, for the event log and for the caller's response"""
         self.rv += 1
         pod.setdefault("metadata", {})["resourceVersion"] = str(self.rv)
+        body = json.dumps(pod, separators=(",", ":")).encode()
         with self.watch_cv:
-            self.events.append((self.rv, etype, copy.deepcopy(pod)))
+            self.events.append((self.rv, etype, body, (pod.get("spec") or {}).get("nodeName"),
+                                (pod.get("status") or {}).get("phase")))
             self.watch_cv.notify_all()
+        return body
 
     def add_pod(self, pod: dict):
         with self.lock:
@@ -263,7 +266,7 @@ class MockKube:
             status = {"kind": "Status", "apiVersion": "v1", "status": "Failure", "reason": "Expired", "code": 410,
                       "message": "too old resource version"}
             with self.watch_cv:
-                self.events.append((self.rv, "ERROR", status))
+                self.events.append((self.rv, "ERROR", json.dumps(status).encode(), None, None))
                 self.watch_cv.notify_all()
 
     def fail_next_patch(self, message: str, times: int = 1):

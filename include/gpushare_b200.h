@@ -262,6 +262,9 @@ typedef struct gsb_allocate_ctx {
   uint32_t slices;          /* getGPUMemory() */
   int32_t unit_gib;         /* metric == GiBPrefix */
   int32_t disable_cgpu_isolation;
+  int32_t pods_unique;      /* caller guarantees that no two on-node pods share a uid (a table keyed by uid):
+                               getPendingPodsInNode's dedupe (podmanager.go:162-212) is then a no-op and is skipped.
+                               0 = dedupe as the reference does */
 } gsb_allocate_ctx;
 
 enum {

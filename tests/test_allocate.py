@@ -25,8 +25,10 @@ def ids(n, g=0):
     return [wo.generateFakeDeviceID(UUIDS[g], j) for j in range(n)]
 
 
-def product_allocate(container_requests, pods, devNameMap, slices=179, unit_gib=True, cgpu=False, node=NODE):
+def product_allocate(container_requests, pods, devNameMap, slices=179, unit_gib=True, cgpu=False, node=NODE,
+                     pods_unique=False):
     actx = AllocateContext(devNameMap, slices, unit_gib, cgpu)
+    actx.ctx.pods_unique = 1 if pods_unique else 0
     req = wo.marshal_AllocateRequest(container_requests)
     table, _keep = pod_table(pods, node)
     buf = C.create_string_buffer(1 << 16)
@@ -162,6 +164,28 @@ def _mk(i, mem, idx, t, assigned, node, has_t):
 def test_randomized_clusters_match_oracle(pods, reqs, one_gpu, cgpu):
     dev = {UUIDS[0]: 5} if one_gpu else MINORS8
     both([ids(n) for n in reqs], pods, dev, cgpu=cgpu)
+
+
+@settings(max_examples=150, deadline=None)
+@given(pods=st.lists(pod_strategy, min_size=13, max_size=60), reqs=st.lists(st.integers(0, 4), max_size=3),
+       one_gpu=st.booleans())
+def test_large_clusters_match_oracle(pods, reqs, one_gpu):
+    """> 12 candidates: the one-pass selection (no sort) against the oracle's full sort, duplicate UIDs and
+    tied assume-times included."""
+    both([ids(n) for n in reqs], pods, {UUIDS[0]: 5} if one_gpu else MINORS8)
+
+
+@settings(max_examples=150, deadline=None)
+@given(pods=st.lists(pod_strategy, max_size=40, unique_by=lambda p: p["metadata"]["uid"]),
+       reqs=st.lists(st.integers(0, 4), max_size=3))
+def test_pods_unique_hint_changes_nothing_on_a_uid_keyed_table(pods, reqs):
+    """gsb_allocate_ctx.pods_unique skips podmanager.go's dedupe; on a table without repeated UIDs the decision and
+    the response bytes are the same either way."""
+    cr = [ids(n) for n in reqs]
+    a = product_allocate(cr, pods, MINORS8)
+    b = product_allocate(cr, pods, MINORS8, pods_unique=True)
+    assert a == b
+    both(cr, pods, MINORS8)
 
 
 def test_malformed_request_is_rejected_not_guessed():

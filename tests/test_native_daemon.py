@@ -416,3 +416,32 @@ def test_reference_exact_mode_lists_on_every_call(world):
         assert wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, req))[0]["ALIYUN_COM_GPU_MEM_IDX"] == str(i // 8)
     assert _count(world, "GET", "/api/v1/pods?fieldSelector") == 10 and world.kube.watches_served == 0
     ch.close()
+
+
+def test_informer_table_survives_churn(world):
+    """Deletes are tombstones that get compacted away; a uid that comes back is a fresh row; order-sensitive
+    decisions (oldest assume time first) stay right through all of it."""
+    d = world.start("--pod-cache-ttl", "0")
+    ch = d.channel()
+    deadline = time.time() + 5
+    while world.kube.watches_served == 0 and time.time() < deadline:
+        time.sleep(0.05)
+    base = 1_600_000_000_000_000_000  # older than every config-4 pod
+    for i in range(100, 200):  # 100 extra pods asking for 3 GiB on GPU 7
+        world.kube.add_pod(make_pod(i, NODE, gpu_mem=3, idx=7, assume_time=base + i))
+    for i in range(100, 190):  # 90 of them go away again: enough tombstones to trigger a compaction
+        world.kube.delete_pod(f"pod-{i}")
+    world.kube.add_pod(make_pod(150, NODE, gpu_mem=3, idx=6, assume_time=base))  # same uid as a deleted pod, now oldest
+    time.sleep(0.5)
+    lists0 = _count(world, "GET", "/api/v1/pods?fieldSelector")
+    three = wo.marshal_AllocateRequest([["a", "b", "c"]])
+    got = [wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, three))[0]["ALIYUN_COM_GPU_MEM_IDX"] for _ in range(11)]
+    assert got == ["6"] + ["7"] * 10  # the returned pod first, then pod-190..199 by age
+    assert _count(world, "GET", "/api/v1/pods?fieldSelector") == lists0
+    patched = [r[1].rsplit("/", 1)[1] for r in world.kube.requests if r[0] == "PATCH" and "/pods/" in r[1]]
+    assert patched == ["pod-150"] + [f"pod-{i}" for i in range(190, 200)]
+    # the original 64 pods are untouched by the churn
+    four = wo.marshal_AllocateRequest([["a", "b", "c", "d"]])
+    for i in range(64):
+        assert wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, four))[0]["ALIYUN_COM_GPU_MEM_IDX"] == str(i // 8)
+    ch.close()
