@@ -691,19 +691,30 @@ class Plugin {
   // stream so the table is current without a LIST per call or per TTL. Optimistic like the TTL cache: a request
   // that finds no candidate still re-LISTs, a failed PATCH forces a resync. Falls back to the TTL cache whenever
   // the watch cannot be established (synced_ == false).
+  // 1 s, 2 s, 4 s ... 64 s between attempts while the apiserver refuses the LIST or the watch (the TTL path serves
+  // meanwhile); a stream that delivered anything resets it
+  void backoff(int *failures) {
+    const int ticks = 20 << std::min(*failures, 6);
+    if (*failures < 6) (*failures)++;
+    const bool resync_at_entry = resync_;  // a resync requested DURING the wait cuts it short, a pending one does not
+    for (int i = 0; i < ticks && !stopping_ && (resync_at_entry || !resync_); i++)
+      std::this_thread::sleep_for(std::chrono::milliseconds(50));
+  }
   void informer() {
+    int failures = 0;
     const std::string sel = "fieldSelector=spec.nodeName%3D" + kube_->node_name + "%2Cstatus.phase%3DPending";
     while (!stopping_) {
       std::string err, rv;
       json::Value list;
       if (!kube_->call("GET", "/api/v1/pods?" + sel, "", "", &list, &err)) {
-        for (int i = 0; i < 20 && !stopping_; i++) std::this_thread::sleep_for(std::chrono::milliseconds(50));
+        backoff(&failures);
         continue;
       }
       if (const json::Value *v = list.path({"metadata", "resourceVersion"})) rv = v->str();
       {
         std::lock_guard<std::mutex> lk(amu_);
         build_table(list, kube_->node_name, false, &table_);
+        reconcile_claims();
         table_.stamp = std::chrono::steady_clock::now();
         table_.valid = true;
         resync_ = false;
@@ -711,7 +722,7 @@ class Plugin {
       std::unique_ptr<http::Conn> conn = kube_->api.open_stream("/api/v1/pods?watch=true&" + sel + "&resourceVersion=" + rv, 300, &err);
       if (!conn) {
         synced_ = false;
-        for (int i = 0; i < 20 && !stopping_; i++) std::this_thread::sleep_for(std::chrono::milliseconds(50));
+        backoff(&failures);
         continue;
       }
       {
@@ -721,6 +732,8 @@ class Plugin {
         if (stopping_ || resync_) conn->abort();
       }
       int status = 0;
+      size_t events = 0;
+      const auto opened = std::chrono::steady_clock::now();
       conn->read_stream(&status, [&](int st) { synced_ = st == 200; },  // stream is up: table kept current from here on
                         [&](const std::string &line) -> bool {
         if (status >= 400) return false;
@@ -730,6 +743,7 @@ class Plugin {
         if (!type || !obj) return true;
         if (type->str() == "ERROR") return false;  // e.g. 410 Gone (resourceVersion too old): start over from a LIST
         apply_event(type->str(), *obj);
+        events++;
         return !stopping_ && !resync_;
       });
       {
@@ -737,6 +751,11 @@ class Plugin {
         watch_conn_ = nullptr;
       }
       synced_ = false;  // until the next LIST + watch are in place the TTL path answers
+      // a stream that was refused (4xx), never answered, or was closed at once without delivering anything counts as
+      // a failure; one that worked resets the backoff
+      const bool worked = status == 200 && (events > 0 || std::chrono::steady_clock::now() - opened > std::chrono::seconds(5));
+      if (worked || resync_) failures = 0;
+      else backoff(&failures);
     }
     synced_ = false;
   }
@@ -801,9 +820,29 @@ class Plugin {
       }
     }
     build_table(list, kube_->node_name, pending_only, &table_);
+    reconcile_claims();
     table_.stamp = std::chrono::steady_clock::now();
     table_.valid = true;
     return true;
+  }
+  // A LIST is a snapshot that can pre-date a PATCH still in flight (the lock is not held across the PATCH): a pod
+  // claimed here stays hidden in every rebuilt table until the apiserver's own copy stops saying assigned=="false".
+  // Caller holds amu_.
+  void reconcile_claims() {
+    for (auto it = claimed_.begin(); it != claimed_.end();) {
+      auto row = table_.by_uid.find(*it);
+      if (row == table_.by_uid.end()) {  // no longer a pending pod of this node
+        it = claimed_.erase(it);
+        continue;
+      }
+      gsb_pod &g = table_.pods[row->second];
+      if (g.has_assigned && !g.assigned_is_false) {  // confirmed
+        it = claimed_.erase(it);
+        continue;
+      }
+      g.assigned_is_false = 0;
+      ++it;
+    }
   }
   bool cache_fresh() const {
     if (synced_ && table_.valid && !resync_) return true;  // kept current by the watch stream
@@ -830,7 +869,7 @@ class Plugin {
 
   std::string allocate(const std::string &req) {  // allocate.go:42-198
     VLOG(1, "----Allocating GPU for gpu mem is started----");
-    std::string resp, name, ns, err;
+    std::string resp, name, ns, err, claimed_uid;
     int32_t pidx = -1;
     uint32_t pod_req = 0;
     int kind;
@@ -859,7 +898,8 @@ class Plugin {
         name = table_.recs[pidx]->name;
         ns = table_.recs[pidx]->ns;
         table_.pods[pidx].assigned_is_false = 0;  // claimed: hidden from the next request
-        claimed_.insert(table_.recs[pidx]->uid);
+        claimed_uid = table_.recs[pidx]->uid;
+        claimed_.insert(claimed_uid);
       }
     }
     if (kind == GSB_ALLOC_MATCHED) {
@@ -876,7 +916,7 @@ class Plugin {
         WARN("Failed due to %s", err.c_str());
         std::lock_guard<std::mutex> lk(amu_);
         table_.valid = false;  // drop the cache: it no longer reflects the apiserver
-        claimed_.clear();
+        claimed_.erase(claimed_uid);  // this pod is a candidate again; other claims in flight stay
         resync_ = true;        // and make the informer start over from a fresh LIST
         {
           std::lock_guard<std::mutex> wl(wmu_);

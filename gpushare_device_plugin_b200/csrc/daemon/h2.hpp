@@ -431,6 +431,11 @@ struct Shared {
   std::map<std::string, Handler> handlers;
   std::atomic<bool> stopping{false};
   std::shared_ptr<WorkerPool> pool = std::make_shared<WorkerPool>();
+  // handlers currently executing: Server::stop() returns only once they have all returned, so whatever the
+  // handlers capture (the plugin object) can be destroyed after it
+  std::mutex active_mu;
+  std::condition_variable active_cv;
+  int active = 0;
 };
 
 class Connection : public std::enable_shared_from_this<Connection> {
@@ -626,8 +631,21 @@ class Connection : public std::enable_shared_from_this<Connection> {
       if (!ok_msg) {
         status = 13;  // INTERNAL: compressed or truncated message
       } else if (it != self->sh_->handlers.end()) {
-        Call call(self, s);
-        status = it->second(call, msg);
+        {
+          std::lock_guard<std::mutex> lk(self->sh_->active_mu);
+          self->sh_->active++;
+        }
+        if (!self->sh_->stopping) {
+          Call call(self, s);
+          status = it->second(call, msg);
+        } else {
+          status = 14;  // UNAVAILABLE: the server is going away
+        }
+        {
+          std::lock_guard<std::mutex> lk(self->sh_->active_mu);
+          self->sh_->active--;
+          self->sh_->active_cv.notify_all();
+        }
       }
       self->finish(s, status);
     });
@@ -719,9 +737,9 @@ class Server {
     if (::bind(lfd_, (sockaddr *)&a, sizeof a) < 0) return fail(err, "bind");
     if (::listen(lfd_, 1024) < 0) return fail(err, "listen");
     sh_->stopping = false;
-    acceptor_ = std::thread([this] {
+    acceptor_ = std::thread([this, lfd = lfd_] {  // the listener fd by value: stop() owns the member
       for (;;) {
-        const int fd = ::accept4(lfd_, nullptr, nullptr, SOCK_CLOEXEC);
+        const int fd = ::accept4(lfd, nullptr, nullptr, SOCK_CLOEXEC);
         if (fd < 0) {
           if (errno == EINTR) continue;
           return;  // listener closed
@@ -743,16 +761,21 @@ class Server {
   // grpc.Server.Stop(): close the listener and every connection (server.go:141-143)
   void stop() {
     sh_->stopping = true;
+    if (lfd_ >= 0) ::shutdown(lfd_, SHUT_RDWR);  // wakes accept4 with an error; the fd stays ours until it has returned
+    if (acceptor_.joinable()) acceptor_.join();
     if (lfd_ >= 0) {
-      ::shutdown(lfd_, SHUT_RDWR);
       ::close(lfd_);
       lfd_ = -1;
     }
-    if (acceptor_.joinable()) acceptor_.join();
-    std::lock_guard<std::mutex> lk(mu_);
-    for (auto &w : conns_)
-      if (auto c = w.lock()) c->go_away();
-    conns_.clear();
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      for (auto &w : conns_)
+        if (auto c = w.lock()) c->go_away();
+      conns_.clear();
+    }
+    // handlers see their call cancelled (connection gone) and `stopping`; each is bounded by its own timeouts
+    std::unique_lock<std::mutex> lk(sh_->active_mu);
+    sh_->active_cv.wait(lk, [this] { return sh_->active == 0; });
   }
 
   ~Server() { stop(); }

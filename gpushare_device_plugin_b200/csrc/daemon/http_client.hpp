@@ -229,6 +229,13 @@ class Conn {
 
 class Client {
  public:
+  Client() = default;
+  Client(const Client &) = delete;
+  Client &operator=(const Client &) = delete;
+  ~Client() {
+    idle_.clear();
+    if (ctx_) SSL_CTX_free(ctx_);
+  }
   // base_url: http://host:port or https://host:port
   // optional TLS material given as PEM text (kubeconfig *-data fields) or files (client cert for mTLS)
   struct TlsExtra {
@@ -239,6 +246,15 @@ class Client {
     token_ = token;
     timeout_s_ = timeout_s;
     insecure_ = insecure;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      idle_.clear();  // connections made under the previous configuration
+    }
+    if (ctx_) {
+      SSL_CTX_free(ctx_);
+      ctx_ = nullptr;
+    }
+    tls_ = false;
     std::string rest;
     if (base_url.compare(0, 8, "https://") == 0) {
       tls_ = true;

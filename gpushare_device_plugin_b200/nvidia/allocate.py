@@ -65,11 +65,14 @@ class PendingPodCache:
     every Allocate while holding the plugin lock. This keeps the last LIST and its gsb_pod table for
     `ttl` seconds. It is optimistic, never authoritative: a request that finds no candidate in a
     cached table re-LISTs and is decided again on fresh data, a failed PATCH drops the cache, and a pod
-    claimed by one request is hidden from the next (its PATCH runs outside the lock). ttl == 0
-    restores the reference's LIST-per-call exactly."""
+    claimed by one request is hidden from the next (its PATCH runs outside the lock) — in every table
+    rebuilt from a later LIST too, until the apiserver's own copy stops saying assigned == "false": a LIST
+    is a snapshot that can pre-date a PATCH still in flight. ttl == 0 LISTs on every call like the
+    reference."""
 
     def __init__(self, ttl: float):
         self.ttl = ttl
+        self.claimed: set = set()  # uids claimed here and not yet confirmed by a LIST
         self.pods: Optional[List[dict]] = None
         self.table = None
         self._keep = None
@@ -82,13 +85,23 @@ class PendingPodCache:
         self.pods = podmanager.getPendingPodsInNode(plugin.queryKubelet, plugin.kubeletClient)
         self.table, self._keep = pod_table(self.pods, podmanager.nodeName)
         self.stamp = time.monotonic()
+        if self.claimed:  # reconcile: keep in-flight claims hidden, forget confirmed / departed ones
+            still = set()
+            for i, p in enumerate(self.pods):
+                uid = (p.get("metadata") or {}).get("uid") or ""
+                if uid in self.claimed and self.table[i].has_assigned and self.table[i].assigned_is_false:
+                    self.table[i].assigned_is_false = 0
+                    still.add(uid)
+            self.claimed = still
 
-    def claim(self, i: int):
+    def claim(self, i: int) -> str:
         self.table[i].assigned_is_false = 0  # no longer a candidate (isGPUMemoryAssumedPod)
+        uid = (self.pods[i].get("metadata") or {}).get("uid") or ""
+        self.claimed.add(uid)
+        return uid
 
-    def unclaim(self, i: int):
-        if self.table is not None and i < len(self.table):
-            self.table[i].assigned_is_false = 1
+    def unclaim(self, uid: str):
+        self.claimed.discard(uid)  # the PATCH failed: still unassigned on the apiserver, a candidate again
 
     def drop(self):
         self.pods = self.table = self._keep = None
@@ -129,8 +142,7 @@ def allocate(plugin, req: bytes) -> bytes:
         pod = None
         if kind == _abi.GSB_ALLOC_MATCHED:
             pod = cache.pods[pidx]
-            cache.claim(pidx)
-            pods_ref = cache.pods
+            claimed_uid = cache.claim(pidx)
     if kind == _abi.GSB_ALLOC_MATCHED:
         md = pod["metadata"]
         log.info("Found Assumed GPU shared Pod %s in ns %s with GPU Memory %d", md.get("name"), md.get("namespace"),
@@ -150,8 +162,7 @@ def allocate(plugin, req: bytes) -> bytes:
         if err is not None:
             log.warning("Failed due to %s", err)
             with plugin.lock:
-                if cache.pods is pods_ref:
-                    cache.unclaim(pidx)  # still unassigned on the apiserver
+                cache.unclaim(claimed_uid)
                 cache.drop()
             return buildErrResponse(actx, req)
         log.info("----Allocating GPU for gpu mem for %s is ended----", md.get("name"))

@@ -66,6 +66,7 @@ class MockKube:
         self.closing = False
         self.watches_served = 0
         self.enable_watch = True
+        self.patch_delay = 0.0
         self.lock = threading.Lock()
         self.nodes: Dict[str, dict] = {node["metadata"]["name"]: node}
         self.pods: Dict[tuple, dict] = {(p["metadata"]["namespace"], p["metadata"]["name"]): p for p in pods}
@@ -191,6 +192,8 @@ class MockKube:
                 u = urllib.parse.urlparse(self.path)
                 parts = [p for p in u.path.split("/") if p]
                 body = self.rfile.read(int(self.headers.get("Content-Length", "0")))
+                if mock.patch_delay:  # a slow apiserver: the write lands this much later than it was sent
+                    threading.Event().wait(mock.patch_delay)  # not time.sleep: tests stub that out
                 with mock.lock:
                     mock.requests.append(("PATCH", self.path, body, self.headers.get("Content-Type")))
                     try:

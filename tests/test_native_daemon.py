@@ -21,7 +21,7 @@ from . import fakes
 from .test_server import Frames, next_frame
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-GSBD = os.path.join(ROOT, "gpushare_device_plugin_b200", "gsbd")
+GSBD = os.environ.get("GSBD_BINARY") or os.path.join(ROOT, "gpushare_device_plugin_b200", "gsbd")  # GSBD_BINARY: a sanitizer build
 KAT = json.load(open(os.path.join(ROOT, "tests", "golden", "wire_kat.json")))
 NODE = "b200-0"
 
@@ -445,3 +445,26 @@ def test_informer_table_survives_churn(world):
     for i in range(64):
         assert wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, four))[0]["ALIYUN_COM_GPU_MEM_IDX"] == str(i // 8)
     ch.close()
+
+
+@pytest.mark.parametrize("mode", [("--pod-informer=false", "--pod-cache-ttl", "0"), ("--pod-cache-ttl", "0"),
+                                  ("--pod-informer=false", "--pod-cache-ttl", "60")])
+def test_a_list_taken_before_a_patch_lands_cannot_hand_out_the_pod_twice(world, mode):
+    """The lock is not held across the PATCH, so a LIST (per call, on TTL expiry, or the informer's) can show a pod
+    as still unassigned while this daemon's PATCH for it is in flight. Claims survive every table rebuild."""
+    world.kube.patch_delay = 0.25
+    d = world.start(*mode)
+    results = []
+
+    def one():
+        ch = d.channel()
+        results.append(wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, wo.marshal_AllocateRequest([["a", "b", "c", "d"]])))[0])
+        ch.close()
+    ts = [threading.Thread(target=one) for _ in range(12)]
+    for t in ts:
+        t.start()
+        time.sleep(0.03)  # staggered: each request decides while the earlier PATCHes are still in flight
+    [t.join(30) for t in ts]
+    assert len(results) == 12 and all(r["ALIYUN_COM_GPU_MEM_IDX"] != "-1" for r in results)
+    patched = [r[1] for r in world.kube.requests if r[0] == "PATCH" and "/pods/" in r[1]]
+    assert len(patched) == 12 and len(set(patched)) == 12

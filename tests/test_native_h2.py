@@ -11,7 +11,7 @@ import grpc
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-BIN = os.path.join(ROOT, "build", "h2_selftest")
+BIN = os.environ.get("H2_SELFTEST_BINARY") or os.path.join(ROOT, "build", "h2_selftest")
 
 pytestmark = pytest.mark.skipif(not os.access(BIN, os.X_OK), reason="build/h2_selftest not built")
 

@@ -305,6 +305,30 @@ def test_concurrent_allocates_never_share_a_pod(world):
     assert len(patched) == 64 and len(set(patched)) == 64  # every pod claimed exactly once
 
 
+@pytest.mark.parametrize("ttl", [0, 60])
+def test_a_list_taken_before_a_patch_lands_cannot_hand_out_the_pod_twice(world, ttl):
+    """The lock is not held across the PATCH, so a later LIST can still show a pod as unassigned while this
+    plugin's PATCH for it is in flight; claims are kept by UID across every table rebuild."""
+    world.kube.patch_delay = 0.25
+    p = world.make(pod_cache_ttl=ttl, max_workers=32)
+    p.Serve(world.kubelet.socket)
+    results = []
+
+    def one():
+        ch = world.kubelet.channel("aliyungpushare.sock")
+        results.append(wo.unmarshal_AllocateResponse(
+            world.kubelet.allocate(ch, wo.marshal_AllocateRequest([["a", "b", "c", "d"]])))[0])
+        ch.close()
+    ts = [threading.Thread(target=one) for _ in range(12)]
+    for t in ts:
+        t.start()
+        threading.Event().wait(0.03)  # staggered: each request decides while earlier PATCHes are in flight
+    [t.join(30) for t in ts]
+    assert len(results) == 12 and all(r["ALIYUN_COM_GPU_MEM_IDX"] != "-1" for r in results)
+    patched = [r[1] for r in world.kube.requests if r[0] == "PATCH" and "/pods/" in r[1]]
+    assert len(patched) == 12 and len(set(patched)) == 12
+
+
 def test_optional_recovery_is_off_by_default_and_flag_gated(world):
     """server.go:180 FIXME: the reference never leaves Unhealthy. Default: a RECOVERED probe event changes
     nothing; with health_recovery_cycles > 0 the GPU's fake devices flip back — but only after a PROBE

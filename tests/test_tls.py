@@ -13,7 +13,7 @@ from gpushare_device_plugin_b200.testing.mock_kube import MockKube, config4_pods
 from oracle import wire_oracle as wo
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-GSBD = os.path.join(ROOT, "gpushare_device_plugin_b200", "gsbd")
+GSBD = os.environ.get("GSBD_BINARY") or os.path.join(ROOT, "gpushare_device_plugin_b200", "gsbd")
 NODE = "b200-0"
 
 
