@@ -468,3 +468,20 @@ def test_a_list_taken_before_a_patch_lands_cannot_hand_out_the_pod_twice(world, 
     assert len(results) == 12 and all(r["ALIYUN_COM_GPU_MEM_IDX"] != "-1" for r in results)
     patched = [r[1] for r in world.kube.requests if r[0] == "PATCH" and "/pods/" in r[1]]
     assert len(patched) == 12 and len(set(patched)) == 12
+
+
+def test_flag_errors_follow_go_flag_package():
+    """cmd/nvidia/main.go uses Go's flag package: -h prints the usage and exits 0, an undefined flag or a missing
+    value prints the message plus the usage and exits 2; the ten reference flags keep their names and help texts."""
+    p = subprocess.run([GSBD, "-h"], capture_output=True, text=True)
+    assert p.returncode == 0 and p.stderr.startswith("Usage of ")
+    for line in ('-memory-unit string\n    \tSet memoryUnit of the GPU Memroy, support \'GiB\' and \'MiB\' (default "GiB")',
+                 "-query-kubelet\n    \tQuery pending pods from kubelet instead of kube-apiserver",
+                 "-kubelet-port uint\n    \tKubelet listened Port (default 10250)",
+                 "-timeout int\n    \tKubelet client http timeout duration (default 10)",
+                 "-mps\n    \tEnable or Disable MPS", "-health-check\n    \tEnable or disable Health check"):
+        assert line in p.stderr
+    p = subprocess.run([GSBD, "--no-such-flag"], capture_output=True, text=True)
+    assert p.returncode == 2 and p.stderr.startswith("flag provided but not defined: -no-such-flag\nUsage of ")
+    p = subprocess.run([GSBD, "-token"], capture_output=True, text=True)
+    assert p.returncode == 2 and p.stderr.startswith("flag needs an argument: -token\nUsage of ")
