@@ -221,7 +221,8 @@ def bench_allocate(impl: str, quick: bool = False) -> dict:
             env = dict(os.environ, NODE_NAME=node, GPUSHARE_PLUGIN_DIR=tmp + "/", GPUSHARE_DUMP_DIR=tmp,
                        GSBD_ALLOW_FAKE_INVENTORY="1")
             env.pop("KUBECONFIG", None)
-            proc = subprocess.Popen([os.path.join(ROOT, "gpushare_device_plugin_b200", "gsbd"), "--fake-inventory", "8",
+            proc = subprocess.Popen([os.path.join(ROOT, "gpushare_device_plugin_b200", "gsbd"), "-logtostderr", "--v=5",
+                                     "--fake-inventory", "8",  # the DaemonSet's own flags: every glog line is produced
                                      "--kube-api-url", url] + list(gsbd_extra) + os.environ.get("GSBD_EXTRA", "").split(), env=env, stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL)
             kubelet.register_requests.get(timeout=30)
             time.sleep(0.3)  # let the pod informer finish its first LIST + watch (the kubelet calls Allocate much later)
@@ -280,10 +281,10 @@ def bench_allocate(impl: str, quick: bool = False) -> dict:
             out["config4_by_pod_source"][label] = load(sock, 1, 64)["p50_us"]
             close()
     # config 5: 1024 pending pods, concurrency sweep 1..1024 (bounded: max(256, c) requests per point)
-    for c in ((1, 16) if quick else (1, 4, 16, 64, 256, 1024)):
+    for c in ((1, 16) if quick else tuple(1 << k for k in range(11))):  # c = 1, 2, 4, ... 1 024
         sock, close = start(1024, True)
         # each Allocate consumes one of the 1 024 pending pods; the reference arm (~40 req/s) gets a smaller sample
-        r = load(sock, c, 64 if quick else (max(256, c) if impl == "reference" else max(1000, c)))
+        r = load(sock, c, 64 if quick else (max(128, c) if impl == "reference" else max(1000, c)))
         close()
         out["sweep"].append(r)
     out["p50_us"] = out["config4"]["p50_us"]

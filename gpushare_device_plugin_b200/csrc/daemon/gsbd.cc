@@ -57,21 +57,92 @@ const char kEnvResourceAssumeTime[] = "ALIYUN_COM_GPU_MEM_ASSUME_TIME";
 const char kEnvNodeLabelForDisableCGPU[] = "cgpu.disable.isolation";
 
 // ---------------------------------------------------------------- logging (glog-shaped, stderr)
+// The reference logs synchronously from inside Allocate's critical section (>= 6 glog lines per call at --v=5,
+// SURVEY §8 a12). Here a line is formatted by the caller and handed to one writer thread; the RPC path never
+// waits for stderr (a container runtime's log pipe). Order is preserved; warnings and errors, and everything
+// when GSBD_SYNC_LOG=1, are written before logf returns; log_flush() runs before every exit.
 int g_v = 0;
-std::mutex g_log_mu;
+class AsyncLog {
+ public:
+  void write(const char *line, size_t n, bool sync) {
+    std::unique_lock<std::mutex> lk(mu_);
+    buf_.append(line, n);
+    if (sync || !running_ || buf_.size() > (1u << 20)) {  // also the back-pressure path: never grow without bound
+      drain_locked();
+      return;
+    }
+    if (idle_) cv_.notify_one();
+  }
+  void start() {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (running_ || getenv("GSBD_SYNC_LOG")) return;
+    running_ = true;
+    th_ = std::thread([this] { run(); });
+  }
+  void flush() {  // stop the writer and write what is left; logging stays usable (synchronous) afterwards
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      if (!running_) {
+        drain_locked();
+        return;
+      }
+      running_ = false;
+      cv_.notify_one();
+    }
+    th_.join();
+    std::lock_guard<std::mutex> lk(mu_);
+    drain_locked();
+  }
+
+ private:
+  void drain_locked() {
+    if (buf_.empty()) return;
+    fwrite(buf_.data(), 1, buf_.size(), stderr);
+    fflush(stderr);
+    buf_.clear();
+  }
+  void run() {
+    std::string out;
+    std::unique_lock<std::mutex> lk(mu_);
+    while (running_) {
+      if (buf_.empty()) {
+        idle_ = true;
+        cv_.wait(lk, [this] { return !running_ || !buf_.empty(); });
+        idle_ = false;
+      }
+      out.swap(buf_);
+      lk.unlock();
+      if (!out.empty()) {
+        fwrite(out.data(), 1, out.size(), stderr);
+        fflush(stderr);
+        out.clear();
+      }
+      lk.lock();
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::string buf_;
+  bool running_ = false, idle_ = false;
+  std::thread th_;
+} g_log;
+void log_flush() { g_log.flush(); }
+
 void logf(char sev, const char *fmt, ...) {
-  char msg[2048];
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(msg, sizeof msg, fmt, ap);
-  va_end(ap);
+  char line[2200];
   timeval tv;
   gettimeofday(&tv, nullptr);
   tm t;
   localtime_r(&tv.tv_sec, &t);
-  std::lock_guard<std::mutex> lk(g_log_mu);
-  fprintf(stderr, "%c%02d%02d %02d:%02d:%02d.%06ld %7d gsbd] %s\n", sev, t.tm_mon + 1, t.tm_mday, t.tm_hour, t.tm_min,
-          t.tm_sec, (long)tv.tv_usec, (int)getpid(), msg);
+  int n = snprintf(line, 64, "%c%02d%02d %02d:%02d:%02d.%06ld %7d gsbd] ", sev, t.tm_mon + 1, t.tm_mday, t.tm_hour,
+                   t.tm_min, t.tm_sec, (long)tv.tv_usec, (int)getpid());
+  va_list ap;
+  va_start(ap, fmt);
+  const int m = vsnprintf(line + n, sizeof line - (size_t)n - 1, fmt, ap);
+  va_end(ap);
+  n += m < 0 ? 0 : std::min(m, (int)sizeof line - n - 2);
+  line[n++] = '\n';
+  g_log.write(line, (size_t)n, sev != 'I');
 }
 #define INFO(...) logf('I', __VA_ARGS__)
 #define WARN(...) logf('W', __VA_ARGS__)
@@ -1059,6 +1130,8 @@ int main(int argc, char **argv) {
   sigaddset(&mask, SIGQUIT);
   pthread_sigmask(SIG_BLOCK, &mask, nullptr);
   signal(SIGPIPE, SIG_IGN);
+  g_log.start();      // after the mask: every thread must inherit it, or a signal would land outside the signalfd
+  atexit(log_flush);  // every _exit() below follows a WARN, which is written synchronously
 
   Kube kube;
   std::string err;
