@@ -92,3 +92,41 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cc", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and '"oracle/' not in text, f
+
+
+def test_plain_c99_client_sees_the_reference_bytes(tmp_path):
+    """tests/native/c_client.c is what a cgo binding looks like from the C side: strict C99, no C++ types, caller
+    buffers. Its printed results are held against the golden vectors and the oracle."""
+    from oracle import wire_oracle as wo
+    exe = tmp_path / "c_client"
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    "-o", str(exe), os.path.join(ROOT, "tests", "native", "c_client.c"),
+                    "-L", os.path.dirname(_abi.LIB_PATH), "-lgpushare_b200",
+                    "-Wl,-rpath," + os.path.dirname(_abi.LIB_PATH)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()
+    line = {l.split(" ", 1)[0]: l.split(" ", 1)[1] for l in out if l.split(" ", 1)[0] != "allocate"}
+    allocs = [l.split(" ") for l in out if l.startswith("allocate ")]
+    u0, u1 = "GPU-fef8089b-4820-abfc-e83e-94318197576e", "GPU-fef8089c-4820-abfc-e83e-94318197576f"
+    assert line["abi"] == "1" and line["slices"] == "179 183359 0"
+    assert line["fake"] == f"46 {wo.generateFakeDeviceID(u0, 178)}" and line["real"] == f"40 {u0}"
+    assert line["small-buffer"] == "buffer too small" and line["xid"] == "1 1 1 0 0"
+    devs = [[wo.generateFakeDeviceID(u, j), wo.Unhealthy if (u, j) == (u0, 1) else wo.Healthy] for u in (u0, u1) for j in range(3)]
+    want = wo.marshal_ListAndWatchResponse(devs)
+    assert line["lw"] == f"{len(want)} {want.hex()}" and line["lw179"] == "10451"
+    want = wo.marshal_RegisterRequest(wo.Version, wo.serverSockName, wo.resourceName)
+    assert line["register"] == f"{len(want)} {want.hex()}"
+    pods = [{"metadata": {"name": f"pod-0{i}", "namespace": "default", "uid": f"uid-{i}",
+                          "annotations": {wo.EnvResourceIndex: idx, wo.EnvResourceAssumeTime: t, wo.EnvAssignedFlag: "false"}},
+             "spec": {"nodeName": "n", "containers": [{"resources": {"limits": {wo.resourceName: "4"}}}]},
+             "status": {"phase": "Pending"}} for i, (idx, t) in enumerate([("3", "20"), ("1", "10")])]
+    dev_map = {u0: 3, u1: 1}
+    envs, pod = wo.Allocate([["a", "b", "c", "d"]], pods, "n", dev_map, 179, wo.GiBPrefix, False)
+    assert pod["metadata"]["name"] == "pod-01"
+    assert allocs[0][1:6] == ["1", "pod", "1", "req", "4"] and allocs[0][6] == wo.marshal_AllocateResponse(envs).hex()
+    envs, pod = wo.Allocate([["a", "b", "c", "d"]], pods[:1], "n", dev_map, 179, wo.GiBPrefix, False)
+    assert allocs[1][1:6] == ["1", "pod", "0", "req", "4"] and allocs[1][6] == wo.marshal_AllocateResponse(envs).hex()
+    want = wo.marshal_AllocateResponse(wo.buildErrResponse([["a", "b", "c", "d"]], 4, wo.GiBPrefix, 179))
+    assert line["err"] == f"0 {want.hex()}"
+    want = wo.patchPodAnnotationSpecAssigned(1_700_000_000_000_000_000).decode()
+    assert line["patch"] == f"{len(want)} {want}"
+    assert line["device_count"] == "not initialized"  # no silent stand-in for a missing driver
