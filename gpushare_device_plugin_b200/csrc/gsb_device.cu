@@ -583,8 +583,18 @@ int run_probe_locked(Device *d, const gsb_probe_cfg *cfg, gsb_probe_result *out)
   return probe_end_locked(d, &fl, out);
 }
 
+// diagnostic knob GSB_NVML_SERIAL=1: one NVML/driver query at a time across this process's device threads (the
+// open question behind profiles/node_cycle_8gpu_bimodal_r01.txt: do concurrent queries convoy on the driver's lock?)
+std::mutex g_nvml_serial_mu;
+const bool kNvmlSerial = [] {
+  const char *e = getenv("GSB_NVML_SERIAL");
+  return e && atoi(e) != 0;
+}();
+
 int query_info(Device *d, gsb_device_info *out) {
   memset(out, 0, sizeof *out);
+  std::unique_lock<std::mutex> serial(g_nvml_serial_mu, std::defer_lock);
+  if (kNvmlSerial) serial.lock();
   // identity: re-read from both sides, every call
   char uuid[GSB_UUID_BUFFER_SIZE] = {0};
   ML_TRY(G.ml.getUUID(d->nvml, uuid, GSB_UUID_BUFFER_SIZE));

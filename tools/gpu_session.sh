@@ -17,6 +17,8 @@ if [ "$MODE" = node ]; then
   for spin in 0 50 400; do
     GSB_WORKER_SPIN_US=$spin timeout 300 python tools/node_cycle.py > $OUT/node_cycle_${N}gpu_spin$spin.json 2>> $OUT/node_cycle_${N}gpu.err
   done
+  # hypothesis: the slow mode is a convoy of concurrent NVML queries on the driver's lock -> one query at a time
+  GSB_NVML_SERIAL=1 timeout 300 python tools/node_cycle.py > $OUT/node_cycle_${N}gpu_nvml_serial.json 2>> $OUT/node_cycle_${N}gpu.err
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
     bench.py --gpus $N --steps 200 --warmup 5 > $OUT/bench_${N}gpu.json 2> $OUT/bench_${N}gpu.err
   exit 0
