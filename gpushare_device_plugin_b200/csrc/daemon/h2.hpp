@@ -363,6 +363,7 @@ struct Stream {
   std::string body;      // request DATA (gRPC length-prefixed message)
   std::string hdr_block; // HEADERS + CONTINUATION fragments
   bool hdr_end_stream = false;
+  bool too_large = false;  // request message beyond kMaxRecvMessage: answered RESOURCE_EXHAUSTED, bytes not kept
   int64_t send_window = 65535;
   std::atomic<bool> cancelled{false};
   bool headers_sent = false;
@@ -476,6 +477,19 @@ class Connection : public std::enable_shared_from_this<Connection> {
         case CONTINUATION: {
           std::shared_ptr<Stream> s = f.type == HEADERS ? open_stream(f.stream) : find(f.stream);
           if (!s) goto done;
+          if (f.type == HEADERS && open_streams() > kMaxConcurrentStreams) {  // beyond what SETTINGS advertised
+            const uint8_t refused[4] = {0, 0, 0, 7};                           // REFUSED_STREAM: safe to retry
+            erase(f.stream);
+            if (!raw_write(frame_bytes(RST_STREAM, 0, f.stream, refused, 4))) goto done;
+            if (!(f.flags & F_END_HEADERS)) goto done;  // its CONTINUATIONs would desynchronise HPACK: give up
+            {
+              const uint8_t *hp;
+              size_t hn;
+              Headers ignored;  // the block still has to pass through the decoder: HPACK state is per connection
+              if (!strip(f, &hp, &hn) || !hpack_.decode(hp, hn, &ignored)) goto done;
+            }
+            break;
+          }
           const uint8_t *p;
           size_t n;
           if (f.type == HEADERS) {
@@ -486,6 +500,7 @@ class Connection : public std::enable_shared_from_this<Connection> {
             n = f.payload.size();
           }
           s->hdr_block.append((const char *)p, n);
+          if (s->hdr_block.size() > kMaxHeaderBlock) goto done;  // CONTINUATION flood: drop the connection
           if (f.flags & F_END_HEADERS) {
             continuation_of = 0;
             Headers hs;
@@ -512,7 +527,12 @@ class Connection : public std::enable_shared_from_this<Connection> {
             if (!raw_write(out)) goto done;
           }
           if (!s) break;  // stream already finished/reset: ignore
-          s->body.append((const char *)p, n);
+          if (s->body.size() + n > kMaxRecvMessage + 5) {  // grpc-go's default MaxRecvMsgSize (4 MiB): refuse, do not buffer
+            s->too_large = true;
+            s->body.clear();
+          } else if (!s->too_large) {
+            s->body.append((const char *)p, n);
+          }
           if (f.flags & F_END_STREAM) dispatch(s);
           break;
         }
@@ -552,6 +572,13 @@ class Connection : public std::enable_shared_from_this<Connection> {
  private:
   friend class Call;
   static constexpr uint32_t kRecvWindow = 4u << 20;
+  static constexpr size_t kMaxRecvMessage = 4u << 20;    // grpc.NewServer() default (vendor/google.golang.org/grpc/server.go:53)
+  static constexpr size_t kMaxHeaderBlock = 1u << 20;
+  static constexpr size_t kMaxConcurrentStreams = 1024;  // what serve() advertises in SETTINGS
+  size_t open_streams() {
+    std::lock_guard<std::mutex> lk(mu_);
+    return streams_.size();
+  }
 
   bool raw_write(const std::string &bytes) {
     std::lock_guard<std::mutex> lk(wmu_);
@@ -575,6 +602,8 @@ class Connection : public std::enable_shared_from_this<Connection> {
     std::lock_guard<std::mutex> lk(mu_);
     auto it = streams_.find(id);
     if (it != streams_.end()) return it->second;  // trailers of a client-streaming call: not used here
+    if (id <= last_stream_) return nullptr;        // stream ids only grow (RFC 9113 5.1.1): connection error
+    last_stream_ = id;
     auto s = std::make_shared<Stream>();
     s->id = id;
     s->send_window = peer_initial_window_;
@@ -618,6 +647,10 @@ class Connection : public std::enable_shared_from_this<Connection> {
       int status = 12;  // UNIMPLEMENTED
       std::string msg;
       bool ok_msg = false;
+      if (s->too_large) {
+        self->finish(s, 8);  // RESOURCE_EXHAUSTED, as grpc-go answers a message over its receive limit
+        return;
+      }
       if (s->body.size() >= 5 && s->body[0] == 0) {
         const uint32_t n = be32((const uint8_t *)s->body.data() + 1);
         if (s->body.size() == 5 + (size_t)n) {
@@ -716,6 +749,7 @@ class Connection : public std::enable_shared_from_this<Connection> {
   int64_t conn_send_window_ = 65535;
   int64_t peer_initial_window_ = 65535;
   uint32_t peer_max_frame_ = 16384;
+  uint32_t last_stream_ = 0;
 };
 
 inline bool Call::send_message(const void *msg, size_t len) { return conn_->send_message(stream_.get(), msg, len); }

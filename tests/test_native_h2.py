@@ -293,3 +293,99 @@ def test_interop_with_curl_nghttp2(server, tmp_path):
         assert body == b"\0" + len(msg).to_bytes(4, "big") + msg
         hdr = (tmp_path / "hdr.txt").read_text().lower()
         assert "http/2 200" in hdr and "content-type: application/grpc" in hdr and "grpc-status: 0" in hdr
+
+
+# ---- limits: what grpc-go's defaults would also refuse ----------------------------------------------------
+
+def _connect(sock_path):
+    import socket as _s
+    s = _s.socket(_s.AF_UNIX, _s.SOCK_STREAM)
+    s.connect(sock_path)
+    s.settimeout(10)
+    s.sendall(b"PRI * HTTP/2.0\r\n\r\nSM\r\n\r\n" + frame(4, 0, 0))
+    return s
+
+
+def _headers(path: bytes) -> bytes:
+    return bytes([0x83, 0x86, 0x04, len(path)]) + path + bytes([0x0f, 0x10, 16]) + b"application/grpc"
+
+
+def _frames_until(s, pred, limit=20000):
+    buf, out = b"", []
+    while len(out) < limit:
+        try:
+            chunk = s.recv(1 << 16)
+        except OSError:
+            break
+        if not chunk:
+            break
+        buf += chunk
+        while len(buf) >= 9:
+            ln = int.from_bytes(buf[:3], "big")
+            if len(buf) < 9 + ln:
+                break
+            f = (buf[3], buf[4], int.from_bytes(buf[5:9], "big") & 0x7FFFFFFF, buf[9:9 + ln])
+            buf = buf[9 + ln:]
+            out.append(f)
+            if pred(f):
+                return out
+    return out
+
+
+def test_message_over_4_mib_is_refused_not_buffered(server):
+    """grpc.NewServer()'s default receive limit (vendor/google.golang.org/grpc/server.go:53): RESOURCE_EXHAUSTED."""
+    _, sock_path, _ = server
+    s = _connect(sock_path)
+    big = (4 << 20) + 100
+    s.sendall(frame(1, 0x4, 1, _headers(b"/test.Echo/Unary")))
+    body = b"\0" + big.to_bytes(4, "big") + b"x" * big
+    for off in range(0, len(body), 16384):
+        chunk = body[off:off + 16384]
+        s.sendall(frame(0, 0x1 if off + 16384 >= len(body) else 0, 1, chunk))
+    frames = _frames_until(s, lambda f: f[0] == 1 and f[2] == 1 and f[1] & 1)
+    trailers = [f for f in frames if f[0] == 1 and f[2] == 1 and f[1] & 1][0]
+    assert trailers[3].endswith(b"grpc-status\x018")
+    # the connection is still good for the next call
+    msg = b"\0" + (2).to_bytes(4, "big") + b"ok"
+    s.sendall(frame(1, 0x4, 3, _headers(b"/test.Echo/Unary")) + frame(0, 0x1, 3, msg))
+    frames = _frames_until(s, lambda f: f[0] == 1 and f[2] == 3 and f[1] & 1)
+    assert b"".join(f[3] for f in frames if f[0] == 0 and f[2] == 3) == msg
+    s.close()
+
+
+def test_continuation_flood_and_stream_id_reuse_close_the_connection(server):
+    _, sock_path, _ = server
+    s = _connect(sock_path)
+    s.sendall(frame(1, 0, 1, _headers(b"/test.Echo/Unary")))  # no END_HEADERS: CONTINUATIONs follow, without end
+    try:
+        for _ in range(200):
+            s.sendall(frame(9, 0, 1, bytes([0x00, 1, 0x61, 0x7f, 0x80, 0x7f]) + b"v" * 16000))
+    except OSError:
+        pass
+    frames = _frames_until(s, lambda f: False)
+    assert not any(f[0] == 1 for f in frames)  # never answered; the peer was dropped after 1 MiB of header block
+    s.close()
+    s = _connect(sock_path)
+    msg = b"\0" + (2).to_bytes(4, "big") + b"ok"
+    s.sendall(frame(1, 0x4, 5, _headers(b"/test.Echo/Unary")) + frame(0, 0x1, 5, msg))
+    _frames_until(s, lambda f: f[0] == 1 and f[2] == 5 and f[1] & 1)
+    s.sendall(frame(1, 0x4, 3, _headers(b"/test.Echo/Unary")) + frame(0, 0x1, 3, msg))  # ids must only grow
+    frames = _frames_until(s, lambda f: False)
+    assert not any(f[2] == 3 and f[0] in (0, 1) for f in frames)
+    s.close()
+
+
+def test_streams_beyond_the_advertised_maximum_are_refused(server):
+    """SETTINGS_MAX_CONCURRENT_STREAMS = 1024: stream 1025 gets RST_STREAM(REFUSED_STREAM), the others finish."""
+    _, sock_path, _ = server
+    s = _connect(sock_path)
+    n = 1024 + 6
+    for i in range(n):  # open, do not finish: HEADERS only
+        s.sendall(frame(1, 0x4, 2 * i + 1, _headers(b"/test.Echo/Unary")))
+    msg = b"\0" + (2).to_bytes(4, "big") + b"ok"
+    s.sendall(frame(0, 0x1, 1, msg))  # finish the first one
+    frames = _frames_until(s, lambda f: f[0] == 1 and f[2] == 1 and f[1] & 1)
+    refused = sorted(f[2] for f in frames if f[0] == 3 and f[3] == (7).to_bytes(4, "big"))
+    assert refused == [2 * i + 1 for i in range(1024, n)]
+    assert b"".join(f[3] for f in frames if f[0] == 0 and f[2] == 1) == msg
+    s.close()
