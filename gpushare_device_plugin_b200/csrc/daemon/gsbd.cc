@@ -398,6 +398,7 @@ uint64_t quantity_value(const json::Value &q) {
 // ---------------------------------------------------------------- pending pods -> gsb_pod table
 struct PodRec {
   std::string name, ns, uid;
+  uint64_t rv = 0;  // metadata.resourceVersion when it is a decimal number (etcd's are), else 0 = "cannot compare"
 };
 // The pending-pod table gsb_allocate reads. Rows keep the order in which the apiserver listed (then streamed)
 // them; the strings a gsb_pod points at live in heap records that never move, so an upsert touches one row.
@@ -405,6 +406,7 @@ struct PodTable {
   std::vector<std::unique_ptr<PodRec>> recs;
   std::vector<gsb_pod> pods;
   std::unordered_map<std::string, size_t> by_uid;  // live rows only
+  uint64_t list_rv = 0; // resourceVersion of the LIST the table was last rebuilt from
   size_t dead = 0;      // rows deleted by a watch event: on_node = 0 makes gsb_allocate skip them entirely
   bool unique = true;   // no two live rows share a uid (always true for a table the informer maintains)
   std::chrono::steady_clock::time_point stamp;
@@ -416,6 +418,7 @@ struct PodTable {
     by_uid.clear();
     dead = 0;
     unique = true;
+    list_rv = 0;
   }
   void point(size_t i) {
     pods[i].name = recs[i]->name.c_str();
@@ -489,6 +492,7 @@ void pod_row(const json::Value &p, const std::string &node, PodRec *r, gsb_pod *
     if (auto *v = md->get("name")) r->name = v->str();
     if (auto *v = md->get("namespace")) r->ns = v->str();
     if (auto *v = md->get("uid")) r->uid = v->str();
+    if (auto *v = md->get("resourceVersion")) parse_uint64(v->str(), &r->rv);
   }
   memset(g, 0, sizeof *g);
   g->gpu_idx = -1;
@@ -533,6 +537,7 @@ void build_table(const json::Value &list, const std::string &node, bool pending_
     pod_row(p, node, &r, &g);
     t->append(std::move(r), g);
   }
+  if (const json::Value *v = list.path({"metadata", "resourceVersion"})) parse_uint64(v->str(), &t->list_rv);
 }
 
 // ---------------------------------------------------------------- the plugin (server.go)
@@ -816,6 +821,7 @@ class Plugin {
     while (!stopping_) {
       std::string err, rv;
       json::Value list;
+      const auto list_started = std::chrono::steady_clock::now();
       if (!kube_->call("GET", "/api/v1/pods?" + sel, "", "", &list, &err)) {
         backoff(&failures);
         continue;
@@ -823,10 +829,14 @@ class Plugin {
       if (const json::Value *v = list.path({"metadata", "resourceVersion"})) rv = v->str();
       {
         std::lock_guard<std::mutex> lk(amu_);
-        build_table(list, kube_->node_name, false, &table_);
-        reconcile_claims();
-        table_.stamp = std::chrono::steady_clock::now();
-        table_.valid = true;
+        uint64_t rv_num = 0;
+        parse_uint64(rv, &rv_num);
+        if (!(table_.valid && rv_num && rv_num < table_.list_rv)) {  // an Allocate's own LIST may already be newer
+          build_table(list, kube_->node_name, false, &table_);
+          reconcile_claims(list_started);
+          table_.stamp = std::chrono::steady_clock::now();
+          table_.valid = true;
+        }
         resync_ = false;
       }
       std::unique_ptr<http::Conn> conn = kube_->api.open_stream("/api/v1/pods?watch=true&" + sel + "&resourceVersion=" + rv, 300, &err);
@@ -875,17 +885,17 @@ class Plugin {
     gsb_pod g;
     pod_row(obj, kube_->node_name, &r, &g);
     std::lock_guard<std::mutex> lk(amu_);
+    // the stream is ordered, but the table can be NEWER than the stream (an Allocate that found no candidate
+    // rebuilt it from its own LIST): an event at or below that LIST's resourceVersion, or older than the row it
+    // touches, would move the table back in time
+    if (r.rv && r.rv <= table_.list_rv) return;
+    auto row = table_.by_uid.find(r.uid);
+    if (row != table_.by_uid.end() && r.rv && table_.recs[row->second]->rv > r.rv) return;
     if (type == "DELETED") {
       claimed_.erase(r.uid);
       table_.remove(r.uid);
     } else if (type == "ADDED" || type == "MODIFIED") {
-      // a pod this daemon has claimed (PATCH possibly still in flight) stays hidden until the apiserver's copy
-      // itself stops saying assigned == "false"
-      auto c = claimed_.find(r.uid);
-      if (c != claimed_.end()) {
-        if (g.has_assigned && !g.assigned_is_false) claimed_.erase(c);
-        else g.assigned_is_false = 0;
-      }
+      if (claimed_.count(r.uid)) g.assigned_is_false = 0;  // handed out by this daemon: never a candidate again
       table_.upsert(std::move(r), g);
     } else {
       return;  // BOOKMARK: nothing to apply
@@ -895,6 +905,7 @@ class Plugin {
 
   // ---- Allocate
   bool load_pods(std::string *err) {
+    const auto list_started = std::chrono::steady_clock::now();
     json::Value list;
     bool pending_only = false;
     bool ok = false;
@@ -930,27 +941,25 @@ class Plugin {
       }
     }
     build_table(list, kube_->node_name, pending_only, &table_);
-    reconcile_claims();
+    reconcile_claims(list_started);
     table_.stamp = std::chrono::steady_clock::now();
     table_.valid = true;
     return true;
   }
-  // A LIST is a snapshot that can pre-date a PATCH still in flight (the lock is not held across the PATCH): a pod
-  // claimed here stays hidden in every rebuilt table until the apiserver's own copy stops saying assigned=="false".
+  // A LIST is a snapshot that can pre-date a PATCH still in flight (the lock is not held across the PATCH), and a
+  // watch event can be older than the table. So a pod handed out by this daemon is never a candidate again, in any
+  // rebuilt or updated table, for as long as it is a pending pod of this node: the claim is dropped only when the
+  // PATCH fails, when the pod is DELETED on the watch, or when a LIST issued AFTER the claim no longer contains it.
   // Caller holds amu_.
-  void reconcile_claims() {
+  void reconcile_claims(std::chrono::steady_clock::time_point list_started) {
     for (auto it = claimed_.begin(); it != claimed_.end();) {
-      auto row = table_.by_uid.find(*it);
-      if (row == table_.by_uid.end()) {  // no longer a pending pod of this node
-        it = claimed_.erase(it);
+      auto row = table_.by_uid.find(it->first);
+      if (row == table_.by_uid.end()) {
+        if (it->second < list_started) it = claimed_.erase(it);  // gone from the pending set for good
+        else ++it;                                               // the snapshot may simply pre-date the pod
         continue;
       }
-      gsb_pod &g = table_.pods[row->second];
-      if (g.has_assigned && !g.assigned_is_false) {  // confirmed
-        it = claimed_.erase(it);
-        continue;
-      }
-      g.assigned_is_false = 0;
+      table_.pods[row->second].assigned_is_false = 0;
       ++it;
     }
   }
@@ -1009,7 +1018,7 @@ class Plugin {
         ns = table_.recs[pidx]->ns;
         table_.pods[pidx].assigned_is_false = 0;  // claimed: hidden from the next request
         claimed_uid = table_.recs[pidx]->uid;
-        claimed_.insert(claimed_uid);
+        claimed_[claimed_uid] = std::chrono::steady_clock::now();
       }
     }
     if (kind == GSB_ALLOC_MATCHED) {
@@ -1088,7 +1097,7 @@ class Plugin {
   PodTable table_;
   std::thread informer_thread_;
   std::atomic<bool> synced_{false}, resync_{false};
-  std::set<std::string> claimed_;  // uids claimed here whose assigned="true" has not come back on the watch yet
+  std::unordered_map<std::string, std::chrono::steady_clock::time_point> claimed_;  // uid -> when it was handed out
   std::mutex wmu_;
   http::Conn *watch_conn_ = nullptr;
   int retry_sleep_ms_ = 1000;

@@ -67,6 +67,7 @@ class MockKube:
         self.watches_served = 0
         self.enable_watch = True
         self.patch_delay = 0.0
+        self.patched_ok: List[str] = []  # pod PATCHes that were applied (requests[] also holds the refused ones)
         self.lock = threading.Lock()
         self.nodes: Dict[str, dict] = {node["metadata"]["name"]: node}
         self.pods: Dict[tuple, dict] = {(p["metadata"]["namespace"], p["metadata"]["name"]): p for p in pods}
@@ -215,6 +216,7 @@ class MockKube:
                             return self._status(404, f'pods "{parts[5]}" not found')
                         p["metadata"].setdefault("annotations", {}).update(
                             (patch.get("metadata") or {}).get("annotations") or {})
+                        mock.patched_ok.append(self.path)
                         return self._send(200, mock._emit("MODIFIED", p))
                 self._status(404, "not found")
 

@@ -485,3 +485,112 @@ def test_flag_errors_follow_go_flag_package():
     assert p.returncode == 2 and p.stderr.startswith("flag provided but not defined: -no-such-flag\nUsage of ")
     p = subprocess.run([GSBD, "-token"], capture_output=True, text=True)
     assert p.returncode == 2 and p.stderr.startswith("flag needs an argument: -token\nUsage of ")
+
+
+@pytest.mark.parametrize("mode", [(), ("--pod-informer=false",), ("--pod-informer=false", "--pod-cache-ttl", "0")],
+                         ids=["informer", "ttl-cache", "list-per-call"])
+def test_everything_at_once_for_a_few_seconds(world, mode):
+    """Soak: Allocates from several kubelet connections, pod churn on the apiserver, health events, ListAndWatch
+    streams opening and closing, a kubelet restart in the middle. Afterwards: the daemon is alive and exits 0, no pod
+    was handed out twice, no request was refused while a matching pod existed at the end, and a fresh stream shows
+    exactly the GPUs that were marked. (tools/sanitize.sh runs this under TSan and ASan.)"""
+    d = world.start(*mode)
+    stop = threading.Event()
+    errors, results = [], []
+    next_id = [1000]
+    lock = threading.Lock()
+
+    def guard(fn):
+        def run():
+            try:
+                while not stop.is_set():
+                    fn()
+            except Exception as e:  # noqa: BLE001
+                if not stop.is_set():
+                    errors.append(repr(e))
+        return run
+
+    def allocator():
+        ch = d.channel()
+        try:
+            while not stop.is_set():
+                try:
+                    r = wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, wo.marshal_AllocateRequest([["a", "b"]])))[0]
+                    results.append(r["ALIYUN_COM_GPU_MEM_IDX"])
+                except grpc.RpcError:  # the kubelet-restart window: the plugin's socket is being re-created
+                    time.sleep(0.05)
+                    ch.close()
+                    ch = d.channel()
+        finally:
+            ch.close()
+
+    def churn():
+        with lock:
+            i = next_id[0]
+            next_id[0] += 1
+        world.kube.add_pod(make_pod(i, NODE, gpu_mem=2, idx=i % 8, assume_time=1_800_000_000_000_000_000 + i))
+        if i % 3 == 0:
+            try:
+                world.kube.delete_pod(f"pod-{i - 2}")
+            except KeyError:
+                pass
+        time.sleep(0.004)
+
+    def watcher():
+        ch = d.channel()
+        try:
+            call = d.kubelet.list_and_watch(ch)
+            next(iter(call))
+            time.sleep(0.05)
+            call.cancel()
+        except grpc.RpcError:
+            time.sleep(0.05)
+        finally:
+            ch.close()
+
+    def health():
+        ch = d.channel()
+        try:
+            d.inject(ch, fakes.UUIDS[3], 8, 31)   # benign: changes nothing
+            d.inject(ch, fakes.UUIDS[6], 0x100, 1)
+        except grpc.RpcError:
+            pass
+        finally:
+            ch.close()
+        time.sleep(0.02)
+
+    ts = [threading.Thread(target=guard(f)) for f in (churn, watcher, watcher, health)] + \
+         [threading.Thread(target=allocator) for _ in range(4)]
+    [t.start() for t in ts]
+    time.sleep(2.0)
+    d.kubelet.stop()  # kubelet restart: the daemon rebuilds and registers again while everything keeps going
+    time.sleep(0.2)
+    d.kubelet.start()
+    assert d.kubelet.register_requests.get(timeout=20) == d.register_request
+    time.sleep(2.0)
+    stop.set()
+    [t.join(30) for t in ts]
+    assert not errors, errors[:3]
+    assert d.proc.poll() is None and len(results) > 50
+    patched = list(world.kube.patched_ok)  # applied PATCHes only: a pod deleted by the churn answers 404, possibly twice
+    twice = sorted({p for p in patched if patched.count(p) > 1})
+    if twice:  # show what the daemon logged about the first such pod
+        name = twice[0].rsplit("/", 1)[1]
+        d.log.flush()
+        print("\n".join(l for l in open(world.dir / "gsbd.log").read().splitlines() if name in l or "Failed" in l)[-3000:])
+    assert not twice  # no pod handed out twice
+    # the calls in flight when the kubelet restarted lost their responses with the old socket
+    ok = len([r for r in results if r != "-1"])
+    assert len(patched) - 8 <= ok <= len(patched)
+    ch = d.channel()
+    d.inject(ch, fakes.UUIDS[6], 0x100, 1)  # the rebuilt plugin starts all-Healthy, like the reference's: mark again
+    deadline, devs = time.time() + 5, None
+    while time.time() < deadline:
+        devs = wo.unmarshal_ListAndWatchResponse(next(iter(d.kubelet.list_and_watch(ch))))
+        if devs == all_devs(unhealthy={6}):
+            break
+        time.sleep(0.1)
+    assert devs == all_devs(unhealthy={6})
+    ch.close()
+    d.proc.send_signal(signal.SIGTERM)
+    assert d.proc.wait(timeout=20) == 0
