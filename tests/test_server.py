@@ -329,6 +329,71 @@ def test_a_list_taken_before_a_patch_lands_cannot_hand_out_the_pod_twice(world, 
     assert len(patched) == 12 and len(set(patched)) == 12
 
 
+@pytest.mark.parametrize("ttl", [0, 0.05, 60])
+def test_everything_at_once_for_a_few_seconds(world, ttl):
+    """Soak of the Python front end: concurrent Allocates, pod churn on the apiserver, health events and
+    ListAndWatch streams coming and going. No applied PATCH may repeat, the plugin keeps answering, and the final
+    stream shows exactly the marked GPU."""
+    p = world.make(pod_cache_ttl=ttl, max_workers=32)
+    p.Serve(world.kubelet.socket)
+    stop, errors, results = threading.Event(), [], []
+    ids = iter(range(1000, 100000))
+    pause = threading.Event().wait  # time.sleep is stubbed out by the fixture
+
+    def guard(fn):
+        def run():
+            try:
+                while not stop.is_set():
+                    fn()
+            except Exception as e:  # noqa: BLE001
+                if not stop.is_set():
+                    errors.append(repr(e))
+        return run
+
+    def allocator():
+        ch = world.kubelet.channel("aliyungpushare.sock")
+        r = wo.unmarshal_AllocateResponse(world.kubelet.allocate(ch, wo.marshal_AllocateRequest([["a", "b"]])))[0]
+        results.append(r["ALIYUN_COM_GPU_MEM_IDX"])
+        ch.close()
+
+    def churn():
+        i = next(ids)
+        world.kube.add_pod(make_pod(i, NODE, gpu_mem=2, idx=i % 8, assume_time=1_800_000_000_000_000_000 + i))
+        if i % 3 == 0:
+            try:
+                world.kube.delete_pod(f"pod-{i - 2}")
+            except KeyError:
+                pass
+        pause(0.01)
+
+    def watcher():
+        ch = world.kubelet.channel("aliyungpushare.sock")
+        call = world.kubelet.list_and_watch(ch)
+        next(iter(call))
+        pause(0.05)
+        call.cancel()
+        ch.close()
+
+    def health():
+        device.health_inject(fakes.UUIDS[3], 8, 31)  # benign XID
+        device.health_inject(fakes.UUIDS[6], 0x100, 1)
+        pause(0.05)
+
+    ts = [threading.Thread(target=guard(f)) for f in (churn, watcher, health, allocator, allocator, allocator)]
+    [t.start() for t in ts]
+    pause(3.0)
+    stop.set()
+    [t.join(30) for t in ts]
+    assert not errors, errors[:3]
+    applied = list(world.kube.patched_ok)
+    assert len(results) > 30 and len(applied) == len(set(applied))
+    assert len([r for r in results if r != "-1"]) <= len(applied) <= len([r for r in results if r != "-1"]) + 3
+    ch = world.kubelet.channel("aliyungpushare.sock")
+    devs = wo.unmarshal_ListAndWatchResponse(next(iter(world.kubelet.list_and_watch(ch))))
+    assert {wo.extractRealDeviceID(i) for i, h in devs if h == wo.Unhealthy} == {fakes.UUIDS[6]}
+    ch.close()
+
+
 def test_optional_recovery_is_off_by_default_and_flag_gated(world):
     """server.go:180 FIXME: the reference never leaves Unhealthy. Default: a RECOVERED probe event changes
     nothing; with health_recovery_cycles > 0 the GPU's fake devices flip back — but only after a PROBE
