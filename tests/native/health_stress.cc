@@ -13,7 +13,7 @@
 
 int main(int argc, char **argv) {
   const double seconds = argc > 1 ? atof(argv[1]) : 2.0;
-  std::atomic<bool> stop{false};
+  std::atomic<bool> stop{false}, stop_inject{false};
   std::atomic<long> injected{0}, received{0}, timeouts{0}, stopped{0}, lifecycle{0};
   std::vector<std::thread> ts;
   for (int i = 0; i < 4; i++)
@@ -22,7 +22,7 @@ int main(int argc, char **argv) {
       memset(&ev, 0, sizeof ev);
       snprintf(ev.uuid, sizeof ev.uuid, "GPU-%08d-0000-0000-0000-000000000000", i);
       ev.etype = 8;
-      while (!stop) {
+      while (!stop_inject) {
         ev.edata = 31 + (uint64_t)(injected % 50);
         if (gsb_health_inject(&ev) == GSB_OK) injected++;
         if ((injected & 63) == 0) std::this_thread::sleep_for(std::chrono::microseconds(200));
@@ -60,8 +60,12 @@ int main(int argc, char **argv) {
       }
     });
   std::this_thread::sleep_for(std::chrono::milliseconds((int)(seconds * 1000)));
+  stop_inject = true;  // producers first; the consumers then drain what is queued (every event exactly once)
+  for (int i = 0; i < 4; i++) ts[(size_t)i].join();
+  for (int spin = 0; spin < 400 && received.load() < injected.load(); spin++)
+    std::this_thread::sleep_for(std::chrono::milliseconds(5));
   stop = true;
-  for (auto &t : ts) t.join();
+  for (size_t i = 4; i < ts.size(); i++) ts[i].join();
   printf("injected %ld received %ld timeouts %ld stopped %ld lifecycle %ld\n", injected.load(), received.load(),
          timeouts.load(), stopped.load(), lifecycle.load());
   return received.load() > 0 && lifecycle.load() > 0 ? 0 : 1;
