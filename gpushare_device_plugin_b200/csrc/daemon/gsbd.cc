@@ -608,9 +608,16 @@ class Plugin {
     });
     srv_->handle("/v1beta1.DevicePlugin/ListAndWatch", [this](h2::Call &c, const std::string &) { return list_and_watch(c); });
     srv_->handle("/v1beta1.DevicePlugin/Allocate", [this](h2::Call &c, const std::string &req) {
+      // grpc-go decodes the request before the handler runs: bytes gogo's Unmarshal refuses never reach Allocate and
+      // the call fails with INTERNAL (vendor/google.golang.org/grpc: "grpc: error unmarshalling request: ...")
+      size_t ignored = 0;
+      if (gsb_allocate_err_response(&actx_, (const uint8_t *)req.data(), req.size(), nullptr, 0, &ignored) == GSB_ERR_MALFORMED) {
+        c.set_status_message("grpc: error unmarshalling request");
+        return 13;
+      }
       const std::string resp = allocate(req);
       c.send_message(resp.data(), resp.size());
-      return 0;  // Allocate never returns a gRPC error (allocate.go: every failure is in the envs)
+      return 0;  // Allocate itself never returns a gRPC error (allocate.go: every failure is in the envs)
     });
     if (f_.fake_inventory > 0) {
       // test hook (synthetic-inventory mode only): "<uuid|-> <etype> <edata>" -> gsb_health_inject, i.e. an

@@ -11,6 +11,7 @@
 
 #include <errno.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <string.h>
 #include <sys/socket.h>
 #include <sys/un.h>
@@ -364,6 +365,7 @@ struct Stream {
   std::string hdr_block; // HEADERS + CONTINUATION fragments
   bool hdr_end_stream = false;
   bool too_large = false;  // request message beyond kMaxRecvMessage: answered RESOURCE_EXHAUSTED, bytes not kept
+  std::string status_message;  // grpc-message of a non-OK status
   int64_t send_window = 65535;
   std::atomic<bool> cancelled{false};
   bool headers_sent = false;
@@ -376,6 +378,7 @@ class Call {
   bool send_message(const void *msg, size_t len);  // false once the peer is gone / cancelled
   bool cancelled() const;
   const std::string &path() const { return stream_->path; }
+  void set_status_message(const std::string &m) { stream_->status_message = m; }  // sent as grpc-message with a non-OK status
 
  private:
   friend class Connection;
@@ -733,6 +736,19 @@ class Connection : public std::enable_shared_from_this<Connection> {
         hpack_put_static_name(&block, 31, "application/grpc");
       }
       hpack_put_header(&block, "grpc-status", std::to_string(status));
+      if (status != 0 && !s->status_message.empty()) {  // percent-encoded as the gRPC HTTP/2 spec asks
+        std::string enc;
+        for (unsigned char ch : s->status_message) {
+          if (ch >= 0x20 && ch <= 0x7E && ch != '%') {
+            enc.push_back((char)ch);
+          } else {
+            char e[4];
+            snprintf(e, sizeof e, "%%%02X", ch);
+            enc += e;
+          }
+        }
+        hpack_put_header(&block, "grpc-message", enc);
+      }
       raw_write(frame_bytes(HEADERS, F_END_HEADERS | F_END_STREAM, s->id, block.data(), block.size()));
     }
     erase(s->id);

@@ -72,11 +72,13 @@ std::string dec(uint64_t v) {
 const char kHealthy[] = "Healthy";      // pluginapi.Healthy   (v1beta1/constants.go)
 const char kUnhealthy[] = "Unhealthy";  // pluginapi.Unhealthy
 
-// ---- minimal proto3 reader -------------------------------------------------------------
+// ---- proto3 reader with the accept/reject behaviour of gogo's generated Unmarshal ----------------------------
+// (api.pb.go:2141-2300 for AllocateRequest / ContainerAllocateRequest, skipApi at :2991-3089): what grpc-go would
+// refuse with "error unmarshalling request" is refused here too, what it skips is skipped.
 
 struct Reader {
   const uint8_t *p, *end;
-  bool varint(uint64_t *v) {
+  bool varint(uint64_t *v) {  // <= 10 bytes, else ErrIntOverflowApi; running out = io.ErrUnexpectedEOF
     uint64_t r = 0;
     for (int shift = 0; shift < 64; shift += 7) {
       if (p >= end) return false;
@@ -89,49 +91,72 @@ struct Reader {
     }
     return false;
   }
-  bool skip(uint32_t wire) {
-    uint64_t n;
-    switch (wire) {
+  // skipApi: p stands on the KEY of an unknown field; consumes the whole field. Groups recurse (depth-bounded here:
+  // Go would recurse without limit, nothing legitimate nests 64 groups).
+  bool skip_field(int depth = 0) {
+    if (depth > 64) return false;
+    uint64_t key, n;
+    if (!varint(&key)) return false;
+    switch (key & 7) {
       case 0: return varint(&n);
       case 1: if (end - p < 8) return false; p += 8; return true;
-      case 2: if (!varint(&n) || (uint64_t)(end - p) < n) return false; p += n; return true;
+      case 2:
+        if (!varint(&n) || (int64_t)n < 0 || (uint64_t)(end - p) < n) return false;  // int(length) < 0: ErrInvalidLength
+        p += n;
+        return true;
+      case 3:
+        for (;;) {
+          const uint8_t *start = p;
+          uint64_t inner;
+          if (!varint(&inner)) return false;
+          if ((inner & 7) == 4) return true;
+          p = start;
+          if (!skip_field(depth + 1)) return false;
+        }
+      case 4: return true;
       case 5: if (end - p < 4) return false; p += 4; return true;
-      default: return false;
+      default: return false;  // "proto: illegal wireType"
     }
   }
 };
 
-// AllocateRequest -> number of devicesIDs per container request
-bool decode_allocate_request(const uint8_t *req, size_t len, std::vector<uint64_t> *per_container) {
-  Reader r{req, req + len};
+// One message whose only known field is number 1, length-delimited (both request messages have that shape).
+template <typename F>
+bool decode_field1_message(const uint8_t *b, size_t len, F on_field1) {
+  Reader r{b, b + len};
   while (r.p < r.end) {
+    const uint8_t *pre = r.p;
     uint64_t key;
     if (!r.varint(&key)) return false;
-    const uint32_t field = (uint32_t)(key >> 3), wire = (uint32_t)(key & 7);
-    if (field == 1 && wire == 2) {  // container_requests
+    const int32_t field = (int32_t)(uint32_t)(key >> 3);  // int32(wire >> 3), wrap included
+    const uint32_t wire = (uint32_t)(key & 7);
+    if (wire == 4 || field <= 0) return false;  // "wiretype end group for non-group" / "illegal tag"
+    if (field == 1) {
+      if (wire != 2) return false;  // "wrong wireType"
       uint64_t n;
-      if (!r.varint(&n) || (uint64_t)(r.end - r.p) < n) return false;
-      Reader c{r.p, r.p + n};
+      if (!r.varint(&n) || (int64_t)n < 0 || (uint64_t)(r.end - r.p) < n) return false;
+      if (!on_field1(r.p, (size_t)n)) return false;
       r.p += n;
-      uint64_t ids = 0;
-      while (c.p < c.end) {
-        uint64_t k2;
-        if (!c.varint(&k2)) return false;
-        if ((k2 >> 3) == 1 && (k2 & 7) == 2) {  // devicesIDs
-          uint64_t sl;
-          if (!c.varint(&sl) || (uint64_t)(c.end - c.p) < sl) return false;
-          c.p += sl;
-          ids++;
-        } else if (!c.skip((uint32_t)(k2 & 7))) {
-          return false;
-        }
-      }
-      per_container->push_back(ids);
-    } else if (!r.skip(wire)) {
-      return false;
+    } else {
+      r.p = pre;
+      if (!r.skip_field()) return false;
     }
   }
   return true;
+}
+
+// AllocateRequest -> number of devicesIDs per container request
+bool decode_allocate_request(const uint8_t *req, size_t len, std::vector<uint64_t> *per_container) {
+  return decode_field1_message(req, len, [&](const uint8_t *c, size_t n) {
+    uint64_t ids = 0;
+    if (!decode_field1_message(c, n, [&](const uint8_t *, size_t) {
+          ids++;
+          return true;
+        }))
+      return false;
+    per_container->push_back(ids);
+    return true;
+  });
 }
 
 struct Env {

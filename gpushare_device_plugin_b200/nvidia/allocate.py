@@ -60,6 +60,12 @@ def buildErrResponse(actx: AllocateContext, req: bytes) -> bytes:  # allocate.go
     return buf.raw[: n.value]
 
 
+def decodable(actx: AllocateContext, req: bytes) -> bool:
+    """Would gogo's AllocateRequest.Unmarshal (api.pb.go:2141-2221) accept these bytes?"""
+    n = C.c_size_t(0)
+    return lib.gsb_allocate_err_response(C.byref(actx.ctx), req, len(req), None, 0, C.byref(n)) != _abi.GSB_ERR_MALFORMED
+
+
 class PendingPodCache:
     """the reference LISTs (and JSON-decodes) every pending pod of the node on
     every Allocate while holding the plugin lock. This keeps the last LIST and its gsb_pod table for

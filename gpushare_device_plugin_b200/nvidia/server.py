@@ -116,6 +116,10 @@ class NvidiaDevicePlugin:
                 yield f
 
     def Allocate(self, request: bytes, context) -> bytes:
+        # grpc-go decodes the request before the handler runs: what gogo's Unmarshal refuses fails the call
+        # with INTERNAL and never reaches allocate.go
+        if not _allocate.decodable(self.allocate_ctx, request):
+            context.abort(grpc.StatusCode.INTERNAL, "grpc: error unmarshalling request")
         return _allocate.allocate(self, request)
 
     # ---- health plumbing (server.go:187-189, 203-221) ----------------------------------------

@@ -169,6 +169,121 @@ def marshal_AllocateResponse(container_envs: List[Dict[str, str]]) -> bytes:  # 
     return bytes(out)
 
 
+# ---- gogo's generated decoder for AllocateRequest, restated (api.pb.go:2141-2221, 2222-2300, skipApi 2991-3089) ------
+
+class UnmarshalError(ValueError):
+    """What grpc-go turns into status INTERNAL ("grpc: error unmarshalling request: ...")."""
+
+
+def _go_varint(b: bytes, i: int) -> Tuple[int, int]:
+    """The inlined loop every field read uses: `shift >= 64` => ErrIntOverflowApi, running out => io.ErrUnexpectedEOF."""
+    v = shift = 0
+    while True:
+        if shift >= 64:
+            raise UnmarshalError("proto: integer overflow")
+        if i >= len(b):
+            raise UnmarshalError("unexpected EOF")
+        x = b[i]
+        i += 1
+        v |= (x & 0x7F) << shift
+        if x < 0x80:
+            return v & 0xFFFFFFFFFFFFFFFF, i
+        shift += 7
+
+
+def _go_int(v: int) -> int:  # int(uint64): two's complement
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def _int32(v: int) -> int:   # int32(wire >> 3)
+    v &= 0xFFFFFFFF
+    return v - (1 << 32) if v >= (1 << 31) else v
+
+
+def skipApi(b: bytes, depth: int = 0) -> int:  # api.pb.go:2991-3089; returns the number of bytes of one field
+    if depth > 64:  # the product refuses deeper group nesting; Go would recurse on (SURVEY: deviation, unreachable in practice)
+        raise UnmarshalError("proto: group nesting too deep")
+    if not b:
+        raise AssertionError("unreachable in the reference too: callers pass at least the key")
+    wire, i = _go_varint(b, 0)
+    wt = wire & 7
+    if wt == 0:
+        shift = 0
+        while True:
+            if shift >= 64:
+                raise UnmarshalError("proto: integer overflow")
+            if i >= len(b):
+                raise UnmarshalError("unexpected EOF")
+            i += 1
+            if b[i - 1] < 0x80:
+                return i
+            shift += 7
+    if wt == 1:
+        return i + 8
+    if wt == 2:
+        length, i = _go_varint(b, i)
+        length = _go_int(length)
+        if length < 0:
+            raise UnmarshalError("proto: negative length found during unmarshaling")
+        return i + length
+    if wt == 3:
+        while True:
+            start = i
+            inner, i = _go_varint(b, i)
+            if inner & 7 == 4:
+                return i
+            if start >= len(b):
+                raise UnmarshalError("unexpected EOF")
+            i = start + skipApi(b[start:], depth + 1)
+            if i > len(b):  # Go would slice past the end on the next round: panic -> the RPC fails either way
+                raise UnmarshalError("unexpected EOF")
+    if wt == 4:
+        return i
+    if wt == 5:
+        return i + 4
+    raise UnmarshalError("proto: illegal wireType %d" % wt)
+
+
+def _unmarshal_message(b: bytes, name: str, field1: str, on_field1) -> None:
+    i, l = 0, len(b)
+    while i < l:
+        pre = i
+        wire, i = _go_varint(b, i)
+        field, wt = _int32(wire >> 3), wire & 7
+        if wt == 4:
+            raise UnmarshalError("proto: %s: wiretype end group for non-group" % name)
+        if field <= 0:
+            raise UnmarshalError("proto: %s: illegal tag %d (wire type %d)" % (name, field, wire))
+        if field == 1:
+            if wt != 2:
+                raise UnmarshalError("proto: wrong wireType = %d for field %s" % (wt, field1))
+            n, i = _go_varint(b, i)
+            n = _go_int(n)
+            if n < 0:
+                raise UnmarshalError("proto: negative length found during unmarshaling")
+            if i + n > l:
+                raise UnmarshalError("unexpected EOF")
+            on_field1(b[i:i + n])
+            i += n
+        else:
+            skippy = skipApi(b[pre:])
+            if pre + skippy > l:
+                raise UnmarshalError("unexpected EOF")
+            i = pre + skippy
+
+
+def unmarshal_AllocateRequest(b: bytes) -> List[List[bytes]]:
+    """AllocateRequest.Unmarshal + ContainerAllocateRequest.Unmarshal: devicesIDs per container, or UnmarshalError."""
+    out: List[List[bytes]] = []
+
+    def container(payload: bytes):
+        ids: List[bytes] = []
+        _unmarshal_message(payload, "ContainerAllocateRequest", "DevicesIDs", ids.append)
+        out.append(ids)
+    _unmarshal_message(b, "AllocateRequest", "ContainerRequests", container)
+    return out
+
+
 def _read_varint(b: bytes, i: int) -> Tuple[int, int]:
     v = shift = 0
     while True:

@@ -201,3 +201,72 @@ def test_malformed_request_is_rejected_not_guessed():
     rc = _abi.lib.gsb_allocate(C.byref(actx.ctx), None, 0, ok, len(ok), buf, len(buf), C.byref(n), C.byref(pidx),
                                C.byref(preq))
     assert rc == _abi.GSB_ALLOC_ERR_RESPONSE and preq.value == 2
+
+
+# ---- request decoding: same accept / reject as gogo's generated Unmarshal (api.pb.go:2141-2300, 2991-3089) ----------
+
+def _product_decode(req: bytes):
+    """(accepted, devicesIDs-per-container) as gsb_allocate sees the request: on a one-GPU node every decodable
+    request is answered, with POD = the total and CONTAINER = the per-container count."""
+    actx = AllocateContext({UUIDS[0]: 0}, 179, True, False)
+    buf = C.create_string_buffer(1 << 20)
+    n, pidx, preq = C.c_size_t(0), C.c_int32(-1), C.c_uint32(0)
+    rc = _abi.lib.gsb_allocate(C.byref(actx.ctx), None, 0, req, len(req), buf, len(buf), C.byref(n), C.byref(pidx),
+                               C.byref(preq))
+    if rc == _abi.GSB_ERR_MALFORMED:
+        return False, None
+    assert rc > 0, rc
+    return True, [int(e["ALIYUN_COM_GPU_MEM_CONTAINER"]) for e in wo.unmarshal_AllocateResponse(buf.raw[: n.value])]
+
+
+def _oracle_decode(req: bytes):
+    try:
+        return True, [len(ids) for ids in wo.unmarshal_AllocateRequest(req)]
+    except wo.UnmarshalError:
+        return False, None
+
+
+_valid_requests = st.lists(st.lists(st.text(alphabet="GPU-0123456789abcdef_", max_size=50), max_size=5), max_size=4) \
+    .map(wo.marshal_AllocateRequest)
+_unknown_field = st.one_of(
+    st.builds(lambda f, v: wo.encodeVarintApi(f << 3 | 0) + wo.encodeVarintApi(v), st.integers(2, 40), st.integers(0, 1 << 40)),
+    st.builds(lambda f, b: wo.encodeVarintApi(f << 3 | 2) + wo.encodeVarintApi(len(b)) + b, st.integers(2, 40), st.binary(max_size=12)),
+    st.builds(lambda f, b: wo.encodeVarintApi(f << 3 | 1) + b, st.integers(2, 40), st.binary(min_size=8, max_size=8)),
+    st.builds(lambda f, b: wo.encodeVarintApi(f << 3 | 5) + b, st.integers(2, 40), st.binary(min_size=4, max_size=4)),
+    st.builds(lambda f, g: wo.encodeVarintApi(f << 3 | 3) + g + wo.encodeVarintApi(f << 3 | 4), st.integers(2, 40),
+              st.sampled_from([b"", b"\x10\x01", b"\x1a\x02ab", b"\x23\x24", b"\x23\x10\x05\x24"])))
+
+
+@settings(max_examples=400, deadline=None)
+@given(parts=st.lists(st.one_of(_valid_requests, _unknown_field, st.binary(max_size=6)), max_size=5),
+       cut=st.integers(0, 400), flip=st.lists(st.tuples(st.integers(0, 400), st.integers(0, 255)), max_size=3))
+def test_request_decoder_accepts_and_rejects_what_gogo_does(parts, cut, flip):
+    req = bytearray(b"".join(parts))
+    for pos, val in flip:  # point mutations: wrong wire types, broken lengths, stray end-groups, tag 0 ...
+        if req:
+            req[pos % len(req)] = val
+    req = bytes(req[: max(0, len(req) - cut % 7)]) if cut % 3 == 0 else bytes(req)
+    assert _product_decode(req) == _oracle_decode(req), req.hex()
+
+
+def test_request_decoder_known_edge_cases():
+    cases = {
+        b"": (True, []),
+        b"\x0a\x00": (True, [0]),
+        b"\x0a\x03\x0a\x01a\x0a\x00": (True, [1, 0]),
+        b"\x08\x01": (False, None),                    # field 1 as varint: "wrong wireType"
+        b"\x0c": (False, None),                        # stray end-group
+        b"\x00\x00": (False, None),                    # tag 0
+        b"\x0a\x02\x08\x01": (False, None),            # devicesIDs as varint
+        b"\x13\x08\x01\x14": (True, []),              # unknown group field 2 skipped
+        b"\x13\x08\x01": (False, None),                # ... unterminated
+        b"\x16": (False, None),                        # wire type 6
+        b"\x10" + b"\xff" * 10 + b"\x01": (False, None),  # 11-byte varint: integer overflow
+        b"\x10" + b"\xff" * 9 + b"\x7f": (True, []),     # 10-byte varint is fine
+        b"\x12\xff\xff\xff\xff\xff\xff\xff\xff\xff\x01": (False, None),  # length with bit 63 set: negative
+        b"\x89\x80\x80\x80\x80\x01\x00": (False, None),  # tag (1<<32|1)<<3|1: int32 wraps to field 1, wire type 1: "wrong wireType"
+        b"\x8a\x80\x80\x80\x80\x01\x00": (True, [0]),   # same wrap with wire type 2: read as container_requests
+    }
+    for req, want in cases.items():
+        assert _oracle_decode(req) == want, req.hex()
+        assert _product_decode(req) == want, req.hex()

@@ -185,8 +185,16 @@ def test_allocate_failure_paths_and_cache(world):
         world.kube.order.append(("default", "pod-99"))
     envs = wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, wo.marshal_AllocateRequest([["a", "b"]])))
     assert envs[0]["ALIYUN_COM_GPU_MEM_IDX"] == "5" and n("GET", "/api/v1/pods?") == lists + 1  # refresh on a miss
-    # malformed request bytes: answered with an empty message, not a crash
-    assert d.kubelet.allocate(ch, b"\x0a\x05\x0a") == b""
+    # bytes gogo's Unmarshal refuses: the call fails with INTERNAL as under grpc-go, and nothing was LISTed or PATCHed
+    before = len(world.kube.requests)
+    for bad in (b"\x0a\x05\x0a", b"\x08\x01", b"\x0c"):
+        with pytest.raises(grpc.RpcError) as e:
+            d.kubelet.allocate(ch, bad)
+        assert e.value.code() == grpc.StatusCode.INTERNAL and "error unmarshalling request" in e.value.details()
+    assert len(world.kube.requests) == before
+    # unknown fields are skipped like any proto3 reader does: still answered
+    ok = wo.marshal_AllocateRequest([["a", "b"]]) + b"\x10\x07"
+    assert wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, ok))[0]["ALIYUN_COM_GPU_MEM_CONTAINER"] == "2"
     ch.close()
 
 

@@ -207,6 +207,13 @@ def test_allocate_failure_paths_never_raise(world):
     # LIST fails three times then works: the request is served
     world.kube.fail_lists = 3
     assert wo.unmarshal_AllocateResponse(world.kubelet.allocate(ch, req))[0]["ALIYUN_COM_GPU_MEM_IDX"] == "0"
+    # bytes gogo's Unmarshal refuses: the call fails with INTERNAL as under grpc-go; nothing is LISTed or PATCHed
+    before = len(world.kube.requests)
+    for bad in (b"\x0a\x05\x0a", b"\x08\x01", b"\x0c"):
+        with pytest.raises(grpc.RpcError) as e:
+            world.kubelet.allocate(ch, bad)
+        assert e.value.code() == grpc.StatusCode.INTERNAL and "error unmarshalling request" in e.value.details()
+    assert len(world.kube.requests) == before
     ch.close()
 
 
