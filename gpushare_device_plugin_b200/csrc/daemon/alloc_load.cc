@@ -4,6 +4,7 @@
 // testing/allocate_load.py, without an interpreter's ~100 us per call on the client side.
 //   alloc_load <socket> <concurrency> <total> <uuid,uuid,...>
 #include <stdio.h>
+#include <sys/resource.h>
 #include <stdlib.h>
 #include <time.h>
 
@@ -141,6 +142,13 @@ int main(int argc, char **argv) {
   if (argc < 5) {
     fprintf(stderr, "usage: alloc_load <socket> <concurrency> <total> <uuid,uuid,...>\n");
     return 64;
+  }
+  {  // one fd per connection: lift the soft limit to the hard one (a container's default soft limit can be 1024)
+    rlimit rl;
+    if (getrlimit(RLIMIT_NOFILE, &rl) == 0 && rl.rlim_cur < rl.rlim_max) {
+      rl.rlim_cur = rl.rlim_max;
+      setrlimit(RLIMIT_NOFILE, &rl);
+    }
   }
   const std::string sock = argv[1];
   const int conc = atoi(argv[2]), total = atoi(argv[3]);

@@ -14,6 +14,7 @@
 #include <signal.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <sys/resource.h>
 #include <stdlib.h>
 #include <string.h>
 #include <sys/inotify.h>
@@ -1145,6 +1146,13 @@ int main(int argc, char **argv) {
   sigaddset(&mask, SIGTERM);
   sigaddset(&mask, SIGQUIT);
   pthread_sigmask(SIG_BLOCK, &mask, nullptr);
+  {  // one fd per connection: lift the soft limit to the hard one (a container's default soft limit can be 1024)
+    rlimit rl;
+    if (getrlimit(RLIMIT_NOFILE, &rl) == 0 && rl.rlim_cur < rl.rlim_max) {
+      rl.rlim_cur = rl.rlim_max;
+      setrlimit(RLIMIT_NOFILE, &rl);
+    }
+  }
   signal(SIGPIPE, SIG_IGN);
   g_log.start();      // after the mask: every thread must inherit it, or a signal would land outside the signalfd
   atexit(log_flush);  // every _exit() below follows a WARN, which is written synchronously

@@ -15,6 +15,7 @@
 #include <netinet/tcp.h>
 #include <signal.h>
 #include <stdio.h>
+#include <sys/resource.h>
 #include <stdlib.h>
 #include <string.h>
 #include <sys/socket.h>
@@ -443,6 +444,13 @@ int main(int argc, char **argv) {
     else {
       fprintf(stderr, "usage: gsb_mock_kube [--node NAME] [--pods N] [--mod] [--pad BYTES]\n");
       return 64;
+    }
+  }
+  {  // one fd per connection: lift the soft limit to the hard one (a container's default soft limit can be 1024)
+    rlimit rl;
+    if (getrlimit(RLIMIT_NOFILE, &rl) == 0 && rl.rlim_cur < rl.rlim_max) {
+      rl.rlim_cur = rl.rlim_max;
+      setrlimit(RLIMIT_NOFILE, &rl);
     }
   }
   signal(SIGPIPE, SIG_IGN);
