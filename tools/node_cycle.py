@@ -23,18 +23,31 @@ for _ in range(5):
     node.step()
 t0 = time.perf_counter()
 kern = [0] * n
+inv = [[] for _ in range(n)]  # per device: ns the NVML query + encode took inside the cycle (runs while the kernel does)
+per_step = []
 for _ in range(steps):
+    ts = time.perf_counter_ns()
     res = node.step()
+    per_step.append(time.perf_counter_ns() - ts)
     assert all(r.healthy for r in res)
     for i, r in enumerate(res):
         kern[i] += r.probe.kernel_ns
+        inv[i].append(r.inventory_ns)
 wall = time.perf_counter() - t0
+per_step.sort()
 w = wgib * GiB if wgib else min(arenas)
 out = {"n_gpus": n, "steps": steps, "window_bytes": w, "node_cycles_per_s": steps / wall,
        "device_cycles_per_s": n * steps / wall, "ms_per_node_cycle": wall * 1e3 / steps,
        "kernel_ms_per_cycle_per_device": [k / 1e6 / steps for k in kern],
        "aggregate_hbm_gbs": sum(2 * w * steps / (k / 1e9) / 1e9 for k in kern),
-       "lw_bytes": node.lw_len, "devices_advertised": 179 * n}
+       "lw_bytes": node.lw_len, "devices_advertised": 179 * n,
+       # where a slow node cycle spends its time (the round-1 open item: 0.4 ms in some processes, 1-2 ms in others)
+       "step_ms": {"min": per_step[0] / 1e6, "p50": per_step[len(per_step) // 2] / 1e6,
+                   "p99": per_step[min(len(per_step) - 1, int(len(per_step) * 0.99))] / 1e6, "max": per_step[-1] / 1e6},
+       "inventory_us_p50_per_device": [sorted(v)[len(v) // 2] / 1e3 for v in inv],
+       "inventory_us_max_per_device": [max(v) / 1e3 for v in inv],
+       "knobs": {k: os.environ[k] for k in ("GSB_WORKER_SPIN_US", "GSB_NVML_SERIAL", "GSB_CYCLE_ORDER") if k in os.environ},
+       "cpus_allowed": len(os.sched_getaffinity(0))}
 ref = subprocess.run(["taskset", "-c", "0", os.path.join(ROOT, "oracle", "_ref", "ref_inventory"), "bench", "--iters", "50"],
                      capture_output=True, text=True)
 if ref.returncode == 0:
