@@ -350,15 +350,29 @@ struct Kube {
       *err = "unable to load in-cluster configuration, KUBERNETES_SERVICE_HOST and KUBERNETES_SERVICE_PORT must be defined";
       return false;
     }
-    const std::string sa = "/var/run/secrets/kubernetes.io/serviceaccount/";
-    return api.configure(std::string("https://") + h + ":" + p, read_file(sa + "token"), sa + "ca.crt", false, 30, err);
+    const char *sa_dir = getenv("GSBD_SERVICEACCOUNT_DIR");  // tests; the pod's mount otherwise
+    const std::string sa = sa_dir ? std::string(sa_dir) + "/" : "/var/run/secrets/kubernetes.io/serviceaccount/";
+    token_file = sa + "token";
+    std::string tok = read_file(token_file);
+    while (!tok.empty() && (tok.back() == '\n' || tok.back() == '\r')) tok.pop_back();
+    return api.configure(std::string("https://") + h + ":" + p, tok, sa + "ca.crt", false, 30, err);
   }
+  std::string token_file;  // in-cluster only: the kubelet rewrites it before the token it holds expires
 
   // returns false + *err (= Status.message when the apiserver answered) on failure
   bool call(const std::string &method, const std::string &path, const std::string &body, const std::string &ctype,
             json::Value *out, std::string *err) {
     http::Response r;
     if (!api.request(method, path, body, ctype, &r, err)) return false;
+    if (r.status == 401 && !token_file.empty()) {  // rotated service-account token: pick up the new one, once
+      std::string tok = read_file(token_file);
+      while (!tok.empty() && (tok.back() == '\n' || tok.back() == '\r')) tok.pop_back();
+      if (!tok.empty() && tok != api.token()) {
+        api.set_token(tok);
+        r = http::Response();
+        if (!api.request(method, path, body, ctype, &r, err)) return false;
+      }
+    }
     json::Value v;
     const bool parsed = json::parse(r.body, &v);
     if (r.status >= 400) {

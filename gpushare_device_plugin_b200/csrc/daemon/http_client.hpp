@@ -329,13 +329,24 @@ class Client {
     return true;
   }
 
+  // bearer token, replaceable while requests are in flight (a projected service-account token is rotated on disk)
+  std::string token() {
+    std::lock_guard<std::mutex> lk(mu_);
+    return token_;
+  }
+  void set_token(const std::string &t) {
+    std::lock_guard<std::mutex> lk(mu_);
+    token_ = t;
+  }
+
   // A dedicated connection for a long-lived GET (watch): returns the connection with the request already sent.
   std::unique_ptr<Conn> open_stream(const std::string &path, int read_timeout_s, std::string *err) {
     std::unique_ptr<Conn> c(new Conn());
     if (!c->open(host_, port_, ctx_, host_, timeout_s_, err, !insecure_)) return nullptr;
     c->set_read_timeout(read_timeout_s);
     std::string req = "GET " + path + " HTTP/1.1\r\nHost: " + host_ + "\r\nAccept: application/json\r\n";
-    if (!token_.empty()) req += "Authorization: Bearer " + token_ + "\r\n";
+    const std::string tok = token();
+    if (!tok.empty()) req += "Authorization: Bearer " + tok + "\r\n";
     req += "\r\n";
     if (!c->write_all(req)) {
       *err = "GET " + path + ": connection failed";
@@ -348,7 +359,8 @@ class Client {
   bool request(const std::string &method, const std::string &path, const std::string &body,
                const std::string &content_type, Response *out, std::string *err) {
     std::string req = method + " " + path + " HTTP/1.1\r\nHost: " + host_ + "\r\nAccept: application/json\r\n";
-    if (!token_.empty()) req += "Authorization: Bearer " + token_ + "\r\n";
+    const std::string tok = token();
+    if (!tok.empty()) req += "Authorization: Bearer " + tok + "\r\n";
     if (!content_type.empty()) req += "Content-Type: " + content_type + "\r\n";
     if (!body.empty() || method == "PATCH" || method == "POST" || method == "PUT")
       req += "Content-Length: " + std::to_string(body.size()) + "\r\n";

@@ -68,6 +68,7 @@ class MockKube:
         self.enable_watch = True
         self.patch_delay = 0.0
         self.patched_ok: List[str] = []  # pod PATCHes that were applied (requests[] also holds the refused ones)
+        self.required_token: Optional[str] = None  # when set: any other bearer token is answered 401 Unauthorized
         self.lock = threading.Lock()
         self.nodes: Dict[str, dict] = {node["metadata"]["name"]: node}
         self.pods: Dict[tuple, dict] = {(p["metadata"]["namespace"], p["metadata"]["name"]): p for p in pods}
@@ -106,8 +107,19 @@ class MockKube:
                 self._send(code, {"kind": "Status", "apiVersion": "v1", "status": "Failure", "message": message,
                                   "code": code})
 
+            def _authorized(self) -> bool:
+                if mock.required_token is None or self.headers.get("Authorization") == "Bearer " + mock.required_token:
+                    return True
+                n = int(self.headers.get("Content-Length", "0"))
+                if n:
+                    self.rfile.read(n)
+                self._status(401, "Unauthorized")
+                return False
+
             def do_GET(self):
                 mock.auth_headers.append(self.headers.get("Authorization"))
+                if not self._authorized():
+                    return
                 u = urllib.parse.urlparse(self.path)
                 parts = [p for p in u.path.split("/") if p]
                 with mock.lock:
@@ -190,6 +202,9 @@ class MockKube:
                 self.close_connection = True
 
             def do_PATCH(self):
+                mock.auth_headers.append(self.headers.get("Authorization"))
+                if not self._authorized():
+                    return
                 u = urllib.parse.urlparse(self.path)
                 parts = [p for p in u.path.split("/") if p]
                 body = self.rfile.read(int(self.headers.get("Content-Length", "0")))

@@ -117,6 +117,46 @@ class TestNativeDaemonTls:
             kube.close()
 
 
+@pytest.mark.skipif(not os.access(GSBD, os.X_OK), reason="gsbd not built")
+def test_in_cluster_config_and_rotated_service_account_token(pki, tmp_path):
+    """rest.InClusterConfig (podmanager.go:32-40): KUBERNETES_SERVICE_HOST/PORT + the mounted token and ca.crt. The
+    kubelet rewrites a projected token before it expires; a 401 makes the daemon read the file again, once."""
+    kube = MockKube(make_node(NODE), config4_pods(NODE), tls=(str(pki / "server.crt"), str(pki / "server.key")))
+    kube.required_token = "token-1"
+    sa = tmp_path / "sa"
+    sa.mkdir()
+    (sa / "token").write_text("token-1\n")
+    (sa / "ca.crt").write_bytes((pki / "ca.crt").read_bytes())
+    kubelet = FakeKubelet(str(tmp_path))
+    env = dict(os.environ, NODE_NAME=NODE, KUBERNETES_SERVICE_HOST="127.0.0.1", KUBERNETES_SERVICE_PORT=str(kube.port),
+               GSBD_SERVICEACCOUNT_DIR=str(sa), GPUSHARE_PLUGIN_DIR=str(tmp_path) + "/", GPUSHARE_RETRY_SLEEP_MS="1",
+               GSBD_ALLOW_FAKE_INVENTORY="1")
+    env.pop("KUBECONFIG", None)
+    log = open(tmp_path / "gsbd.log", "w")
+    p = subprocess.Popen([GSBD, "--v=5", "--fake-inventory", "8", "--pod-informer=false"], env=env, stderr=log, stdout=log)
+    try:
+        kubelet.register_requests.get(timeout=20)
+        ch = kubelet.channel("aliyungpushare.sock")
+        req = wo.marshal_AllocateRequest([["a", "b", "c", "d"]])
+        assert wo.unmarshal_AllocateResponse(kubelet.allocate(ch, req))[0]["ALIYUN_COM_GPU_MEM_IDX"] == "0"
+        # rotation: the apiserver stops honouring the old token, the new one is on disk
+        (sa / "token").write_text("token-2\n")
+        kube.required_token = "token-2"
+        for _ in range(3):
+            assert wo.unmarshal_AllocateResponse(kubelet.allocate(ch, req))[0]["ALIYUN_COM_GPU_MEM_IDX"] == "0"
+        assert kube.auth_headers.count("Bearer token-1") >= 3 and "Bearer token-2" in kube.auth_headers
+        # a token that is simply wrong (file unchanged) is not retried for ever: the request is refused
+        kube.required_token = "token-3"
+        assert wo.unmarshal_AllocateResponse(kubelet.allocate(ch, req))[0]["ALIYUN_COM_GPU_MEM_IDX"] == "-1"
+        ch.close()
+    finally:
+        p.terminate()
+        p.wait(timeout=10)
+        log.close()
+        kubelet.stop()
+        kube.close()
+
+
 def test_python_kube_client_tls_forms(pki, tmp_path, monkeypatch):
     kube = MockKube(make_node(NODE), config4_pods(NODE), tls=(str(pki / "server.crt"), str(pki / "server.key")),
                     client_ca=str(pki / "ca.crt"))
