@@ -46,6 +46,7 @@ class Clientset:
             if cert:
                 self.ctx.load_cert_chain(*cert)
         self._tl = threading.local()
+        self.token_file: Optional[str] = None  # in-cluster only: the kubelet rewrites it before the token expires
 
     def _conn(self) -> http.client.HTTPConnection:
         c = getattr(self._tl, "conn", None)
@@ -62,6 +63,19 @@ class Clientset:
         return c
 
     def request(self, method: str, path: str, body: Optional[bytes] = None, content_type: Optional[str] = None):
+        try:
+            return self._request(method, path, body, content_type)
+        except ApiError as e:
+            if e.status != 401 or not self.token_file:
+                raise
+            with open(self.token_file) as f:  # rotated service-account token: pick up the new one, once
+                fresh = f.read().strip()
+            if not fresh or fresh == self.token:
+                raise
+            self.token = fresh
+            return self._request(method, path, body, content_type)
+
+    def _request(self, method: str, path: str, body: Optional[bytes] = None, content_type: Optional[str] = None):
         headers = {"Accept": "application/json"}
         if self.token:
             headers["Authorization"] = "Bearer " + self.token
@@ -136,5 +150,7 @@ def from_environment() -> Clientset:
         raise RuntimeError("unable to load in-cluster configuration, KUBERNETES_SERVICE_HOST and "
                            "KUBERNETES_SERVICE_PORT must be defined")
     with open(os.path.join(SA_DIR, "token")) as f:
-        token = f.read()
-    return Clientset(f"https://{host}:{port}", token=token, ca_file=os.path.join(SA_DIR, "ca.crt"))
+        token = f.read().strip()
+    cs = Clientset(f"https://{host}:{port}", token=token, ca_file=os.path.join(SA_DIR, "ca.crt"))
+    cs.token_file = os.path.join(SA_DIR, "token")
+    return cs

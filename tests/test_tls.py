@@ -174,3 +174,28 @@ def test_python_kube_client_tls_forms(pki, tmp_path, monkeypatch):
             kubeclient.from_environment().get_node(NODE)
     finally:
         kube.close()
+
+
+def test_python_kube_client_in_cluster_and_rotated_token(pki, tmp_path, monkeypatch):
+    kube = MockKube(make_node(NODE), config4_pods(NODE), tls=(str(pki / "server.crt"), str(pki / "server.key")))
+    kube.required_token = "token-1"
+    try:
+        sa = tmp_path / "sa"
+        sa.mkdir()
+        (sa / "token").write_text("token-1\n")
+        (sa / "ca.crt").write_bytes((pki / "ca.crt").read_bytes())
+        monkeypatch.delenv("KUBECONFIG", raising=False)
+        monkeypatch.setenv("KUBERNETES_SERVICE_HOST", "127.0.0.1")
+        monkeypatch.setenv("KUBERNETES_SERVICE_PORT", str(kube.port))
+        monkeypatch.setattr(kubeclient, "SA_DIR", str(sa))
+        cs = kubeclient.from_environment()
+        assert cs.get_node(NODE)["metadata"]["name"] == NODE
+        (sa / "token").write_text("token-2\n")
+        kube.required_token = "token-2"
+        assert cs.get_node(NODE)["metadata"]["name"] == NODE and cs.token == "token-2"
+        kube.required_token = "token-3"  # simply wrong, nothing new on disk: the error surfaces
+        with pytest.raises(kubeclient.ApiError) as e:
+            cs.get_node(NODE)
+        assert e.value.status == 401
+    finally:
+        kube.close()
