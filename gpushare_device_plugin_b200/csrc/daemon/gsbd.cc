@@ -9,6 +9,9 @@
 //   pod / node helpers          pkg/gpu/nvidia/podmanager.go, podutils.go
 //   kubelet /pods/ client       pkg/kubelet/client/client.go:75-134
 // gRPC framing is csrc/daemon/h2.hpp; every message byte comes from the C ABI encoders.
+// Pieces private to this translation unit: gsbd_log.hpp (constants, logging), gsbd_flags.hpp (command line),
+// gsbd_kube.hpp (apiserver client configuration and calls), gsbd_pods.hpp (pod JSON -> gsb_pod table); this file is
+// the plugin (server.go + allocate.go) and the manager loop.
 #include <fcntl.h>
 #include <poll.h>
 #include <signal.h>
@@ -43,517 +46,12 @@
 #include "http_client.hpp"
 #include "json.hpp"
 
+#include "gsbd_flags.hpp"
+#include "gsbd_kube.hpp"
+#include "gsbd_log.hpp"
+#include "gsbd_pods.hpp"
+
 namespace {
-
-// ---------------------------------------------------------------- constants (const.go, v1beta1/constants.go)
-const char kResourceName[] = "aliyun.com/gpu-mem";
-const char kResourceCount[] = "aliyun.com/gpu-count";
-const char kDevicePluginPath[] = "/var/lib/kubelet/device-plugins/";
-const char kServerSockName[] = "aliyungpushare.sock";
-const char kOptimisticLockErrorMsg[] =
-    "the object has been modified; please apply your changes to the latest version and try again";
-const char kEnvResourceIndex[] = "ALIYUN_COM_GPU_MEM_IDX";
-const char kEnvAssignedFlag[] = "ALIYUN_COM_GPU_MEM_ASSIGNED";
-const char kEnvResourceAssumeTime[] = "ALIYUN_COM_GPU_MEM_ASSUME_TIME";
-const char kEnvNodeLabelForDisableCGPU[] = "cgpu.disable.isolation";
-
-// ---------------------------------------------------------------- logging (glog-shaped, stderr)
-// The reference logs synchronously from inside Allocate's critical section (>= 6 glog lines per call at --v=5,
-// SURVEY §8 a12). Here a line is formatted by the caller and handed to one writer thread; the RPC path never
-// waits for stderr (a container runtime's log pipe). Order is preserved; warnings and errors, and everything
-// when GSBD_SYNC_LOG=1, are written before logf returns; log_flush() runs before every exit.
-int g_v = 0;
-class AsyncLog {
- public:
-  void write(const char *line, size_t n, bool sync) {
-    std::unique_lock<std::mutex> lk(mu_);
-    buf_.append(line, n);
-    if (sync || !running_ || buf_.size() > (1u << 20)) {  // also the back-pressure path: never grow without bound
-      drain_locked();
-      return;
-    }
-    if (idle_) cv_.notify_one();
-  }
-  void start() {
-    std::lock_guard<std::mutex> lk(mu_);
-    if (running_ || getenv("GSBD_SYNC_LOG")) return;
-    running_ = true;
-    th_ = std::thread([this] { run(); });
-  }
-  void flush() {  // stop the writer and write what is left; logging stays usable (synchronous) afterwards
-    {
-      std::lock_guard<std::mutex> lk(mu_);
-      if (!running_) {
-        drain_locked();
-        return;
-      }
-      running_ = false;
-      cv_.notify_one();
-    }
-    th_.join();
-    std::lock_guard<std::mutex> lk(mu_);
-    drain_locked();
-  }
-
- private:
-  void drain_locked() {
-    if (buf_.empty()) return;
-    fwrite(buf_.data(), 1, buf_.size(), stderr);
-    fflush(stderr);
-    buf_.clear();
-  }
-  void run() {
-    std::string out;
-    std::unique_lock<std::mutex> lk(mu_);
-    while (running_) {
-      if (buf_.empty()) {
-        idle_ = true;
-        cv_.wait(lk, [this] { return !running_ || !buf_.empty(); });
-        idle_ = false;
-      }
-      out.swap(buf_);
-      lk.unlock();
-      if (!out.empty()) {
-        fwrite(out.data(), 1, out.size(), stderr);
-        fflush(stderr);
-        out.clear();
-      }
-      lk.lock();
-    }
-  }
-  std::mutex mu_;
-  std::condition_variable cv_;
-  std::string buf_;
-  bool running_ = false, idle_ = false;
-  std::thread th_;
-} g_log;
-void log_flush() { g_log.flush(); }
-
-void logf(char sev, const char *fmt, ...) {
-  char line[2200];
-  timeval tv;
-  gettimeofday(&tv, nullptr);
-  tm t;
-  localtime_r(&tv.tv_sec, &t);
-  int n = snprintf(line, 64, "%c%02d%02d %02d:%02d:%02d.%06ld %7d gsbd] ", sev, t.tm_mon + 1, t.tm_mday, t.tm_hour,
-                   t.tm_min, t.tm_sec, (long)tv.tv_usec, (int)getpid());
-  va_list ap;
-  va_start(ap, fmt);
-  const int m = vsnprintf(line + n, sizeof line - (size_t)n - 1, fmt, ap);
-  va_end(ap);
-  n += m < 0 ? 0 : std::min(m, (int)sizeof line - n - 2);
-  line[n++] = '\n';
-  g_log.write(line, (size_t)n, sev != 'I');
-}
-#define INFO(...) logf('I', __VA_ARGS__)
-#define WARN(...) logf('W', __VA_ARGS__)
-#define VLOG(n, ...)                 \
-  do {                               \
-    if (g_v >= (n)) logf('I', __VA_ARGS__); \
-  } while (0)
-
-std::string last_error() {
-  char buf[512];
-  gsb_last_error(buf, sizeof buf);
-  return buf;
-}
-
-// ---------------------------------------------------------------- flags (cmd/nvidia/main.go:15-26 + glog's)
-struct Flags {
-  bool mps = false, health_check = false, query_kubelet = false;
-  std::string memory_unit = "GiB", kubelet_address = "0.0.0.0", client_cert, client_key, token;
-  int kubelet_port = 10250, timeout = 10;
-  // additions (active probe, test hooks); none changes the wire contract
-  int probe_period_ms = 1000, probe_window_mib = 1024, probe_arena_mib = 4096, fake_inventory = 0;
-  int health_recovery_cycles = 0;  // 0 = the reference's sticky Unhealthy
-  bool startup_full_walk = false, coalesce_health = true, pod_informer = true;
-  double pod_cache_ttl = 1.0;
-  std::string kube_api_url, kubelet_scheme = "https";
-};
-
-bool parse_bool(const std::string &v) { return v == "" || v == "1" || v == "t" || v == "T" || v == "true" || v == "TRUE" || v == "True"; }
-
-// What Go's flag package prints for -h / an undefined flag (PrintDefaults: sorted by name, "  -name type" then a
-// tab-indented description with the non-zero default). The first ten are cmd/nvidia/main.go:15-26 verbatim.
-void usage(const char *prog) {
-  fprintf(stderr, "Usage of %s:\n", prog);
-  static const char *const lines[][2] = {
-      {"-client-cert string", "Kubelet TLS client certificate"},
-      {"-client-key string", "Kubelet TLS client key"},
-      {"-coalesce-health", "Fold the health events already queued into one ListAndWatch resend; false = one resend per fake device, as the reference (default true)"},
-      {"-health-check", "Enable or disable Health check"},
-      {"-health-recovery-cycles int", "Consecutive clean probe cycles after which a probe-faulted GPU is Healthy again; 0 = sticky Unhealthy, as the reference"},
-      {"-kube-api-url string", "Apiserver base URL instead of KUBECONFIG / in-cluster discovery"},
-      {"-kubelet-address string", "Kubelet IP Address (default \"0.0.0.0\")"},
-      {"-kubelet-port uint", "Kubelet listened Port (default 10250)"},
-      {"-kubelet-scheme string", "http or https for the kubelet /pods/ client (default \"https\")"},
-      {"-memory-unit string", "Set memoryUnit of the GPU Memroy, support 'GiB' and 'MiB' (default \"GiB\")"},
-      {"-mps", "Enable or Disable MPS"},
-      {"-pod-cache-ttl float", "Seconds a pending-pod LIST may be reused when the watch informer is off or down; 0 = LIST on every Allocate (default 1)"},
-      {"-pod-informer", "Keep the pending-pod table current from a LIST + watch stream instead of LISTing inside Allocate (default true)"},
-      {"-probe-arena-mib int", "HBM probe arena per GPU in MiB; 0 = everything allocatable (default 4096)"},
-      {"-probe-period-ms int", "Period of the HBM health probe per GPU (default 1000)"},
-      {"-probe-window-mib int", "HBM bytes verified and re-written per probe cycle (default 1024)"},
-      {"-query-kubelet", "Query pending pods from kubelet instead of kube-apiserver"},
-      {"-startup-full-walk", "Verify the whole arena once before serving"},
-      {"-timeout int", "Kubelet client http timeout duration (default 10)"},
-      {"-token string", "Kubelet client bearer token"},
-      {"-v value", "log level for V logs (glog)"},
-  };
-  for (auto &l : lines) fprintf(stderr, "  %s\n    \t%s\n", l[0], l[1]);
-}
-
-// Go's flag syntax: -f, --f, -f=v, -f v (non-boolean). Returns 0 = go on, otherwise the process exit code + 1.
-int parse_flags(int argc, char **argv, Flags *f) {
-  for (int i = 1; i < argc; i++) {
-    std::string a = argv[i];
-    if (a.size() < 2 || a[0] != '-') {
-      fprintf(stderr, "unexpected argument %s\n", a.c_str());
-      return 3;
-    }
-    a.erase(0, a[1] == '-' ? 2 : 1);
-    std::string name = a, val;
-    bool has_val = false;
-    const size_t eq = a.find('=');
-    if (eq != std::string::npos) {
-      name = a.substr(0, eq);
-      val = a.substr(eq + 1);
-      has_val = true;
-    }
-    if (name == "h" || name == "help") {  // flag.ErrHelp: usage, exit status 0
-      usage(argv[0]);
-      return 1;
-    }
-    auto need = [&]() -> bool {
-      if (has_val) return true;
-      if (i + 1 >= argc) {
-        fprintf(stderr, "flag needs an argument: -%s\n", name.c_str());
-        usage(argv[0]);
-        return false;
-      }
-      val = argv[++i];
-      return true;
-    };
-    auto boolean = [&](bool *dst) { *dst = has_val ? parse_bool(val) : true; };
-    if (name == "mps") boolean(&f->mps);
-    else if (name == "health-check") boolean(&f->health_check);
-    else if (name == "query-kubelet") boolean(&f->query_kubelet);
-    else if (name == "startup-full-walk") boolean(&f->startup_full_walk);
-    else if (name == "coalesce-health") boolean(&f->coalesce_health);
-    else if (name == "pod-informer") boolean(&f->pod_informer);
-    else if (name == "logtostderr" || name == "alsologtostderr") { bool ignored; boolean(&ignored); }
-    else if (name == "memory-unit") { if (!need()) return 3; f->memory_unit = val; }
-    else if (name == "kubelet-address") { if (!need()) return 3; f->kubelet_address = val; }
-    else if (name == "kubelet-port") { if (!need()) return 3; f->kubelet_port = atoi(val.c_str()); }
-    else if (name == "client-cert") { if (!need()) return 3; f->client_cert = val; }
-    else if (name == "client-key") { if (!need()) return 3; f->client_key = val; }
-    else if (name == "token") { if (!need()) return 3; f->token = val; }
-    else if (name == "timeout") { if (!need()) return 3; f->timeout = atoi(val.c_str()); }
-    else if (name == "v") { if (!need()) return 3; g_v = atoi(val.c_str()); }
-    else if (name == "stderrthreshold" || name == "log_dir" || name == "vmodule" || name == "log_backtrace_at") { if (!need()) return 3; }
-    else if (name == "probe-period-ms") { if (!need()) return 3; f->probe_period_ms = atoi(val.c_str()); }
-    else if (name == "probe-window-mib") { if (!need()) return 3; f->probe_window_mib = atoi(val.c_str()); }
-    else if (name == "probe-arena-mib") { if (!need()) return 3; f->probe_arena_mib = atoi(val.c_str()); }
-    else if (name == "health-recovery-cycles") { if (!need()) return 3; f->health_recovery_cycles = atoi(val.c_str()); }
-    else if (name == "pod-cache-ttl") { if (!need()) return 3; f->pod_cache_ttl = atof(val.c_str()); }
-    else if (name == "kube-api-url") { if (!need()) return 3; f->kube_api_url = val; }
-    else if (name == "kubelet-scheme") { if (!need()) return 3; f->kubelet_scheme = val; }
-    else if (name == "fake-inventory") { if (!need()) return 3; f->fake_inventory = atoi(val.c_str()); }
-    else {
-      fprintf(stderr, "flag provided but not defined: -%s\n", name.c_str());
-      usage(argv[0]);
-      return 3;  // flag.ExitOnError: exit status 2
-    }
-  }
-  return 0;
-}
-
-std::string read_file(const std::string &p) {
-  std::ifstream f(p);
-  std::stringstream ss;
-  ss << f.rdbuf();
-  return ss.str();
-}
-bool file_exists(const std::string &p) {
-  struct stat st;
-  return !p.empty() && stat(p.c_str(), &st) == 0;
-}
-
-// ---------------------------------------------------------------- kube API (podmanager.go kubeInit + the calls)
-struct Kube {
-  http::Client api;
-  std::string node_name;
-
-  // kubeInit (podmanager.go:29-57): $KUBECONFIG if the file exists, else in-cluster; NODE_NAME required.
-  bool init(const Flags &f, std::string *err) {
-    const char *nn = getenv("NODE_NAME");
-    node_name = nn ? nn : "";
-    if (node_name.empty()) {
-      *err = "Please set env NODE_NAME";
-      return false;
-    }
-    if (!f.kube_api_url.empty()) return api.configure(f.kube_api_url, "", "", true, 30, err);
-    const char *kc = getenv("KUBECONFIG");
-    if (kc && file_exists(kc)) {
-      // first cluster / first user of the kubeconfig: server, token, CA (file or *-data), client cert/key
-      // (file or *-data), insecure-skip-tls-verify — the forms kubeadm / cloud kubeconfigs use
-      std::string server, token, ca;
-      http::Client::TlsExtra extra;
-      bool insecure = false;
-      std::istringstream in(read_file(kc));
-      std::string line;
-      auto val = [](const std::string &l) {
-        size_t c = l.find(':');
-        std::string v = l.substr(c + 1);
-        while (!v.empty() && (v.front() == ' ' || v.front() == '"' || v.front() == '\'')) v.erase(0, 1);
-        while (!v.empty() && (v.back() == ' ' || v.back() == '"' || v.back() == '\'' || v.back() == '\r')) v.pop_back();
-        return v;
-      };
-      auto b64 = [](const std::string &in) {
-        std::string out;
-        int acc = 0, bits = -8;
-        for (unsigned char c : in) {
-          int d = c >= 'A' && c <= 'Z' ? c - 'A' : c >= 'a' && c <= 'z' ? c - 'a' + 26 : c >= '0' && c <= '9' ? c - '0' + 52
-                  : c == '+' ? 62 : c == '/' ? 63 : -1;
-          if (d < 0) continue;
-          acc = (acc << 6) | d;
-          bits += 6;
-          if (bits >= 0) {
-            out.push_back((char)((acc >> bits) & 0xFF));
-            bits -= 8;
-          }
-        }
-        return out;
-      };
-      auto starts = [](const std::string &t, const char *k) { return t.compare(0, strlen(k), k) == 0; };
-      while (std::getline(in, line)) {
-        std::string t = line;
-        t.erase(0, t.find_first_not_of(" -"));
-        if (starts(t, "server:") && server.empty()) server = val(t);
-        else if (starts(t, "token:") && token.empty()) token = val(t);
-        else if (starts(t, "certificate-authority-data:") && extra.ca_pem.empty()) extra.ca_pem = b64(val(t));
-        else if (starts(t, "certificate-authority:") && ca.empty()) ca = val(t);
-        else if (starts(t, "client-certificate-data:") && extra.cert_pem.empty()) extra.cert_pem = b64(val(t));
-        else if (starts(t, "client-key-data:") && extra.key_pem.empty()) extra.key_pem = b64(val(t));
-        else if (starts(t, "client-certificate:") && extra.cert_file.empty()) extra.cert_file = val(t);
-        else if (starts(t, "client-key:") && extra.key_file.empty()) extra.key_file = val(t);
-        else if (starts(t, "insecure-skip-tls-verify:")) insecure = val(t) == "true";
-      }
-      if (server.empty()) {
-        *err = std::string("no cluster server in ") + kc;
-        return false;
-      }
-      return api.configure(server, token, ca, insecure, 30, err, &extra);
-    }
-    const char *h = getenv("KUBERNETES_SERVICE_HOST"), *p = getenv("KUBERNETES_SERVICE_PORT");
-    if (!h || !p) {
-      *err = "unable to load in-cluster configuration, KUBERNETES_SERVICE_HOST and KUBERNETES_SERVICE_PORT must be defined";
-      return false;
-    }
-    const char *sa_dir = getenv("GSBD_SERVICEACCOUNT_DIR");  // tests; the pod's mount otherwise
-    const std::string sa = sa_dir ? std::string(sa_dir) + "/" : "/var/run/secrets/kubernetes.io/serviceaccount/";
-    token_file = sa + "token";
-    std::string tok = read_file(token_file);
-    while (!tok.empty() && (tok.back() == '\n' || tok.back() == '\r')) tok.pop_back();
-    return api.configure(std::string("https://") + h + ":" + p, tok, sa + "ca.crt", false, 30, err);
-  }
-  std::string token_file;  // in-cluster only: the kubelet rewrites it before the token it holds expires
-
-  // returns false + *err (= Status.message when the apiserver answered) on failure
-  bool call(const std::string &method, const std::string &path, const std::string &body, const std::string &ctype,
-            json::Value *out, std::string *err) {
-    http::Response r;
-    if (!api.request(method, path, body, ctype, &r, err)) return false;
-    if (r.status == 401 && !token_file.empty()) {  // rotated service-account token: pick up the new one, once
-      std::string tok = read_file(token_file);
-      while (!tok.empty() && (tok.back() == '\n' || tok.back() == '\r')) tok.pop_back();
-      if (!tok.empty() && tok != api.token()) {
-        api.set_token(tok);
-        r = http::Response();
-        if (!api.request(method, path, body, ctype, &r, err)) return false;
-      }
-    }
-    json::Value v;
-    const bool parsed = json::parse(r.body, &v);
-    if (r.status >= 400) {
-      const json::Value *m = parsed ? v.get("message") : nullptr;
-      *err = m ? m->str() : "HTTP " + std::to_string(r.status);
-      return false;
-    }
-    if (!parsed) {
-      *err = "undecodable response from apiserver";
-      return false;
-    }
-    if (out) *out = std::move(v);
-    return true;
-  }
-};
-
-// resource.Quantity.Value(): integers with optional SI / binary suffix, fractions round up
-uint64_t quantity_value(const json::Value &q) {
-  std::string s = q.str();
-  while (!s.empty() && s.back() == ' ') s.pop_back();
-  static const struct { const char *suf; long double mult; } kSuf[] = {
-      {"Ki", 1024.0L}, {"Mi", 1048576.0L}, {"Gi", 1073741824.0L}, {"Ti", 1099511627776.0L},
-      {"Pi", 1125899906842624.0L}, {"Ei", 1152921504606846976.0L}, {"k", 1e3L}, {"M", 1e6L}, {"G", 1e9L},
-      {"T", 1e12L}, {"P", 1e15L}, {"E", 1e18L}, {"m", 1e-3L}};
-  long double mult = 1.0L;
-  for (auto &e : kSuf) {
-    const size_t n = strlen(e.suf);
-    if (s.size() > n && s.compare(s.size() - n, n, e.suf) == 0) {
-      mult = e.mult;
-      s.resize(s.size() - n);
-      break;
-    }
-  }
-  const long double v = strtold(s.c_str(), nullptr) * mult;
-  return v <= 0 ? 0 : (uint64_t)ceill(v - 1e-9L);
-}
-
-// ---------------------------------------------------------------- pending pods -> gsb_pod table
-struct PodRec {
-  std::string name, ns, uid;
-  uint64_t rv = 0;  // metadata.resourceVersion when it is a decimal number (etcd's are), else 0 = "cannot compare"
-};
-// The pending-pod table gsb_allocate reads. Rows keep the order in which the apiserver listed (then streamed)
-// them; the strings a gsb_pod points at live in heap records that never move, so an upsert touches one row.
-struct PodTable {
-  std::vector<std::unique_ptr<PodRec>> recs;
-  std::vector<gsb_pod> pods;
-  std::unordered_map<std::string, size_t> by_uid;  // live rows only
-  uint64_t list_rv = 0; // resourceVersion of the LIST the table was last rebuilt from
-  size_t dead = 0;      // rows deleted by a watch event: on_node = 0 makes gsb_allocate skip them entirely
-  bool unique = true;   // no two live rows share a uid (always true for a table the informer maintains)
-  std::chrono::steady_clock::time_point stamp;
-  bool valid = false;
-
-  void clear() {
-    recs.clear();
-    pods.clear();
-    by_uid.clear();
-    dead = 0;
-    unique = true;
-    list_rv = 0;
-  }
-  void point(size_t i) {
-    pods[i].name = recs[i]->name.c_str();
-    pods[i].ns = recs[i]->ns.c_str();
-    pods[i].uid = recs[i]->uid.c_str();
-  }
-  void append(PodRec &&r, const gsb_pod &g) {
-    recs.emplace_back(new PodRec(std::move(r)));
-    pods.push_back(g);
-    point(recs.size() - 1);
-    if (!by_uid.emplace(recs.back()->uid, recs.size() - 1).second) unique = false;  // a LIST that repeats a uid
-  }
-  void upsert(PodRec &&r, const gsb_pod &g) {
-    auto it = by_uid.find(r.uid);
-    if (it == by_uid.end()) return append(std::move(r), g);
-    *recs[it->second] = std::move(r);
-    pods[it->second] = g;
-    point(it->second);
-  }
-  void remove(const std::string &uid) {
-    auto it = by_uid.find(uid);
-    if (it == by_uid.end()) return;
-    pods[it->second].on_node = 0;
-    by_uid.erase(it);
-    if (++dead > 64 && dead * 4 > recs.size()) compact();
-  }
-  void compact() {  // drop the tombstones, keeping the order of the live rows
-    size_t w = 0;
-    for (size_t i = 0; i < recs.size(); i++) {
-      auto it = by_uid.find(recs[i]->uid);
-      if (it == by_uid.end() || it->second != i) continue;
-      if (w != i) {
-        recs[w] = std::move(recs[i]);
-        pods[w] = pods[i];
-        it->second = w;
-      }
-      w++;
-    }
-    recs.resize(w);
-    pods.resize(w);
-    dead = 0;
-  }
-};
-
-bool atoi_strict(const std::string &s, long long *out) {  // strconv.Atoi
-  size_t i = (s.size() && (s[0] == '+' || s[0] == '-')) ? 1 : 0;
-  if (i >= s.size()) return false;
-  for (size_t k = i; k < s.size(); k++)
-    if (s[k] < '0' || s[k] > '9') return false;
-  errno = 0;
-  const long long v = strtoll(s.c_str(), nullptr, 10);
-  if (errno) return false;
-  *out = v;
-  return true;
-}
-bool parse_uint64(const std::string &s, uint64_t *out) {  // strconv.ParseUint(s, 10, 64)
-  if (s.empty()) return false;
-  for (char c : s)
-    if (c < '0' || c > '9') return false;
-  errno = 0;
-  const unsigned long long v = strtoull(s.c_str(), nullptr, 10);
-  if (errno) return false;
-  *out = v;
-  return true;
-}
-
-// one v1.Pod JSON object -> (PodRec, gsb_pod) with the fields the reference reads (podutils.go:37-131)
-void pod_row(const json::Value &p, const std::string &node, PodRec *r, gsb_pod *g) {
-  const json::Value *md = p.get("metadata");
-  if (md) {
-    if (auto *v = md->get("name")) r->name = v->str();
-    if (auto *v = md->get("namespace")) r->ns = v->str();
-    if (auto *v = md->get("uid")) r->uid = v->str();
-    if (auto *v = md->get("resourceVersion")) parse_uint64(v->str(), &r->rv);
-  }
-  memset(g, 0, sizeof *g);
-  g->gpu_idx = -1;
-  if (const json::Value *cs = p.path({"spec", "containers"}))  // podutils.go:122-131: spec.containers only
-    for (const json::Value &c : cs->arr)
-      if (const json::Value *lim = c.path({"resources", "limits", kResourceName})) g->gpu_mem_limit += quantity_value(*lim);
-  const json::Value *ann = md ? md->get("annotations") : nullptr;
-  if (ann && ann->type == json::Value::Object) {
-    if (auto *v = ann->get(kEnvResourceIndex)) {
-      long long id;
-      if (atoi_strict(v->str(), &id) && id >= -2147483648LL && id <= 2147483647LL) g->gpu_idx = id < 0 ? -1 : (int32_t)id;
-    }
-    if (auto *v = ann->get(kEnvResourceAssumeTime)) {
-      g->has_assume_time = 1;
-      uint64_t at;
-      if (parse_uint64(v->str(), &at)) g->assume_time = at;
-    }
-    if (auto *v = ann->get(kEnvAssignedFlag)) {
-      g->has_assigned = 1;
-      g->assigned_is_false = v->str() == "false";
-    }
-  }
-  const json::Value *nn = p.path({"spec", "nodeName"});
-  g->on_node = nn && nn->str() == node;
-}
-
-// v1.PodList JSON -> table; `pending_only` = the kubelet path's phase filter (podmanager.go:101-123)
-void build_table(const json::Value &list, const std::string &node, bool pending_only, PodTable *t) {
-  t->clear();
-  const json::Value *items = list.get("items");
-  if (!items || items->type != json::Value::Array) return;
-  t->recs.reserve(items->arr.size());
-  t->pods.reserve(items->arr.size());
-  t->by_uid.reserve(items->arr.size() * 2);
-  for (const json::Value &p : items->arr) {
-    if (pending_only) {
-      const json::Value *ph = p.path({"status", "phase"});
-      if (!ph || ph->str() != "Pending") continue;
-    }
-    PodRec r;
-    gsb_pod g;
-    pod_row(p, node, &r, &g);
-    t->append(std::move(r), g);
-  }
-  if (const json::Value *v = list.path({"metadata", "resourceVersion"})) parse_uint64(v->str(), &t->list_rv);
-}
 
 // ---------------------------------------------------------------- the plugin (server.go)
 class Plugin {
