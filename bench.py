@@ -173,6 +173,49 @@ def run_reference_cycles(iters: int, warmup: int) -> dict:
     return json.loads(out.stdout.strip().splitlines()[-1])
 
 
+def pynvml_twin(iters: int) -> dict:
+    """the same NewDevice getter sequence (nvml.go:297-359) through pynvml, as a sanity bound on the
+    C restatement's inventory phase — an independent binding over the same libnvidia-ml calls. Never fatal."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+
+        def soft(fn, *a):  # bindings.go: NOT_SUPPORTED => nil value, not an error
+            try:
+                return fn(*a)
+            except nv.NVMLError:
+                return None
+        times = []
+        n = nv.nvmlDeviceGetCount()
+        for _ in range(iters):
+            t0 = time.perf_counter_ns()
+            for i in range(nv.nvmlDeviceGetCount()):
+                h = nv.nvmlDeviceGetHandleByIndex(i)
+                soft(nv.nvmlDeviceGetName, h)
+                soft(nv.nvmlDeviceGetUUID, h)
+                soft(nv.nvmlDeviceGetMinorNumber, h)
+                soft(nv.nvmlDeviceGetPowerManagementLimit, h)
+                soft(nv.nvmlDeviceGetMemoryInfo, h)
+                pci = soft(nv.nvmlDeviceGetPciInfo, h)
+                soft(nv.nvmlDeviceGetBAR1MemoryInfo, h)
+                soft(nv.nvmlDeviceGetMaxPcieLinkGeneration, h)
+                soft(nv.nvmlDeviceGetMaxPcieLinkWidth, h)
+                soft(nv.nvmlDeviceGetMaxClockInfo, h, nv.NVML_CLOCK_SM)
+                soft(nv.nvmlDeviceGetMaxClockInfo, h, nv.NVML_CLOCK_MEM)
+                if pci is not None:  # numaNode(busid): one sysfs read (nvml.go:262-295)
+                    bus = pci.busId.decode() if isinstance(pci.busId, bytes) else pci.busId
+                    try:
+                        with open(f"/sys/bus/pci/devices/{bus.lower()[4:] if len(bus) > 12 else bus.lower()}/numa_node") as f:
+                            f.read()
+                    except OSError:
+                        pass
+            times.append(time.perf_counter_ns() - t0)
+        times.sort()
+        return {"n_gpus": n, "iters": iters, "inventory_us_p50": times[len(times) // 2] / 1e3, "inventory_us_min": times[0] / 1e3}
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[-200:]}
+
+
 def cpu_model() -> str:
     try:
         with open("/proc/cpuinfo") as f:
@@ -316,7 +359,8 @@ def bench_reference(args) -> None:
                    "devices_seen": n, "fake_devices": r["n_devices"], "lw_bytes": r["lw_len"],
                    "register_calls_per_cycle": r["register_calls_per_cycle"], "register_rc": r["register_rc"],
                    "phases_us_p50": {"inventory": r["inventory_us"]["p50"], "health_setup": r["health_setup_us"]["p50"],
-                                     "health_poll": r["health_poll_us"]["p50"]}},
+                                     "health_poll": r["health_poll_us"]["p50"]},
+                   "pynvml_twin": pynvml_twin(min(args.steps, 50))},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
                          "sample": f"{args.steps} cycles of oracle/_ref/ref_inventory (reference's nvml_dl.c), "
                                    f"taskset -c 0, {cpu_model()}, nproc={os.cpu_count()}"},

@@ -27,6 +27,7 @@ static unsigned long registered;
 static long idx_of(nvmlDevice_t d) { return (long)(size_t)d - 1; }
 
 nvmlReturn_t nvmlInit_v2(void) { return NVML_SUCCESS; }
+nvmlReturn_t nvmlInitWithFlags(unsigned flags) { (void)flags; return NVML_SUCCESS; }  /* what pynvml.nvmlInit() calls */
 nvmlReturn_t nvmlShutdown(void) { return NVML_SUCCESS; }
 const char *nvmlErrorString(nvmlReturn_t r) { return r == NVML_SUCCESS ? "Success" : r == NVML_ERROR_TIMEOUT ? "Timeout" : "Unknown Error"; }
 nvmlReturn_t nvmlSystemGetDriverVersion(char *v, unsigned n) { snprintf(v, n, "580.159.03"); return NVML_SUCCESS; }

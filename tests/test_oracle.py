@@ -108,3 +108,18 @@ class TestReferenceRestatement:
         # per fake device: GetCount + (HandleByIndex + GetUUID) x (gpu index + 1) + RegisterEvents
         want = sum(179 * (1 + 2 * (g + 1) + 1) for g in range(8))
         assert j["register_calls_per_cycle"] == want == 15752
+
+
+def test_pynvml_twin_of_the_reference_inventory_runs_against_the_fake_nvml():
+    """bench.py --impl reference also times the NewDevice getter sequence (nvml.go:297-359) through pynvml as a
+    sanity bound; here the same function against oracle/_fake's libnvidia-ml stand-in."""
+    import subprocess
+    import sys
+    fake = os.path.join(ROOT, "oracle", "_fake")
+    if not os.path.exists(os.path.join(fake, "libnvidia-ml.so.1")):
+        pytest.skip("oracle/_fake not built")
+    env = dict(os.environ, LD_LIBRARY_PATH=fake, FAKE_NVML_GPUS="8", PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, "-c", "import bench, json; print(json.dumps(bench.pynvml_twin(3)))"],
+                         capture_output=True, text=True, env=env, cwd=ROOT, timeout=120)
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r.get("n_gpus") == 8 and r["iters"] == 3 and r["inventory_us_p50"] > 0, (r, out.stderr[-500:])
