@@ -359,7 +359,10 @@ class Plugin {
         }
         resync_ = false;
       }
-      std::unique_ptr<http::Conn> conn = kube_->api.open_stream("/api/v1/pods?watch=true&" + sel + "&resourceVersion=" + rv, 300, &err);
+      // the server ends the stream itself (timeoutSeconds) before our read timeout would: a quiet node re-lists every
+      // 4.5 min, a dead peer is noticed after 5; bookmarks keep resourceVersion fresh on quiet streams
+      std::unique_ptr<http::Conn> conn = kube_->api.open_stream(
+          "/api/v1/pods?watch=true&allowWatchBookmarks=true&timeoutSeconds=270&" + sel + "&resourceVersion=" + rv, 300, &err);
       if (!conn) {
         synced_ = false;
         backoff(&failures);
