@@ -199,3 +199,57 @@ def test_python_kube_client_in_cluster_and_rotated_token(pki, tmp_path, monkeypa
         assert e.value.status == 401
     finally:
         kube.close()
+
+
+@pytest.mark.skipif(not os.access(GSBD, os.X_OK), reason="gsbd not built")
+def test_concurrent_allocates_and_watch_over_tls(pki, tmp_path):
+    """The HTTPS client under concurrency: pooled TLS connections for the PATCHes, a long-lived TLS watch stream, pod
+    churn feeding it. (tools/sanitize.sh runs this under TSan and ASan: one SSL_CTX shared by every connection.)"""
+    import threading
+    import time
+
+    from gpushare_device_plugin_b200.testing.mock_kube import make_pod
+    kube = MockKube(make_node(NODE), config4_pods(NODE), tls=(str(pki / "server.crt"), str(pki / "server.key")))
+    kc = kubeconfig(tmp_path / "kc", kube.url, [f"certificate-authority: {pki / 'ca.crt'}"], ["token: t"])
+    kubelet = FakeKubelet(str(tmp_path))
+    env = dict(os.environ, NODE_NAME=NODE, KUBECONFIG=kc, GPUSHARE_PLUGIN_DIR=str(tmp_path) + "/", GPUSHARE_RETRY_SLEEP_MS="1",
+               GSBD_ALLOW_FAKE_INVENTORY="1")
+    log = open(tmp_path / "gsbd.log", "w")
+    p = subprocess.Popen([GSBD, "--v=5", "--fake-inventory", "8"], env=env, stderr=log, stdout=log)
+    try:
+        kubelet.register_requests.get(timeout=20)
+        stop, results, errors = threading.Event(), [], []
+
+        def allocator():
+            ch = kubelet.channel("aliyungpushare.sock")
+            try:
+                while not stop.is_set():
+                    results.append(wo.unmarshal_AllocateResponse(
+                        kubelet.allocate(ch, wo.marshal_AllocateRequest([["a", "b"]])))[0]["ALIYUN_COM_GPU_MEM_IDX"])
+            except Exception as e:  # noqa: BLE001
+                errors.append(repr(e))
+            finally:
+                ch.close()
+
+        def churn():
+            i = 1000
+            while not stop.is_set():
+                kube.add_pod(make_pod(i, NODE, gpu_mem=2, idx=i % 8, assume_time=1_800_000_000_000_000_000 + i))
+                i += 1
+                time.sleep(0.005)
+        ts = [threading.Thread(target=allocator) for _ in range(6)] + [threading.Thread(target=churn)]
+        [t.start() for t in ts]
+        time.sleep(3)
+        stop.set()
+        [t.join(30) for t in ts]
+        applied = list(kube.patched_ok)
+        assert not errors and len(applied) > 100 and len(applied) == len(set(applied))
+        assert len([r for r in results if r != "-1"]) == len(applied) and kube.watches_served >= 1
+        p.terminate()
+        assert p.wait(timeout=15) == 0
+    finally:
+        if p.poll() is None:
+            p.kill()
+        log.close()
+        kubelet.stop()
+        kube.close()
