@@ -270,3 +270,31 @@ def test_request_decoder_known_edge_cases():
     for req, want in cases.items():
         assert _oracle_decode(req) == want, req.hex()
         assert _product_decode(req) == want, req.hex()
+
+
+# ---- google.protobuf as an independent witness of the Allocate wire bytes ----------------------------------------
+
+from .test_wire import pb  # noqa: E402,F401  (module-scoped fixture: descriptors with the reference's field numbers)
+
+
+@settings(max_examples=100, deadline=None)
+@given(reqs=st.lists(st.lists(st.text(alphabet="GPU-0123456789abcdef_", min_size=1, max_size=48), max_size=6), max_size=4),
+       pods=st.lists(pod_strategy, max_size=10), one_gpu=st.booleans())
+def test_protobuf_library_reads_and_writes_the_same_allocate_bytes(pb, reqs, pods, one_gpu):  # noqa: F811
+    """Requests serialised by google.protobuf are decoded by gsb_allocate like the oracle's; the response bytes parse
+    with google.protobuf into the envs the oracle computes (map entries, repeated messages, field numbers)."""
+    m = pb["AllocateRequest"]()
+    for ids in reqs:
+        m.container_requests.add().devicesIDs.extend(ids)
+    req = m.SerializeToString()
+    assert req == wo.marshal_AllocateRequest(reqs)
+    dev = {UUIDS[0]: 5} if one_gpu else MINORS8
+    actx = AllocateContext(dev, 179, True, False)
+    table, _keep = pod_table(pods, NODE)
+    buf = C.create_string_buffer(1 << 16)
+    n, pidx, preq = C.c_size_t(0), C.c_int32(-1), C.c_uint32(0)
+    assert _abi.lib.gsb_allocate(C.byref(actx.ctx), table, len(pods), req, len(req), buf, len(buf), C.byref(n),
+                                 C.byref(pidx), C.byref(preq)) > 0
+    got = pb["AllocateResponse"].FromString(buf.raw[: n.value])
+    want, _ = wo.Allocate(reqs, pods, NODE, dev, 179, wo.GiBPrefix, False)
+    assert [dict(c.envs) for c in got.container_responses] == want
