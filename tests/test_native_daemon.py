@@ -602,3 +602,31 @@ def test_everything_at_once_for_a_few_seconds(world, mode):
     ch.close()
     d.proc.send_signal(signal.SIGTERM)
     assert d.proc.wait(timeout=20) == 0
+
+
+def test_resource_quantity_spellings_are_read_like_quantity_value(world):
+    """podutils.go:122-131 sums `limits["aliyun.com/gpu-mem"].Value()`: resource.Quantity accepts decimal and binary SI
+    suffixes, exponents and fractions, and Value() rounds fractions up. The daemon's reader (C++), the Python front
+    end's and the oracle's agree on every spelling below."""
+    from gpushare_device_plugin_b200.nvidia import podutils
+    spellings = {"2": 2, "2.0": 2, "2e0": 2, "20e-1": 2, "0.002k": 2, "1999m": 2, "2000m": 2, "1500m": 2, "2001m": 3,
+                 "2.1": 3, "3": 3, "0.003k": 3, "1Ki": 1024, "1k": 1000, "0": 0, "1e3": 1000, "5E-1": 1}
+    for text, want in spellings.items():
+        assert wo.quantity_value(text) == want and podutils.quantityValue(text) == want, text
+    base = 1_500_000_000_000_000_000  # older than every config-4 pod: these are picked first, by age
+    expect = []
+    for i, (text, want) in enumerate(spellings.items()):
+        p = make_pod(300 + i, NODE, gpu_mem=1, idx=i % 8, assume_time=base + i)
+        p["spec"]["containers"][0]["resources"]["limits"]["aliyun.com/gpu-mem"] = text
+        world.kube.add_pod(p)
+        expect.append((want, str(i % 8)))
+    d = world.start("--pod-informer=false", "--pod-cache-ttl", "0")
+    ch = d.channel()
+    for size in (2, 3):
+        req = wo.marshal_AllocateRequest([["x"] * size])
+        for want, idx in [e for e in expect if e[0] == size]:
+            assert wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, req))[0]["ALIYUN_COM_GPU_MEM_IDX"] == idx
+        # none left of that size among the odd spellings
+        got = wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, req))[0]["ALIYUN_COM_GPU_MEM_IDX"]
+        assert got == "-1"
+    ch.close()
