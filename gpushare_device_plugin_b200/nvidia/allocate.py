@@ -11,7 +11,7 @@ from typing import List, Optional, Sequence
 
 from .. import _abi
 from .._abi import AllocateCtx, Pod, check, lib
-from . import const, nvidia, podmanager
+from . import const, podmanager
 from .podutils import (getAssumeTimeFromPodAnnotation, getGPUIDFromPodAnnotation, getGPUMemoryFromPodResource,
                        patchPodAnnotationSpecAssigned)
 

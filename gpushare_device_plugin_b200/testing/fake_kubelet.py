@@ -4,9 +4,8 @@ from __future__ import annotations
 
 import os
 import queue
-import threading
 from concurrent import futures
-from typing import Iterator, List
+from typing import Iterator
 
 import grpc
 

@@ -18,7 +18,6 @@ import logging
 import os
 import socket
 import threading
-import time
 import urllib.parse
 from concurrent import futures
 

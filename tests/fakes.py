@@ -1,7 +1,6 @@
 """Synthetic inventory for GPU-less tests of the host side: replaces ONLY the two calls that need a
 driver (device enumeration, health-thread start); IDs, slice arithmetic, wire bytes and the Allocate
 decision still run in the C ABI."""
-import threading
 
 from gpushare_device_plugin_b200 import device
 from gpushare_device_plugin_b200.nvidia import const, nvidia

@@ -3,7 +3,6 @@ unary, large responses through both flow-control windows, server streaming, many
 cancellation, error status, and the one-shot client against a grpcio server (what Register uses)."""
 import os
 import subprocess
-import threading
 import time
 from concurrent import futures
 

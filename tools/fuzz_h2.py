@@ -52,7 +52,6 @@ while time.time() < end:
     finally:
         s.close(); conns += 1
 # still serving?
-import json
 o = subprocess.run([BIN, "call", sock_path, "/test.Echo/Unary", "6869"], capture_output=True, text=True)
 print("conns", conns, "final call:", o.stdout.strip(), "alive" if p.poll() is None else f"dead {p.returncode}")
 p.stdin.close(); 
