@@ -37,7 +37,9 @@ class FakeKubelet:
 
     def stop(self):
         if self.server:
-            self.server.stop(0)
+            # wait for the teardown: grpc unlinks the unix socket when the listener is destroyed, which would otherwise
+            # remove the file a kubelet restarted on the same path has just bound
+            self.server.stop(0).wait(10)
             self.server = None
         try:
             os.remove(self.socket)
