@@ -867,9 +867,16 @@ inline int unary_call(const std::string &socket_path, const std::string &path, c
   a.sun_family = AF_UNIX;
   if (socket_path.size() >= sizeof a.sun_path) return -1;
   strcpy(a.sun_path, socket_path.c_str());
-  if (::connect(fd, (sockaddr *)&a, sizeof a) < 0) {
-    if (err) *err = std::string("dial ") + socket_path + ": " + strerror(errno);
-    return -1;
+  // grpc.Dial(..., WithBlock(), WithTimeout(5s)) (server.go:90-104) keeps trying until the deadline: a kubelet that
+  // has bound its socket but is not listening yet, or is just being restarted, is not an error
+  const auto deadline = std::chrono::steady_clock::now() + std::chrono::seconds(timeout_s);
+  while (::connect(fd, (sockaddr *)&a, sizeof a) < 0) {
+    const int e = errno;
+    if ((e != ECONNREFUSED && e != ENOENT && e != EAGAIN && e != EINTR) || std::chrono::steady_clock::now() >= deadline) {
+      if (err) *err = std::string("dial ") + socket_path + ": " + strerror(e);
+      return -1;
+    }
+    std::this_thread::sleep_for(std::chrono::milliseconds(100));
   }
   std::string out(kPreface, 24);
   out += frame_bytes(SETTINGS, 0, 0, nullptr, 0);

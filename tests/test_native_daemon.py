@@ -630,3 +630,18 @@ def test_resource_quantity_spellings_are_read_like_quantity_value(world):
         got = wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, req))[0]["ALIYUN_COM_GPU_MEM_IDX"]
         assert got == "-1"
     ch.close()
+
+
+def test_register_waits_for_a_kubelet_that_is_still_coming_up(world, tmp_path):
+    """server.go:90-104 dials with grpc.WithBlock() and a 5 s timeout: a kubelet whose socket appears a moment later
+    is waited for, not treated as a start-up failure (exit 2 only after the deadline, see the exit-code test)."""
+    kubelet = FakeKubelet(str(tmp_path))
+    kubelet.stop()  # not there yet
+    d = world.start(wait_register=False, kubelet=kubelet)
+    time.sleep(1.5)
+    assert d.proc.poll() is None
+    kubelet.start()
+    assert kubelet.register_requests.get(timeout=10) == wo.marshal_RegisterRequest("v1beta1", "aliyungpushare.sock", "aliyun.com/gpu-mem")
+    ch = d.channel()
+    assert len(wo.unmarshal_ListAndWatchResponse(next(iter(kubelet.list_and_watch(ch))))) == 1432
+    ch.close()
