@@ -518,19 +518,30 @@ def test_everything_at_once_for_a_few_seconds(world, mode):
                     errors.append(repr(e))
         return run
 
+    def channel():
+        """None while the plugin socket is away (kubelet-restart window; grpcio's shared reconnect backoff can outlast it)."""
+        try:
+            return d.channel()
+        except grpc.FutureTimeoutError:
+            return None
+
     def allocator():
-        ch = d.channel()
+        ch = None
         try:
             while not stop.is_set():
+                if ch is None:
+                    ch = channel()
+                    continue
                 try:
                     r = wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, wo.marshal_AllocateRequest([["a", "b"]])))[0]
                     results.append(r["ALIYUN_COM_GPU_MEM_IDX"])
-                except grpc.RpcError:  # the kubelet-restart window: the plugin's socket is being re-created
+                except grpc.RpcError:
                     time.sleep(0.05)
                     ch.close()
-                    ch = d.channel()
+                    ch = None
         finally:
-            ch.close()
+            if ch is not None:
+                ch.close()
 
     def churn():
         with lock:
@@ -545,7 +556,9 @@ def test_everything_at_once_for_a_few_seconds(world, mode):
         time.sleep(0.004)
 
     def watcher():
-        ch = d.channel()
+        ch = channel()
+        if ch is None:
+            return
         try:
             call = d.kubelet.list_and_watch(ch)
             next(iter(call))
@@ -557,7 +570,9 @@ def test_everything_at_once_for_a_few_seconds(world, mode):
             ch.close()
 
     def health():
-        ch = d.channel()
+        ch = channel()
+        if ch is None:
+            return
         try:
             d.inject(ch, fakes.UUIDS[3], 8, 31)   # benign: changes nothing
             d.inject(ch, fakes.UUIDS[6], 0x100, 1)
@@ -570,12 +585,13 @@ def test_everything_at_once_for_a_few_seconds(world, mode):
     ts = [threading.Thread(target=guard(f)) for f in (churn, watcher, watcher, health)] + \
          [threading.Thread(target=allocator) for _ in range(4)]
     [t.start() for t in ts]
-    time.sleep(2.0)
+    half = float(os.environ.get("GSB_SOAK_SECONDS", "4")) / 2  # longer runs: GSB_SOAK_SECONDS=60 tools/sanitize.sh
+    time.sleep(half)
     d.kubelet.stop()  # kubelet restart: the daemon rebuilds and registers again while everything keeps going
     time.sleep(0.2)
     d.kubelet.start()
     assert d.kubelet.register_requests.get(timeout=20) == d.register_request
-    time.sleep(2.0)
+    time.sleep(half)
     stop.set()
     [t.join(30) for t in ts]
     assert not errors, errors[:3]
