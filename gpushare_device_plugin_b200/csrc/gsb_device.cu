@@ -521,6 +521,11 @@ int probe_begin_locked(Device *d, const gsb_probe_cfg *cfg, gsb_probe_result *ou
 }
 
 // wait for the launch and collect what the last CTA wrote into pinned host memory
+const uint64_t kWatchdogNs = [] {
+  const char *e = getenv("GSB_PROBE_WATCHDOG_MS");
+  return (uint64_t)(e ? atoll(e) : 0) * 1000000ull;
+}();
+
 int probe_end_locked(Device *d, ProbeFlight *fl, gsb_probe_result *out) {
   const gsb_probe_cfg *cfg = &fl->cfg;
   const gsb_kernel_args &a = fl->args;
@@ -535,6 +540,22 @@ int probe_end_locked(Device *d, ProbeFlight *fl, gsb_probe_result *out) {
       while (*flag != a.launch_seq) {
         for (int i = 0; i < 64; i++) __builtin_ia32_pause();
         if (now_ns() > deadline) break;
+      }
+    }
+    // Optional completion watchdog (knob GSB_PROBE_WATCHDOG_MS, default 0 = off until it has been verified on a
+    // GPU): without it a kernel that never finishes parks this thread in cudaStreamSynchronize for ever, so a
+    // wedged device that raises no XID would stay Healthy. With it the wait polls the stream against a deadline
+    // and the probe fails, which the prober reports like any other probe fault.
+    if (kWatchdogNs && d->out_host->done_flag != a.launch_seq) {
+      const uint64_t deadline = now_ns() + kWatchdogNs + fl->bytes / 10;  // + 1 ns per 10 B: 10 GB/s is "wedged"
+      while (cudaStreamQuery(d->stream) == cudaErrorNotReady) {
+        if (now_ns() > deadline) {
+          set_error("probe kernel did not finish within %llu ms: device wedged?",
+                    (unsigned long long)((kWatchdogNs + fl->bytes / 10) / 1000000ull));
+          return out->status = GSB_ERR_DRIVER;
+        }
+        struct timespec ts = {0, 50000};
+        nanosleep(&ts, nullptr);
       }
     }
     cudaError_t se = cudaStreamSynchronize(d->stream);

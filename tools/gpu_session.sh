@@ -24,6 +24,8 @@ if [ "$MODE" = node ]; then
   exit 0
 fi
 timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log
+# the completion watchdog is off by default until this has passed on a GPU: same tests, watchdog on
+GSB_PROBE_WATCHDOG_MS=20000 timeout 600 python -m pytest tests/test_probe_gpu.py tests/test_cycle_gpu.py -m gpu -x -q > $OUT/pytest_gpu_watchdog.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu_watchdog.log
 timeout 400 python bench.py --impl reference --steps 200 --warmup 5 > $OUT/bench_reference_1gpu.json 2> $OUT/bench_reference_1gpu.err
 timeout 400 python bench.py --steps 200 --warmup 5 > $OUT/bench_1gpu.json 2> $OUT/bench_1gpu.err
 # launch list of the same command (shares, not absolutes: ncu serialises and runs cold)
