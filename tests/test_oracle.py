@@ -123,3 +123,27 @@ def test_pynvml_twin_of_the_reference_inventory_runs_against_the_fake_nvml():
                          capture_output=True, text=True, env=env, cwd=ROOT, timeout=120)
     r = json.loads(out.stdout.strip().splitlines()[-1])
     assert r.get("n_gpus") == 8 and r["iters"] == 3 and r["inventory_us_p50"] > 0, (r, out.stderr[-500:])
+
+
+def test_product_pattern_header_on_the_host_equals_both_oracles(tmp_path):
+    """csrc/gsb_pattern.h is what the sm_100a kernels include; it also compiles for the host. Here it is held against
+    the numpy oracle, the golden fixture and (through the numpy oracle's own test) the C oracle — a divergence of the
+    product's pattern from its specification shows up on the GPU-less builder, not first on a B200."""
+    exe = tmp_path / "pattern_host"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-O1", "-I",
+                    os.path.join(ROOT, "gpushare_device_plugin_b200", "csrc"), "-o", str(exe),
+                    os.path.join(ROOT, "tests", "native", "pattern_host.c")], check=True)
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "probe_pattern.json")))
+    out = subprocess.run([str(exe), "mix", *gold["mix32"].keys()], capture_output=True, text=True, check=True).stdout.split()
+    assert [int(x) for x in out] == list(gold["mix32"].values())
+    for w in gold["words"]:
+        out = subprocess.run([str(exe), "word", str(w["first_word"]), str(len(w["lanes"])), str(w["seed"])],
+                             capture_output=True, text=True, check=True).stdout
+        assert [[int(x) for x in ln.split()] for ln in out.splitlines()] == w["lanes"]
+    rng = np.random.default_rng(7)
+    for _ in range(12):  # random windows, including word indices beyond 2^32 (the hi32 term) and seeds up to 2^32-1
+        first = int(rng.integers(0, 1 << 34)) if rng.random() < 0.7 else (1 << 32) - 3
+        n, seed = int(rng.integers(1, 300)), int(rng.integers(0, 1 << 32))
+        out = subprocess.run([str(exe), "word", str(first), str(n), str(seed)], capture_output=True, text=True, check=True).stdout
+        got = np.array([[int(x) for x in ln.split()] for ln in out.splitlines()], dtype=np.uint32)
+        assert np.array_equal(got, po.pattern(first, n, seed).reshape(-1, 4))
