@@ -144,3 +144,34 @@ def test_event_queue_and_lifecycle_under_concurrency(tmp_path):
     assert out.returncode == 0, out.stdout + out.stderr
     f = dict(zip(out.stdout.split()[::2], map(int, out.stdout.split()[1::2])))
     assert f["injected"] == f["received"] > 1000 and f["lifecycle"] > 10 and f["stopped"] > 10
+
+
+def test_shipped_kernels_move_data_with_tma_bulk_copies():
+    """SASS of the in-tree library: every dynamic-schedule and static TMA kernel (the AUTO choices) stages its loads
+    with UBLKCP (cp.async.bulk, global -> shared) completed on an mbarrier (SYNCS...TRYWAIT); the LDGSTS ring is the
+    cp.async variant; DIRECT has neither. Guards the data path against silently degrading to plain loads."""
+    out = subprocess.run(["cuobjdump", "-sass", _abi.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0 or "Function" not in out.stdout:
+        pytest.skip("cuobjdump unavailable")
+    fns, name = {}, None
+    for line in out.stdout.splitlines():
+        if "Function :" in line:
+            name = line.split("Function :", 1)[1].strip()
+            fns[name] = []
+        elif name and "/*" in line:
+            fns[name].append(line)
+    def has(fn, mnemonic):
+        return any(mnemonic in l for l in fns[fn])
+    dyn = [f for f in fns if "probe_bulk_dyn" in f]
+    static = [f for f in fns if "probe_bulk" in f and "dyn" not in f and "warp" not in f]
+    cpasync = [f for f in fns if "probe_cpasync" in f]
+    direct = [f for f in fns if "probe_direct" in f]
+    assert len(dyn) >= 3 and len(static) >= 3 and cpasync and direct
+    for f in dyn + static:
+        loads = "ILi1E" not in f  # OP is the first template argument: 1 = FILL (stores only, nothing to stage in)
+        if loads:
+            assert has(f, "UBLKCP.S.G") and has(f, "SYNCS.PHASECHK"), f
+    for f in cpasync:
+        assert has(f, "LDGSTS") and not has(f, "UBLKCP"), f
+    for f in direct:
+        assert not has(f, "UBLKCP") and not has(f, "LDGSTS"), f
