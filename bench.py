@@ -323,9 +323,16 @@ def bench_allocate(impl: str, quick: bool = False) -> dict:
         out["config4_by_pod_source"] = {"watch_informer (default)": out["config4"]["p50_us"]}
         for label, extra in (("ttl_cache (--pod-informer=false)", ("--pod-informer=false",)),
                              ("list_per_call, as the reference (--pod-informer=false --pod-cache-ttl 0)",
-                              ("--pod-informer=false", "--pod-cache-ttl", "0"))):
+                              ("--pod-informer=false", "--pod-cache-ttl", "0")),
+                             ("list_per_call + one lock across the PATCH (--serialize-allocate): the reference's Allocate in compiled code",
+                              ("--pod-informer=false", "--pod-cache-ttl", "0", "--serialize-allocate"))):
             sock, close = start(64, False, extra)
             out["config4_by_pod_source"][label] = load(sock, 1, 64)["p50_us"]
+            close()
+        if not quick:  # and what that lock does to concurrency: config 5 at c = 16, reference behaviour in compiled code
+            sock, close = start(1024, True, ("--pod-informer=false", "--pod-cache-ttl", "0", "--serialize-allocate"))
+            out["compiled_reference_behaviour_c16"] = {k: v for k, v in load(sock, 16, 256).items()
+                                                       if k in ("p50_us", "p99_us", "req_per_s", "error_responses", "requests")}
             close()
     # config 5: 1024 pending pods, concurrency sweep 1..1024 (bounded: max(256, c) requests per point)
     for c in ((1, 16) if quick else tuple(1 << k for k in range(11))):  # c = 1, 2, 4, ... 1 024

@@ -510,6 +510,9 @@ class Plugin {
   }
 
   std::string allocate(const std::string &req) {  // allocate.go:42-198
+    // --serialize-allocate: m.Lock(); defer m.Unlock() around the whole call, PATCH included (allocate.go:59-60)
+    std::unique_lock<std::mutex> whole(ref_mu_, std::defer_lock);
+    if (f_.serialize_allocate) whole.lock();
     VLOG(1, "----Allocating GPU for gpu mem is started----");
     std::string resp, name, ns, err, claimed_uid;
     int32_t pidx = -1;
@@ -624,6 +627,7 @@ class Plugin {
   std::mutex wmu_;
   http::Conn *watch_conn_ = nullptr;
   int retry_sleep_ms_ = 1000;
+  std::mutex ref_mu_;  // --serialize-allocate only
 };
 
 }  // namespace

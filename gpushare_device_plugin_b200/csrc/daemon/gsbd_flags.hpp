@@ -22,6 +22,7 @@ struct Flags {
   int probe_period_ms = 1000, probe_window_mib = 1024, probe_arena_mib = 4096, fake_inventory = 0;
   int health_recovery_cycles = 0;  // 0 = the reference's sticky Unhealthy
   bool startup_full_walk = false, coalesce_health = true, pod_informer = true;
+  bool serialize_allocate = false;  // the reference's plugin-wide lock across the whole Allocate, PATCH included
   double pod_cache_ttl = 1.0;
   std::string kube_api_url, kubelet_scheme = "https";
 };
@@ -50,6 +51,7 @@ void usage(const char *prog) {
       {"-probe-period-ms int", "Period of the HBM health probe per GPU (default 1000)"},
       {"-probe-window-mib int", "HBM bytes verified and re-written per probe cycle (default 1024)"},
       {"-query-kubelet", "Query pending pods from kubelet instead of kube-apiserver"},
+      {"-serialize-allocate", "Hold one lock across the whole Allocate, apiserver PATCH included, as the reference does; with -pod-informer=false -pod-cache-ttl 0 this is the reference's Allocate in compiled code"},
       {"-startup-full-walk", "Verify the whole arena once before serving"},
       {"-timeout int", "Kubelet client http timeout duration (default 10)"},
       {"-token string", "Kubelet client bearer token"},
@@ -96,6 +98,7 @@ int parse_flags(int argc, char **argv, Flags *f) {
     else if (name == "startup-full-walk") boolean(&f->startup_full_walk);
     else if (name == "coalesce-health") boolean(&f->coalesce_health);
     else if (name == "pod-informer") boolean(&f->pod_informer);
+    else if (name == "serialize-allocate") boolean(&f->serialize_allocate);
     else if (name == "logtostderr" || name == "alsologtostderr") { bool ignored; boolean(&ignored); }
     else if (name == "memory-unit") { if (!need()) return 3; f->memory_unit = val; }
     else if (name == "kubelet-address") { if (!need()) return 3; f->kubelet_address = val; }

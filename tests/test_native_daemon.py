@@ -661,3 +661,26 @@ def test_register_waits_for_a_kubelet_that_is_still_coming_up(world, tmp_path):
     ch = d.channel()
     assert len(wo.unmarshal_ListAndWatchResponse(next(iter(kubelet.list_and_watch(ch))))) == 1432
     ch.close()
+
+
+def test_serialize_allocate_is_the_reference_locking(world):
+    """allocate.go:59-60 holds the plugin lock across the whole call, the apiserver PATCH included: N concurrent
+    Allocates take N round trips. `--serialize-allocate` reproduces that (the compiled reference-behaviour row of the
+    benchmark); the default releases the lock before the PATCH."""
+    world.kube.patch_delay = 0.15
+    timings = {}
+    for mode, flags in (("default", ()), ("serialized", ("--serialize-allocate",))):
+        d = world.start("--pod-informer=false", "--pod-cache-ttl", "60", *flags)
+        chans = [d.channel() for _ in range(4)]
+        wo.unmarshal_AllocateResponse(d.kubelet.allocate(chans[0], wo.marshal_AllocateRequest([["a", "b", "c", "d"]])))  # warm
+        out = []
+        t0 = time.time()
+        ts = [threading.Thread(target=lambda c=c: out.append(wo.unmarshal_AllocateResponse(
+            d.kubelet.allocate(c, wo.marshal_AllocateRequest([["a", "b", "c", "d"]])))[0]["ALIYUN_COM_GPU_MEM_IDX"])) for c in chans]
+        [t.start() for t in ts]
+        [t.join(30) for t in ts]
+        timings[mode] = time.time() - t0
+        assert len(out) == 4 and "-1" not in out
+        [c.close() for c in chans]
+        d.close()
+    assert timings["default"] < 0.45 and timings["serialized"] > 0.55, timings  # ~1 vs ~4 PATCH round trips of 0.15 s
