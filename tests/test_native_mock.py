@@ -106,4 +106,4 @@ def test_bench_allocate_leg_runs_clean(impl):
     assert "compiled apiserver stand-in" in r["mock"] and "native HTTP/2 client" in r["client"]
     if impl == "ours":
         src = r["config4_by_pod_source"]
-        assert len(src) == 3 and all(v > 0 for v in src.values())
+        assert len(src) == 4 and all(v > 0 for v in src.values())
