@@ -36,18 +36,25 @@ GSB_OP_FILL, GSB_OP_VERIFY, GSB_OP_VERIFY_REFILL = 1, 2, 3
 GSB_VARIANT_AUTO, GSB_VARIANT_DIRECT, GSB_VARIANT_CPASYNC, GSB_VARIANT_BULK, GSB_VARIANT_BULKW, GSB_VARIANT_BULKD = 0, 1, 2, 3, 4, 5
 VARIANT_NAMES = {0: "auto", 1: "direct", 2: "cpasync", 3: "bulk", 4: "bulkw", 5: "bulkd"}
 GSB_PROBE_TIMED, GSB_PROBE_SEED_TABLE = 1, 2
-GSB_EVENT_XID, GSB_EVENT_PROBE = 8, 0x100
-GSB_PROBE_FAULT_MISMATCH, GSB_PROBE_FAULT_LAUNCH, GSB_PROBE_RECOVERED = 1, 2, 3
+GSB_EVENT_XID, GSB_EVENT_PROBE, GSB_EVENT_INVENTORY = 8, 0x100, 0x200
+GSB_PROBE_FAULT_MISMATCH, GSB_PROBE_FAULT_LAUNCH, GSB_PROBE_RECOVERED, GSB_PROBE_FAULT_WEDGED = 1, 2, 3, 4
+GSB_INVENTORY_IDENTITY_CHANGED, GSB_INVENTORY_TOTAL_CHANGED = 1, 2
+GSB_ABI_VERSION = 2
+GSB_ALL_DEVICES = 0xFFFFFFFF
+GSB_OPT_INVENTORY_POLICY, GSB_OPT_WAIT_SPIN_US, GSB_OPT_WATCHDOG_MS, GSB_OPT_INVENTORY_REFRESH_MS, \
+    GSB_OPT_TRANSIENT_KEEP_FREE_BYTES = 1, 2, 3, 4, 5
+GSB_INVENTORY_SNAPSHOT, GSB_INVENTORY_LIVE = 0, 1
 GSB_ALLOC_MATCHED, GSB_ALLOC_SINGLE_GPU, GSB_ALLOC_ERR_RESPONSE = 1, 2, 3
 UINT64_MAX = (1 << 64) - 1
 
 # every symbol include/gpushare_b200.h declares (tests/test_abi.py checks header <-> this list <-> .so)
 SYMBOLS = [
     "gsb_abi_version", "gsb_init", "gsb_shutdown", "gsb_strerror", "gsb_last_error",
-    "gsb_device_count", "gsb_device_info_get", "gsb_slices", "gsb_fake_device_id", "gsb_real_device_id",
+    "gsb_device_count", "gsb_device_info_get", "gsb_inventory_refresh", "gsb_inventory_snapshot",
+    "gsb_set_option", "gsb_get_option", "gsb_slices", "gsb_fake_device_id", "gsb_real_device_id",
     "gsb_encode_list_and_watch", "gsb_encode_register_request",
     "gsb_arena_create", "gsb_arena_destroy", "gsb_arena_bytes", "gsb_probe", "gsb_probe_all",
-    "gsb_arena_read", "gsb_arena_write", "gsb_cycle", "gsb_cycle_all",
+    "gsb_arena_read", "gsb_arena_write", "gsb_test_stall", "gsb_cycle", "gsb_cycle_all",
     "gsb_health_start", "gsb_health_stop", "gsb_health_wait", "gsb_health_inject", "gsb_health_set_recovery", "gsb_xid_is_benign",
     "gsb_allocate", "gsb_allocate_err_response", "gsb_patch_assigned_body",
 ]
@@ -111,6 +118,9 @@ class CycleResult(C.Structure):
         ("lw_len", C.c_int64),
         ("inventory_ns", C.c_uint64),
         ("probe", ProbeResult),
+        ("snapshot_age_ns", C.c_uint64),
+        ("inventory_live", C.c_uint32),
+        ("transient", C.c_uint32),
     ]
 
 
@@ -168,6 +178,11 @@ def _load() -> C.CDLL:
         "gsb_last_error": (C.c_int, [C.c_char_p, C.c_size_t]),
         "gsb_device_count": (C.c_int, [u32p]),
         "gsb_device_info_get": (C.c_int, [C.c_uint32, C.POINTER(DeviceInfo)]),
+        "gsb_inventory_refresh": (C.c_int, [C.c_uint32]),
+        "gsb_inventory_snapshot": (C.c_int, [C.c_uint32, C.POINTER(DeviceInfo), u64p]),
+        "gsb_set_option": (C.c_int, [C.c_uint32, C.c_uint64]),
+        "gsb_get_option": (C.c_int, [C.c_uint32, u64p]),
+        "gsb_test_stall": (C.c_int, [C.c_uint32, C.c_uint32]),
         "gsb_slices": (C.c_uint32, [C.c_uint64, C.c_int]),
         "gsb_fake_device_id": (C.c_int, [C.c_char_p, C.c_uint32, C.c_char_p, C.c_size_t]),
         "gsb_real_device_id": (C.c_int, [C.c_char_p, C.c_char_p, C.c_size_t]),

@@ -49,7 +49,7 @@ def parse(argv):
     # additions (not in the reference): active HBM probe cadence of the health watch
     add("probe-period-ms", default=1000, type=int)
     add("probe-window-mib", default=1024, type=int)
-    add("probe-arena-mib", default=4096, type=int)
+    add("probe-arena-mib", default=0, type=int)  # 0 = transient window per cycle, nothing held
     add("startup-full-walk", default=False, **b)
     add("health-recovery-cycles", default=0, type=int)
     return p.parse_args(argv)

@@ -217,25 +217,32 @@ class Plugin {
     return true;
   }
 
-  std::string list_bytes_locked() {
+  std::string list_bytes(const std::vector<uint8_t> &bits) {
     bool any = false;
-    for (uint8_t b : bits_) any = any || b;
+    for (uint8_t b : bits) any = any || b;
     const int64_t need = gsb_encode_list_and_watch(uuid_ptrs_.data(), (uint32_t)uuids_.size(), slices_,
-                                                   any ? bits_.data() : nullptr, nullptr, 0);
+                                                   any ? bits.data() : nullptr, nullptr, 0);
     std::string out((size_t)(need > 0 ? need : 0), '\0');
     if (need > 0)
-      gsb_encode_list_and_watch(uuid_ptrs_.data(), (uint32_t)uuids_.size(), slices_, any ? bits_.data() : nullptr,
+      gsb_encode_list_and_watch(uuid_ptrs_.data(), (uint32_t)uuids_.size(), slices_, any ? bits.data() : nullptr,
                                 (uint8_t *)&out[0], out.size());
     return out;
   }
 
-  // ListAndWatch (server.go:172-185)
+  // ListAndWatch (server.go:172-185). The node's health state (bits_) is written by the PRODUCER of an event
+  // (mark), never by a stream: an event raised while no stream is attached — a start-up walk fault, a NOT_SUPPORTED
+  // registration, a probe fault during a kubelet reconnect — is in the first frame of the next stream. (The
+  // reference's unbuffered channel gets the same result by blocking the producer until a stream takes the event.)
+  // Each stream replays the events it has not yet sent onto its own copy, which is what makes the reference-exact
+  // mode (one resend per fake device, each frame the state after that event) independent of how far a stream lags.
   int list_and_watch(h2::Call &c) {
     std::string frame;
     size_t cursor;
+    std::vector<uint8_t> mine;
     {
       std::lock_guard<std::mutex> lk(hmu_);
-      frame = list_bytes_locked();
+      mine = bits_;
+      frame = list_bytes(mine);
       cursor = pending_.size();
     }
     if (!c.send_message(frame.data(), frame.size())) return 1;
@@ -246,19 +253,22 @@ class Plugin {
         while (cursor >= pending_.size() && !stopping_ && !c.cancelled()) hcv_.wait_for(lk, std::chrono::milliseconds(250));
         if (stopping_ || c.cancelled()) return 0;  // `case <-m.stop: return nil`
         for (; cursor < pending_.size(); cursor++) {
-          const long long e = pending_[cursor];
-          if (e >= 0) {
-            bits_[(size_t)e >> 3] |= (uint8_t)(1u << (e & 7));  // d.Health = Unhealthy (server.go:181)
-          } else {  // optional recovery (not in the reference): ~e is the device index
-            const size_t i = (size_t)~e;
-            bits_[i >> 3] &= (uint8_t)~(1u << (i & 7));
-          }
-          if (!f_.coalesce_health) frames.push_back(list_bytes_locked());  // the reference's stream: one resend per event
+          apply(&mine, pending_[cursor]);  // d.Health = Unhealthy (server.go:181)
+          if (!f_.coalesce_health) frames.push_back(list_bytes(mine));  // the reference's stream: one resend per event
         }
-        if (f_.coalesce_health) frames.push_back(list_bytes_locked());
+        if (f_.coalesce_health) frames.push_back(list_bytes(mine));
       }
       for (auto &fr : frames)
         if (!c.send_message(fr.data(), fr.size())) return 1;
+    }
+  }
+
+  static void apply(std::vector<uint8_t> *bits, long long e) {
+    if (e >= 0) {
+      (*bits)[(size_t)e >> 3] |= (uint8_t)(1u << (e & 7));
+    } else {  // optional recovery (not in the reference): ~e is the device index
+      const size_t i = (size_t)~e;
+      (*bits)[i >> 3] &= (uint8_t)~(1u << (i & 7));
     }
   }
 
@@ -268,33 +278,52 @@ class Plugin {
       if (uuid.empty() || uuids_[g] == uuid)
         for (uint32_t j = 0; j < slices_; j++) {
           const long long i = (long long)(g * slices_ + j);
-          pending_.push_back(healthy ? ~i : i);
+          const long long e = healthy ? ~i : i;
+          apply(&bits_, e);
+          pending_.push_back(e);
         }
     hcv_.notify_all();
   }
   void mark_unhealthy(const std::string &uuid) { mark(uuid, false); }
 
+  // Probe memory. Default (--probe-arena-mib 0): none is held — every probe cycle allocates its window, walks it and
+  // frees it (transient window), so the slices the node advertises are not oversold by the plugin itself. A standing
+  // arena (--probe-arena-mib N) rotates the window over N MiB the plugin keeps for its lifetime: wider coverage, but
+  // that HBM is then NOT available to tenants although ListAndWatch still advertises it (the reference's count is
+  // kept bit-exact, nvidia.go:73-85) — the log line below says how much. Neither takes the last
+  // --probe-keep-free-mib of free HBM, the start-up walk included.
   void setup_probe_arenas() {
+    const uint64_t keep_free = (uint64_t)f_.probe_keep_free_mib << 20;
+    gsb_set_option(GSB_OPT_TRANSIENT_KEEP_FREE_BYTES, keep_free);
     for (uint32_t i = 0; i < uuids_.size(); i++) {
       uint64_t nbytes = 0;
       if (f_.startup_full_walk) {
-        if (gsb_arena_create(i, 0, 0, &nbytes) == GSB_OK) {
+        if (gsb_arena_create(i, 0, keep_free, &nbytes) == GSB_OK) {
           gsb_probe_cfg cfg;
           memset(&cfg, 0, sizeof cfg);
           cfg.op = GSB_OP_VERIFY;
           cfg.flags = GSB_PROBE_TIMED | GSB_PROBE_SEED_TABLE;
           gsb_probe_result r;
           gsb_probe(i, &cfg, &r);
-          INFO("start-up walk of %s: %llu bytes allocatable, %llu mismatching words, %.1f ms", uuids_[i].c_str(),
-               (unsigned long long)nbytes, (unsigned long long)r.mismatch_words, r.kernel_ns / 1e6);
+          INFO("start-up walk of %s: %llu bytes actually allocatable (%llu MiB left free for tenants), %llu mismatching words, %.1f ms",
+               uuids_[i].c_str(), (unsigned long long)nbytes, (unsigned long long)f_.probe_keep_free_mib,
+               (unsigned long long)r.mismatch_words, r.kernel_ns / 1e6);
           if (r.status != GSB_OK || r.mismatch_words) mark_unhealthy(uuids_[i]);
           gsb_arena_destroy(i);
+        } else {
+          WARN("start-up walk of %s skipped: %s", uuids_[i].c_str(), last_error().c_str());
         }
       }
-      if (gsb_arena_create(i, (uint64_t)f_.probe_arena_mib << 20, 1ull << 30, &nbytes) == GSB_OK)
-        INFO("probe arena on %s: %llu bytes", uuids_[i].c_str(), (unsigned long long)nbytes);
-      else
-        WARN("no probe arena on %s: %s", uuids_[i].c_str(), last_error().c_str());
+      if (f_.probe_arena_mib > 0) {
+        if (gsb_arena_create(i, (uint64_t)f_.probe_arena_mib << 20, keep_free, &nbytes) == GSB_OK)
+          WARN("standing probe arena on %s: %llu bytes held by the plugin and NOT available to tenants "
+               "(aliyun.com/gpu-mem still advertises %u slices)", uuids_[i].c_str(), (unsigned long long)nbytes, slices_);
+        else
+          WARN("no probe arena on %s: %s (falling back to transient windows)", uuids_[i].c_str(), last_error().c_str());
+      } else {
+        INFO("probe of %s: transient %d MiB window per cycle, nothing held between cycles", uuids_[i].c_str(),
+             f_.probe_window_mib);
+      }
     }
   }
 
@@ -304,13 +333,25 @@ class Plugin {
     if (f_.fake_inventory == 0) {
       if (f_.probe_period_ms > 0) setup_probe_arenas();
       gsb_health_set_recovery((uint32_t)f_.health_recovery_cycles);
-      if (gsb_health_start((uint32_t)f_.probe_period_ms, (uint64_t)f_.probe_window_mib << 20) != GSB_OK)
-        WARN("health start: %s", last_error().c_str());
+      gsb_set_option(GSB_OPT_WATCHDOG_MS, (uint64_t)f_.probe_watchdog_ms);
+      gsb_set_option(GSB_OPT_INVENTORY_REFRESH_MS, (uint64_t)f_.inventory_refresh_ms);
+      if (gsb_health_start((uint32_t)f_.probe_period_ms, (uint64_t)f_.probe_window_mib << 20) != GSB_OK) {
+        // nvidia.go:114-116: a registration error other than "Not Supported" is log.Fatalf
+        logf('F', "Fatal error: %s", last_error().c_str());
+        log_flush();
+        _exit(255);
+      }
     }
     while (!stopping_) {
       gsb_event ev;
       const int rc = gsb_health_wait(5000, &ev);  // nvidia.go:126
       if (rc != GSB_OK) continue;                 // timeout / stopped
+      if (ev.etype == GSB_EVENT_INVENTORY) {  // the low-rate NVML refresh no longer agrees with what is advertised
+        WARN("inventory of %s changed under the plugin (%s): marking it unhealthy; SIGHUP re-reads it", ev.uuid,
+             ev.edata == GSB_INVENTORY_IDENTITY_CHANGED ? "identity" : "total memory");
+        mark_unhealthy(ev.uuid);
+        continue;
+      }
       if (ev.etype != GSB_EVENT_XID && ev.etype != GSB_EVENT_PROBE) continue;   // nvidia.go:127-129
       if (ev.etype == GSB_EVENT_XID && gsb_xid_is_benign(ev.edata)) continue;  // nvidia.go:134-136
       if (ev.etype == GSB_EVENT_PROBE && ev.edata == GSB_PROBE_RECOVERED) {  // not in the reference: flag-gated
@@ -527,7 +568,10 @@ class Plugin {
         return err_response(req);
       }
       kind = decide(req, &resp, &pidx, &pod_req);
-      if (kind == GSB_ALLOC_ERR_RESPONSE && was_cached) {  // the cache may be older than the pod being started
+      // the cache may be older than the pod being started: anything but a match (the error response AND, on a
+      // one-GPU node, the single-GPU shortcut of allocate.go:151-177, which would otherwise answer without ever
+      // PATCHing the pod the reference would have found by LISTing) is re-decided on a fresh LIST
+      if (kind != GSB_ALLOC_MATCHED && kind > 0 && was_cached) {
         if (!load_pods(&err)) {
           table_.valid = false;
           return err_response(req);
@@ -581,8 +625,11 @@ class Plugin {
     std::string token = f_.token;
     if (f_.client_cert.empty() && f_.client_key.empty() && token.empty())
       token = read_file("/var/run/secrets/kubernetes.io/serviceaccount/token");  // main.go:29-36
+    http::Client::TlsExtra extra;  // main.go:40-46: TLSClientConfig{CertFile, KeyFile}; server verification off
+    extra.cert_file = f_.client_cert;
+    extra.key_file = f_.client_key;
     kubelet_.configure(f_.kubelet_scheme + "://" + f_.kubelet_address + ":" + std::to_string(f_.kubelet_port), token, "",
-                       true, f_.timeout, err);
+                       true, f_.timeout, err, &extra);
   }
   void set_retry_sleep_ms(int ms) { retry_sleep_ms_ = ms; }
   size_t n_gpus() const { return uuids_.size(); }

@@ -19,7 +19,8 @@ struct Flags {
   std::string memory_unit = "GiB", kubelet_address = "0.0.0.0", client_cert, client_key, token;
   int kubelet_port = 10250, timeout = 10;
   // additions (active probe, test hooks); none changes the wire contract
-  int probe_period_ms = 1000, probe_window_mib = 1024, probe_arena_mib = 4096, fake_inventory = 0;
+  int probe_period_ms = 1000, probe_window_mib = 1024, probe_arena_mib = 0, probe_keep_free_mib = 1024, fake_inventory = 0;
+  int probe_watchdog_ms = 2000, inventory_refresh_ms = 5000;
   int health_recovery_cycles = 0;  // 0 = the reference's sticky Unhealthy
   bool startup_full_walk = false, coalesce_health = true, pod_informer = true;
   bool serialize_allocate = false;  // the reference's plugin-wide lock across the whole Allocate, PATCH included
@@ -39,6 +40,7 @@ void usage(const char *prog) {
       {"-coalesce-health", "Fold the health events already queued into one ListAndWatch resend; false = one resend per fake device, as the reference (default true)"},
       {"-health-check", "Enable or disable Health check"},
       {"-health-recovery-cycles int", "Consecutive clean probe cycles after which a probe-faulted GPU is Healthy again; 0 = sticky Unhealthy, as the reference"},
+      {"-inventory-refresh-ms int", "Period of the off-path NVML re-query that guards the inventory snapshot while health runs; 0 = never (default 5000)"},
       {"-kube-api-url string", "Apiserver base URL instead of KUBECONFIG / in-cluster discovery"},
       {"-kubelet-address string", "Kubelet IP Address (default \"0.0.0.0\")"},
       {"-kubelet-port uint", "Kubelet listened Port (default 10250)"},
@@ -47,8 +49,10 @@ void usage(const char *prog) {
       {"-mps", "Enable or Disable MPS"},
       {"-pod-cache-ttl float", "Seconds a pending-pod LIST may be reused when the watch informer is off or down; 0 = LIST on every Allocate (default 1)"},
       {"-pod-informer", "Keep the pending-pod table current from a LIST + watch stream instead of LISTing inside Allocate (default true)"},
-      {"-probe-arena-mib int", "HBM probe arena per GPU in MiB; 0 = everything allocatable (default 4096)"},
+      {"-probe-arena-mib int", "Standing HBM probe arena per GPU in MiB, held by the plugin and not available to tenants; 0 = hold nothing, probe a transient window per cycle (default 0)"},
+      {"-probe-keep-free-mib int", "Free HBM per GPU that no probe allocation (window, arena or start-up walk) ever takes (default 1024)"},
       {"-probe-period-ms int", "Period of the HBM health probe per GPU (default 1000)"},
+      {"-probe-watchdog-ms int", "A probe launch still running after this long (+1 ms per 10 MB of window) marks the GPU unhealthy; 0 = wait for ever (default 2000)"},
       {"-probe-window-mib int", "HBM bytes verified and re-written per probe cycle (default 1024)"},
       {"-query-kubelet", "Query pending pods from kubelet instead of kube-apiserver"},
       {"-serialize-allocate", "Hold one lock across the whole Allocate, apiserver PATCH included, as the reference does; with -pod-informer=false -pod-cache-ttl 0 this is the reference's Allocate in compiled code"},
@@ -112,6 +116,9 @@ int parse_flags(int argc, char **argv, Flags *f) {
     else if (name == "probe-period-ms") { if (!need()) return 3; f->probe_period_ms = atoi(val.c_str()); }
     else if (name == "probe-window-mib") { if (!need()) return 3; f->probe_window_mib = atoi(val.c_str()); }
     else if (name == "probe-arena-mib") { if (!need()) return 3; f->probe_arena_mib = atoi(val.c_str()); }
+    else if (name == "probe-keep-free-mib") { if (!need()) return 3; f->probe_keep_free_mib = atoi(val.c_str()); }
+    else if (name == "probe-watchdog-ms") { if (!need()) return 3; f->probe_watchdog_ms = atoi(val.c_str()); }
+    else if (name == "inventory-refresh-ms") { if (!need()) return 3; f->inventory_refresh_ms = atoi(val.c_str()); }
     else if (name == "health-recovery-cycles") { if (!need()) return 3; f->health_recovery_cycles = atoi(val.c_str()); }
     else if (name == "pod-cache-ttl") { if (!need()) return 3; f->pod_cache_ttl = atof(val.c_str()); }
     else if (name == "kube-api-url") { if (!need()) return 3; f->kube_api_url = val; }

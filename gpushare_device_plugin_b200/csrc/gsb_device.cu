@@ -34,7 +34,6 @@
 #include <condition_variable>
 #include <deque>
 #include <map>
-#include <functional>
 #include <memory>
 #include <mutex>
 #include <shared_mutex>
@@ -119,6 +118,29 @@ struct Chunk {
   size_t size;
 };
 
+struct Snapshot {
+  char uuid[GSB_UUID_BUFFER_SIZE] = {0};
+  unsigned char uuid_bytes[16] = {0};  // the same UUID as the CUDA driver reports it (cuDeviceGetUuid)
+  bool uuid_parsed = false;
+  uint32_t minor = 0;
+  uint64_t total = 0, free = 0;
+  uint64_t taken_ns = 0;
+  uint64_t refreshes = 0;
+};
+
+// what a device worker runs: plain data, no allocation per hand-off
+struct Job {
+  enum Kind { NONE, PROBE, CYCLE } kind = NONE;
+  uint32_t idx = 0;
+  const gsb_probe_cfg *cfg = nullptr;
+  gsb_probe_result *probe_out = nullptr;
+  uint64_t cycle_no = 0, window_bytes = 0;
+  int unit_gib = 1;
+  uint32_t variant = 0;
+  gsb_cycle_result *cycle_out = nullptr;
+  int rc = 0;
+};
+
 struct Device {
   nvmlDevice_t nvml{};
   int ordinal = -1;
@@ -148,12 +170,20 @@ struct Device {
   std::vector<uint32_t> gen;  // host mirror of seed_table: generation that last wrote each granule
   uint32_t next_gen = 1;
   bool faulted = false;  // prober: sticky
+  std::vector<uint8_t> bits_scratch;  // Unhealthy bit string of this device's own list (faulted devices only)
+  bool wedged = false;   // a launch outlived the watchdog and is still on the stream: no new launches until it drains
+
+  // inventory snapshot: what NVML said at the last (re)start-time query (server.go:39 -> nvidia.go:53-89 queries
+  // once per plugin start, never per poll). The cycle serves identity/total from here and re-validates identity on
+  // the CUDA side; gsb_device_info_get / gsb_inventory_refresh / the low-rate refresher rewrite it.
+  std::mutex smu;
+  Snapshot snap;
 
   // persistent worker (gsb_cycle_all / gsb_probe_all): one host thread per device
   std::thread worker;
   std::mutex wmu;
   std::condition_variable wcv;
-  std::function<void()> job;
+  Job job;
   bool job_ready = false, job_done = false, worker_quit = false;
   std::atomic<bool> job_flag{false}, done_flag{false}, quit_flag{false};  // lock-free mirrors for the spin phase
 };
@@ -168,6 +198,17 @@ struct Global {
   DriverApi cu;
   NvmlApi ml;
   std::vector<std::unique_ptr<Device>> devs;  // NVML index order
+
+  // options (gsb_set_option)
+  std::atomic<uint64_t> inventory_policy{GSB_INVENTORY_SNAPSHOT};
+  std::atomic<uint64_t> wait_spin_us{2000};
+  std::atomic<uint64_t> watchdog_ms{2000};
+  std::atomic<uint64_t> inventory_refresh_ms{5000};
+  std::atomic<uint64_t> transient_keep_free{1ull << 30};
+
+  // node cycle (gsb_cycle_all / gsb_probe_all): one at a time; scratch of the join lives here, not on the heap per call
+  std::mutex all_mu;
+  std::vector<uint8_t> join_bits;
 
   // health
   std::mutex hmu;
@@ -323,6 +364,12 @@ int ensure_ready(Device *d) {
 int arena_destroy_locked(Device *d) {
   if (!d->va) return GSB_OK;
   cudaSetDevice(d->ordinal);
+  if (d->wedged && cudaStreamQuery(d->stream) == cudaErrorNotReady) {
+    // unmapping under a kernel that may never end would block for ever: keep the mapping (the process is about to
+    // report this GPU Unhealthy or exit; the driver reclaims the memory with the context)
+    set_error("%s: arena kept, a wedged launch still uses it", d->uuid);
+    return GSB_ERR_TIMEOUT;
+  }
   cudaStreamSynchronize(d->stream);
   size_t off = 0;
   for (const Chunk &c : d->chunks) {
@@ -343,10 +390,11 @@ int arena_destroy_locked(Device *d) {
 
 int run_probe_locked(Device *d, const gsb_probe_cfg *cfg, gsb_probe_result *out);
 
-int arena_create_locked(Device *d, uint64_t max_bytes, uint64_t keep_free, uint64_t *arena_bytes) {
+int arena_create_locked(Device *d, uint64_t max_bytes, uint64_t keep_free, uint64_t *arena_bytes,
+                        gsb_probe_result *fill_res = nullptr) {
   int rc = ensure_ready(d);
   if (rc) return rc;
-  arena_destroy_locked(d);
+  if ((rc = arena_destroy_locked(d)) != GSB_OK) return rc;
 
   CUmemAllocationProp prop;
   memset(&prop, 0, sizeof prop);
@@ -423,13 +471,16 @@ int arena_create_locked(Device *d, uint64_t max_bytes, uint64_t keep_free, uint6
   fill.variant = GSB_VARIANT_AUTO;
   fill.seed_write = d->next_gen;
   fill.flags = GSB_PROBE_SEED_TABLE;
+  fill.flags = GSB_PROBE_SEED_TABLE | (fill_res ? GSB_PROBE_TIMED : 0u);
   gsb_probe_result res;
   rc = run_probe_locked(d, &fill, &res);
+  if (fill_res) *fill_res = res;
   if (rc) {
     arena_destroy_locked(d);
     return rc;
   }
   d->next_gen++;
+  if (d->next_gen == 0) d->next_gen = 1;
   if (arena_bytes) *arena_bytes = mapped;
   return GSB_OK;
 }
@@ -455,6 +506,13 @@ int probe_begin_locked(Device *d, const gsb_probe_cfg *cfg, gsb_probe_result *ou
   if (!d->va) {
     set_error("no arena on %s: call gsb_arena_create first", d->uuid);
     return out->status = GSB_ERR_NO_ARENA;
+  }
+  if (d->wedged) {  // a launch that outlived the watchdog: queue nothing behind it until it has drained
+    if (cudaStreamQuery(d->stream) == cudaErrorNotReady) {
+      set_error("%s: an earlier probe launch is still running (wedged)", d->uuid);
+      return out->status = GSB_ERR_TIMEOUT;
+    }
+    d->wedged = false;
   }
   if (cfg->op < GSB_OP_FILL || cfg->op > GSB_OP_VERIFY_REFILL || (cfg->window_offset & 15) ||
       (cfg->window_bytes & 15) || cfg->window_offset > d->arena_bytes) {
@@ -521,38 +579,45 @@ int probe_begin_locked(Device *d, const gsb_probe_cfg *cfg, gsb_probe_result *ou
 }
 
 // wait for the launch and collect what the last CTA wrote into pinned host memory
-const uint64_t kWatchdogNs = [] {
-  const char *e = getenv("GSB_PROBE_WATCHDOG_MS");
-  return (uint64_t)(e ? atoll(e) : 0) * 1000000ull;
-}();
+//
+// Three phases, none of which can park the thread for ever:
+//   1. spin on the sequence word the last CTA stores into pinned host memory (option GSB_OPT_WAIT_SPIN_US, default
+//      2000; a prober thread with a period >= 10 ms passes 0): a sleeping wait costs 10-30 us of wake-up latency, a
+//      tenth of a 1 GiB-window cycle, which matters to a caller cycling back to back and not at all to a 1 Hz prober
+//      inside a 1-CPU pod (device-plugin-ds.yaml:34-40);
+//   2. sleep-poll the same word (50 us naps, the stream queried every ~1 ms so a faulted launch is noticed) against
+//      the completion watchdog: GSB_OPT_WATCHDOG_MS (default 2000) + 1 ns per 10 window bytes (10 GB/s is "wedged").
+//      The reference's WaitForEvent returns every 5 s whatever the GPU does (nvidia.go:126); a kernel that never
+//      finishes must not keep this thread — and the GPU's Healthy flag — for ever;
+//   3. cudaStreamSynchronize, which by then returns at once and orders the events.
+thread_local bool tl_wait_blocking = false;  // set by prober threads that have milliseconds to spare
 
 int probe_end_locked(Device *d, ProbeFlight *fl, gsb_probe_result *out) {
   const gsb_probe_cfg *cfg = &fl->cfg;
   const gsb_kernel_args &a = fl->args;
   if (fl->launched) {
-    // The last CTA stores the launch sequence number into pinned host memory after the results
-    // (__threadfence_system between them): poll that word for up to 2 ms before falling back to a
-    // blocking wait — a sleeping cudaStreamSynchronize costs 10-30 us of wake-up latency, a tenth of
-    // a 1 GiB-window cycle. The stream sync below then returns immediately and orders the events.
-    {
-      const volatile uint32_t *flag = &d->out_host->done_flag;
-      const uint64_t deadline = now_ns() + 2000000ull;
+    const volatile uint32_t *flag = &d->out_host->done_flag;
+    const uint64_t spin_ns = tl_wait_blocking ? 0 : G.wait_spin_us.load(std::memory_order_relaxed) * 1000ull;
+    if (spin_ns) {
+      const uint64_t deadline = now_ns() + spin_ns;
       while (*flag != a.launch_seq) {
         for (int i = 0; i < 64; i++) __builtin_ia32_pause();
         if (now_ns() > deadline) break;
       }
     }
-    // Optional completion watchdog (knob GSB_PROBE_WATCHDOG_MS, default 0 = off until it has been verified on a
-    // GPU): without it a kernel that never finishes parks this thread in cudaStreamSynchronize for ever, so a
-    // wedged device that raises no XID would stay Healthy. With it the wait polls the stream against a deadline
-    // and the probe fails, which the prober reports like any other probe fault.
-    if (kWatchdogNs && d->out_host->done_flag != a.launch_seq) {
-      const uint64_t deadline = now_ns() + kWatchdogNs + fl->bytes / 10;  // + 1 ns per 10 B: 10 GB/s is "wedged"
-      while (cudaStreamQuery(d->stream) == cudaErrorNotReady) {
+    const uint64_t wd_ms = G.watchdog_ms.load(std::memory_order_relaxed);
+    if (wd_ms && *flag != a.launch_seq) {
+      const uint64_t budget = wd_ms * 1000000ull + fl->bytes / 10;
+      const uint64_t deadline = fl->t_begin + budget;
+      unsigned naps = 0;
+      while (*flag != a.launch_seq) {
+        if ((++naps & 15u) == 0 && cudaStreamQuery(d->stream) != cudaErrorNotReady) break;  // finished or faulted
         if (now_ns() > deadline) {
-          set_error("probe kernel did not finish within %llu ms: device wedged?",
-                    (unsigned long long)((kWatchdogNs + fl->bytes / 10) / 1000000ull));
-          return out->status = GSB_ERR_DRIVER;
+          d->wedged = true;  // the launch is still on the stream: nothing new is queued behind it
+          set_error("probe kernel on %s did not finish within %llu ms: device wedged?", d->uuid,
+                    (unsigned long long)(budget / 1000000ull));
+          out->wall_ns = now_ns() - fl->t_begin;
+          return out->status = GSB_ERR_TIMEOUT;
         }
         struct timespec ts = {0, 50000};
         nanosleep(&ts, nullptr);
@@ -604,19 +669,54 @@ int run_probe_locked(Device *d, const gsb_probe_cfg *cfg, gsb_probe_result *out)
   return probe_end_locked(d, &fl, out);
 }
 
-// diagnostic knob GSB_NVML_SERIAL=1: one NVML/driver query at a time across this process's device threads (the
-// open question behind profiles/node_cycle_8gpu_bimodal_r01.txt: do concurrent queries convoy on the driver's lock?)
+// diagnostic knob GSB_NVML_SERIAL=1: one NVML/driver query at a time across this process's device threads
+// (GSB_INVENTORY_LIVE only; profiles/node_cycle_8gpu_bimodal_r01.txt)
 std::mutex g_nvml_serial_mu;
 const bool kNvmlSerial = [] {
   const char *e = getenv("GSB_NVML_SERIAL");
   return e && atoi(e) != 0;
 }();
 
+// "GPU-xxxxxxxx-xxxx-xxxx-xxxx-xxxxxxxxxxxx" -> the 16 bytes cuDeviceGetUuid reports for the same device
+bool parse_uuid(const char *s, unsigned char out[16]) {
+  if (strncmp(s, "GPU-", 4) != 0) return false;
+  s += 4;
+  int n = 0;
+  auto hex = [](char c) -> int {
+    if (c >= '0' && c <= '9') return c - '0';
+    if (c >= 'a' && c <= 'f') return c - 'a' + 10;
+    if (c >= 'A' && c <= 'F') return c - 'A' + 10;
+    return -1;
+  };
+  while (*s && n < 16) {
+    if (*s == '-') {
+      s++;
+      continue;
+    }
+    const int hi = hex(s[0]), lo = hi < 0 ? -1 : hex(s[1]);
+    if (lo < 0) return false;
+    out[n++] = (unsigned char)(hi << 4 | lo);
+    s += 2;
+  }
+  return n == 16 && *s == 0;
+}
+
+void fill_static_info(const Device *d, gsb_device_info *out) {
+  snprintf(out->bus_id, sizeof out->bus_id, "%s", d->bus_id);
+  out->cuda_ordinal = d->ordinal;
+  out->sm_count = d->sm_count;
+  out->cc_major = d->cc_major;
+  out->cc_minor = d->cc_minor;
+  out->cuda_total_bytes = d->cuda_total;
+}
+
+// LIVE inventory of one device: the reference's source (NVML UUID, minor, MemoryInfo v1) re-read and the identity
+// cross-checked against the CUDA driver. This is what nvml.NewDevice does at every plugin (re)start
+// (server.go:39 -> nvidia.go:60); it also rewrites the device's snapshot.
 int query_info(Device *d, gsb_device_info *out) {
   memset(out, 0, sizeof *out);
   std::unique_lock<std::mutex> serial(g_nvml_serial_mu, std::defer_lock);
   if (kNvmlSerial) serial.lock();
-  // identity: re-read from both sides, every call
   char uuid[GSB_UUID_BUFFER_SIZE] = {0};
   ML_TRY(G.ml.getUUID(d->nvml, uuid, GSB_UUID_BUFFER_SIZE));
   unsigned minor = 0;
@@ -635,29 +735,88 @@ int query_info(Device *d, gsb_device_info *out) {
     }
   }
   snprintf(out->uuid, sizeof out->uuid, "%s", uuid);
-  snprintf(out->bus_id, sizeof out->bus_id, "%s", d->bus_id);
+  fill_static_info(d, out);
   out->minor = minor;
-  out->cuda_ordinal = d->ordinal;
-  out->sm_count = d->sm_count;
-  out->cc_major = d->cc_major;
-  out->cc_minor = d->cc_minor;
   out->total_bytes = mem.total;
   out->total_mib = mem.total / (1024ull * 1024ull);  // bindings.go:346-349
   out->free_bytes = mem.free;
-  out->cuda_total_bytes = d->cuda_total;
+  {
+    std::lock_guard<std::mutex> lk(d->smu);
+    Snapshot &sn = d->snap;
+    snprintf(sn.uuid, sizeof sn.uuid, "%s", uuid);
+    sn.uuid_parsed = parse_uuid(uuid, sn.uuid_bytes);
+    sn.minor = minor;
+    sn.total = mem.total;
+    sn.free = mem.free;
+    sn.taken_ns = now_ns();
+    sn.refreshes++;
+  }
   return GSB_OK;
 }
 
-// run `fn` on the device's own persistent thread (created on first use). Hand-off is spin-then-block in
-// both directions: a node cycle every few hundred microseconds never pays a futex wake-up (tens of us per
-// hop, a tenth of a 1 GiB-window cycle), an idle daemon's workers park after ~200 us.
+// SNAPSHOT inventory: identity/total as NVML reported them at the last live query, with the identity re-validated
+// against the CUDA driver on every call (cuDeviceGetUuid is answered by the user-mode driver: no ioctl, no
+// driver-wide lock, ~0.1 us — unlike nvmlDeviceGetMemoryInfo, which serialises with every other NVML client of the
+// box: 6 us idle, 0.2-2.3 ms beside an nvidia-smi or dcgm-exporter poller, BENCH_r01 e2e.inventory_us_per_step).
+int snapshot_info(Device *d, gsb_device_info *out, uint64_t *age_ns) {
+  memset(out, 0, sizeof *out);
+  Snapshot sn;
+  {
+    std::lock_guard<std::mutex> lk(d->smu);
+    sn = d->snap;
+  }
+  if (sn.refreshes == 0) return query_info(d, out);  // never queried: take the live path once
+  if (d->ordinal >= 0 && sn.uuid_parsed) {
+    CUuuid cu;
+    CU_TRY(G.cu.cuDeviceGetUuid(&cu, d->cudev));
+    if (memcmp(cu.bytes, sn.uuid_bytes, 16) != 0) {
+      char cuda_uuid[GSB_UUID_BUFFER_SIZE];
+      format_uuid(cu, cuda_uuid);
+      set_error("identity mismatch on minor %u: CUDA %s vs NVML snapshot %s", sn.minor, cuda_uuid, sn.uuid);
+      return GSB_ERR_IDENTITY_MISMATCH;
+    }
+  }
+  memcpy(out->uuid, sn.uuid, sizeof out->uuid);
+  fill_static_info(d, out);
+  out->minor = sn.minor;
+  out->total_bytes = sn.total;
+  out->total_mib = sn.total / (1024ull * 1024ull);
+  out->free_bytes = sn.free;
+  if (age_ns) *age_ns = now_ns() - sn.taken_ns;
+  return GSB_OK;
+}
+
+// Run a Job on the device's own persistent thread (created on first use). Hand-off is spin-then-block in both
+// directions: a node cycle every few hundred microseconds never pays a futex wake-up (tens of us per hop, a tenth
+// of a 1 GiB-window cycle), an idle daemon's workers park after ~200 us. The job is plain data (no std::function,
+// no allocation per hand-off).
 // knob GSB_WORKER_SPIN_US (default 200; 0 = pure condition-variable hand-off)
 const uint64_t kSpinNs = [] {
   const char *e = getenv("GSB_WORKER_SPIN_US");
   return (uint64_t)(e ? atoi(e) : 200) * 1000ull;
 }();
 
-void worker_submit(Device *d, std::function<void()> fn) {
+int cycle_impl(Device *d, uint32_t idx, uint64_t cycle_no, uint64_t window_bytes, int unit_gib, uint32_t variant,
+               uint8_t *lw_buf, size_t lw_cap, bool encode_lw, gsb_cycle_result *out);
+
+void run_job(Device *d, Job *j) {  // on the worker thread; the submitting call holds G.api_mu (shared) throughout
+  switch (j->kind) {
+    case Job::PROBE: {
+      std::lock_guard<std::mutex> lk(d->mu);
+      j->rc = run_probe_locked(d, j->cfg, j->probe_out);
+      break;
+    }
+    case Job::CYCLE:
+      // the node cycle's join re-encodes the whole node's list: the per-device list is not built here
+      j->rc = cycle_impl(d, j->idx, j->cycle_no, j->window_bytes, j->unit_gib, j->variant, nullptr, 0, false,
+                         j->cycle_out);
+      break;
+    default:
+      j->rc = GSB_ERR_INVALID_ARGUMENT;
+  }
+}
+
+void worker_submit(Device *d, const Job &job) {
   std::unique_lock<std::mutex> lk(d->wmu);
   if (!d->worker.joinable()) {
     d->worker = std::thread([d] {
@@ -672,9 +831,8 @@ void worker_submit(Device *d, std::function<void()> fn) {
         if (d->worker_quit) return;
         d->job_ready = false;
         d->job_flag.store(false, std::memory_order_relaxed);
-        std::function<void()> f = std::move(d->job);
         wl.unlock();
-        f();
+        run_job(d, &d->job);  // the submitter does not touch d->job until job_done
         wl.lock();
         d->job_done = true;
         d->done_flag.store(true, std::memory_order_release);
@@ -682,7 +840,7 @@ void worker_submit(Device *d, std::function<void()> fn) {
       }
     });
   }
-  d->job = std::move(fn);
+  d->job = job;
   d->job_done = false;
   d->done_flag.store(false, std::memory_order_relaxed);
   d->job_ready = true;
@@ -690,11 +848,12 @@ void worker_submit(Device *d, std::function<void()> fn) {
   d->wcv.notify_all();
 }
 
-void worker_wait(Device *d) {
+int worker_wait(Device *d) {
   const uint64_t until = now_ns() + 5 * kSpinNs;
   while (!d->done_flag.load(std::memory_order_acquire) && now_ns() < until) __builtin_ia32_pause();
   std::unique_lock<std::mutex> lk(d->wmu);
   d->wcv.wait(lk, [d] { return d->job_done; });
+  return d->job.rc;
 }
 
 void worker_stop(Device *d) {
@@ -805,6 +964,17 @@ int gsb_init(void) {
     }
     G.devs.push_back(std::move(d));
   }
+  // the (re)start-time inventory: every device's identity + memory read from NVML once, as getDevices does
+  for (auto &d : G.devs) {
+    gsb_device_info info;
+    int qrc = query_info(d.get(), &info);
+    if (qrc) {
+      G.devs.clear();
+      return qrc;
+    }
+  }
+  if (const char *e = getenv("GSB_PROBE_WATCHDOG_MS")) G.watchdog_ms = (uint64_t)atoll(e);
+  if (const char *e = getenv("GSB_INVENTORY_POLICY")) G.inventory_policy = strcmp(e, "live") == 0 ? GSB_INVENTORY_LIVE : GSB_INVENTORY_SNAPSHOT;
   G.inited = true;
   return GSB_OK;
 }
@@ -901,18 +1071,25 @@ int gsb_probe(uint32_t idx, const gsb_probe_cfg *cfg, gsb_probe_result *out) {
 }
 
 int gsb_probe_all(uint32_t n, const uint32_t *idxs, const gsb_probe_cfg *cfg, gsb_probe_result *results) {
-  if (!idxs || !cfg || !results) return GSB_ERR_INVALID_ARGUMENT;
-  std::vector<Device *> ds(n, nullptr);
+  if (!idxs || !cfg || !results || n > GSB_MAX_DEVICES) return GSB_ERR_INVALID_ARGUMENT;
+  std::shared_lock<std::shared_mutex> api_lk(G.api_mu);  // held across the fan-out: a shutdown waits for it
+  std::lock_guard<std::mutex> one(G.all_mu);             // each device worker has one job slot
+  Device *ds[GSB_MAX_DEVICES];
   for (uint32_t i = 0; i < n; i++) {
     ds[i] = device_at(idxs[i]);
+    for (uint32_t k = 0; k < i && ds[i]; k++)
+      if (ds[k] == ds[i]) ds[i] = nullptr;  // a device listed twice runs once; the second slot reports the error
     if (!ds[i]) {
       memset(&results[i], 0, sizeof results[i]);
-      results[i].status = G.inited ? GSB_ERR_NO_DEVICE : GSB_ERR_NOT_INITIALIZED;
+      results[i].status = !G.inited ? GSB_ERR_NOT_INITIALIZED : idxs[i] < G.devs.size() ? GSB_ERR_INVALID_ARGUMENT : GSB_ERR_NO_DEVICE;
       continue;
     }
-    const uint32_t idx = idxs[i];
-    gsb_probe_result *out = &results[i];
-    worker_submit(ds[i], [idx, cfg, out] { gsb_probe(idx, cfg, out); });
+    Job j;
+    j.kind = Job::PROBE;
+    j.idx = idxs[i];
+    j.cfg = cfg;
+    j.probe_out = &results[i];
+    worker_submit(ds[i], j);
   }
   int rc = GSB_OK;
   for (uint32_t i = 0; i < n; i++) {
@@ -925,43 +1102,60 @@ int gsb_probe_all(uint32_t n, const uint32_t *idxs, const gsb_probe_cfg *cfg, gs
 int64_t gsb_cycle_all(uint32_t n, const uint32_t *idxs, uint64_t cycle_no, uint64_t window_bytes, int unit_gib,
                       uint32_t variant, uint8_t *lw_buf, size_t lw_cap, gsb_cycle_result *results) {
   if (!idxs || !results || n == 0 || n > GSB_MAX_DEVICES) return GSB_ERR_INVALID_ARGUMENT;
-  std::vector<Device *> ds(n, nullptr);
-  std::vector<int> rcs(n, GSB_OK);
-  std::vector<std::vector<uint8_t>> scratch(n);
+  if (window_bytes % kGranuleBytes) {
+    set_error("cycle window must be a multiple of 64 MiB (or 0 = whole arena)");
+    return GSB_ERR_INVALID_ARGUMENT;
+  }
+  std::shared_lock<std::shared_mutex> api_lk(G.api_mu);
+  std::lock_guard<std::mutex> one(G.all_mu);
+  Device *ds[GSB_MAX_DEVICES];
+  int rcs[GSB_MAX_DEVICES];
   for (uint32_t i = 0; i < n; i++) {
     ds[i] = device_at(idxs[i]);
     if (!ds[i]) return G.inited ? GSB_ERR_NO_DEVICE : GSB_ERR_NOT_INITIALIZED;
+    for (uint32_t k = 0; k < i; k++)
+      if (ds[k] == ds[i]) {
+        set_error("device %u listed twice", idxs[i]);
+        return GSB_ERR_INVALID_ARGUMENT;
+      }
   }
   for (uint32_t i = 0; i < n; i++) {  // fan out: every device runs its own cycle on its own thread
-    scratch[i].resize(1 << 16);
-    const uint32_t idx = idxs[i];
-    gsb_cycle_result *out = &results[i];
-    int *rc = &rcs[i];
-    std::vector<uint8_t> *buf = &scratch[i];
-    worker_submit(ds[i], [=] {
-      *rc = gsb_cycle(idx, cycle_no, window_bytes, unit_gib, variant, buf->data(), buf->size(), out);
-    });
+    Job j;
+    j.kind = Job::CYCLE;
+    j.idx = idxs[i];
+    j.cycle_no = cycle_no;
+    j.window_bytes = window_bytes;
+    j.unit_gib = unit_gib;
+    j.variant = variant;
+    j.cycle_out = &results[i];
+    worker_submit(ds[i], j);
   }
-  for (uint32_t i = 0; i < n; i++) worker_wait(ds[i]);
+  for (uint32_t i = 0; i < n; i++) rcs[i] = worker_wait(ds[i]);
   // the one join: concatenate in index order, slices from the first device, health from each verdict
   const uint32_t slices = results[0].slices;
-  std::vector<const char *> uuids(n);
-  std::vector<uint8_t> bits(((size_t)n * slices + 7) / 8, 0);
+  const char *uuids[GSB_MAX_DEVICES];
   bool any_bad = false;
   int rc_all = GSB_OK;
   for (uint32_t i = 0; i < n; i++) {
-    if (rcs[i] < 0 && rcs[i] != GSB_ERR_DRIVER) rc_all = rcs[i];  // a failed launch is a verdict, not an API error
+    // a failed or timed-out launch is a verdict (healthy = 0), not an API error
+    if (rcs[i] < 0 && rcs[i] != GSB_ERR_DRIVER && rcs[i] != GSB_ERR_TIMEOUT) rc_all = rcs[i];
     uuids[i] = results[i].info.uuid;
-    if (!results[i].healthy) {
-      any_bad = true;
-      for (uint32_t j = 0; j < slices; j++) {
-        const size_t b = (size_t)i * slices + j;
-        bits[b >> 3] |= (uint8_t)(1u << (b & 7));
-      }
-    }
+    if (!results[i].healthy) any_bad = true;
   }
   if (rc_all) return rc_all;
-  return gsb_encode_list_and_watch(uuids.data(), n, slices, any_bad ? bits.data() : nullptr, lw_buf, lw_cap);
+  if (any_bad) {
+    G.join_bits.assign(((size_t)n * slices + 7) / 8, 0);
+    for (uint32_t i = 0; i < n; i++)
+      if (!results[i].healthy)
+        for (uint32_t j = 0; j < slices; j++) {  // every fake device of that GPU (nvidia.go:146-150)
+          const size_t b = (size_t)i * slices + j;
+          G.join_bits[b >> 3] |= (uint8_t)(1u << (b & 7));
+        }
+  }
+  const int64_t len = gsb_encode_list_and_watch(uuids, n, slices, any_bad ? G.join_bits.data() : nullptr, lw_buf, lw_cap);
+  if (len >= 0)
+    for (uint32_t i = 0; i < n; i++) results[i].lw_len = i == 0 ? len : 0;  // the node's list is reported once
+  return len;
 }
 
 int gsb_arena_read(uint32_t idx, uint64_t offset, void *dst, uint64_t bytes) {
@@ -995,79 +1189,193 @@ int gsb_cycle(uint32_t idx, uint64_t cycle_no, uint64_t window_bytes, int unit_g
   memset(out, 0, sizeof *out);
   Device *d = device_at(idx);
   if (!d) return G.inited ? GSB_ERR_NO_DEVICE : GSB_ERR_NOT_INITIALIZED;
+  return cycle_impl(d, idx, cycle_no, window_bytes, unit_gib, variant, lw_buf, lw_cap, true, out);
+}
+
+int gsb_set_option(uint32_t key, uint64_t value) {
+  switch (key) {
+    case GSB_OPT_INVENTORY_POLICY:
+      if (value != GSB_INVENTORY_SNAPSHOT && value != GSB_INVENTORY_LIVE) return GSB_ERR_INVALID_ARGUMENT;
+      G.inventory_policy = value;
+      return GSB_OK;
+    case GSB_OPT_WAIT_SPIN_US: G.wait_spin_us = value; return GSB_OK;
+    case GSB_OPT_WATCHDOG_MS: G.watchdog_ms = value; return GSB_OK;
+    case GSB_OPT_INVENTORY_REFRESH_MS: G.inventory_refresh_ms = value; return GSB_OK;
+    case GSB_OPT_TRANSIENT_KEEP_FREE_BYTES: G.transient_keep_free = value; return GSB_OK;
+    default: set_error("unknown option %u", key); return GSB_ERR_INVALID_ARGUMENT;
+  }
+}
+
+int gsb_get_option(uint32_t key, uint64_t *value) {
+  if (!value) return GSB_ERR_INVALID_ARGUMENT;
+  switch (key) {
+    case GSB_OPT_INVENTORY_POLICY: *value = G.inventory_policy; return GSB_OK;
+    case GSB_OPT_WAIT_SPIN_US: *value = G.wait_spin_us; return GSB_OK;
+    case GSB_OPT_WATCHDOG_MS: *value = G.watchdog_ms; return GSB_OK;
+    case GSB_OPT_INVENTORY_REFRESH_MS: *value = G.inventory_refresh_ms; return GSB_OK;
+    case GSB_OPT_TRANSIENT_KEEP_FREE_BYTES: *value = G.transient_keep_free; return GSB_OK;
+    default: set_error("unknown option %u", key); return GSB_ERR_INVALID_ARGUMENT;
+  }
+}
+
+int gsb_inventory_refresh(uint32_t idx) {
+  std::shared_lock<std::shared_mutex> api_lk(G.api_mu);
+  if (!G.inited) return GSB_ERR_NOT_INITIALIZED;
+  gsb_device_info info;
+  if (idx == GSB_ALL_DEVICES) {
+    for (auto &d : G.devs) {
+      int rc = query_info(d.get(), &info);
+      if (rc) return rc;
+    }
+    return GSB_OK;
+  }
+  Device *d = device_at(idx);
+  if (!d) return GSB_ERR_NO_DEVICE;
+  return query_info(d, &info);
+}
+
+int gsb_inventory_snapshot(uint32_t idx, gsb_device_info *out, uint64_t *age_ns) {
+  std::shared_lock<std::shared_mutex> api_lk(G.api_mu);
+  if (!out) return GSB_ERR_INVALID_ARGUMENT;
+  Device *d = device_at(idx);
+  if (!d) return G.inited ? GSB_ERR_NO_DEVICE : GSB_ERR_NOT_INITIALIZED;
+  int rc = snapshot_info(d, out, age_ns);
+  out->index = idx;
+  return rc;
+}
+
+int gsb_test_stall(uint32_t idx, uint32_t ms) {
+  std::shared_lock<std::shared_mutex> api_lk(G.api_mu);
+  Device *d = device_at(idx);
+  if (!d) return G.inited ? GSB_ERR_NO_DEVICE : GSB_ERR_NOT_INITIALIZED;
+  std::lock_guard<std::mutex> lk(d->mu);
+  int rc = ensure_ready(d);
+  if (rc) return rc;
+  const int e = gsb_kernel_stall((unsigned long long)ms * 1000000ull, d->stream);
+  if (e) {
+    set_error("stall kernel: %s", cudaGetErrorString((cudaError_t)e));
+    return GSB_ERR_DRIVER;
+  }
+  return GSB_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// One inventory + health-probe cycle of one device. The caller holds G.api_mu (shared).
+int cycle_impl(Device *d, uint32_t idx, uint64_t cycle_no, uint64_t window_bytes, int unit_gib, uint32_t variant,
+               uint8_t *lw_buf, size_t lw_cap, bool encode_lw, gsb_cycle_result *out) {
+  memset(out, 0, sizeof *out);
   if (window_bytes % kGranuleBytes) {
     set_error("cycle window must be a multiple of 64 MiB (or 0 = whole arena)");
     return GSB_ERR_INVALID_ARGUMENT;
   }
   std::lock_guard<std::mutex> lk(d->mu);
-  if (!d->va) {
-    set_error("no arena on %s: call gsb_arena_create first", d->uuid);
-    return GSB_ERR_NO_ARENA;
+  // Transient window (SURVEY §7 hard-part 2, the tenant-safe steady state): with no standing arena the cycle
+  // allocates the window, fills it, verifies it and gives it back, so between cycles the plugin holds no HBM beyond
+  // its CUDA context and the 179 advertised slices are not oversold. "Nothing free to probe" (tenants hold the
+  // HBM) is not a GPU fault.
+  const bool transient = !d->va;
+  gsb_probe_result fill_res;
+  memset(&fill_res, 0, sizeof fill_res);
+  int prc = GSB_OK;
+  bool skip_probe = false;
+  if (transient) {
+    if (window_bytes == 0) {
+      set_error("no arena on %s: call gsb_arena_create first (or pass a window for a transient probe)", d->uuid);
+      return GSB_ERR_NO_ARENA;
+    }
+    out->transient = 1;
+    uint64_t got = 0;
+    prc = arena_create_locked(d, window_bytes, G.transient_keep_free.load(), &got, &fill_res);
+    if (prc == GSB_ERR_OUT_OF_MEMORY) {
+      out->probe.status = GSB_ERR_OUT_OF_MEMORY;
+      prc = GSB_OK;
+      skip_probe = true;
+    } else if (prc) {
+      out->probe = fill_res;
+      out->probe.status = prc;
+      skip_probe = true;
+    }
   }
-  // 1. health: enqueue the VERIFY_REFILL of this cycle's window (asynchronous)
+  // 1. health: enqueue this cycle's walk (asynchronous). Standing arena: VERIFY_REFILL of the cycle's window.
+  //    Transient window: the FILL above wrote generation g, VERIFY reads it back.
   gsb_probe_cfg cfg;
   memset(&cfg, 0, sizeof cfg);
-  cfg.op = GSB_OP_VERIFY_REFILL;
+  cfg.op = transient ? GSB_OP_VERIFY : GSB_OP_VERIFY_REFILL;
   cfg.variant = variant;
   cfg.flags = GSB_PROBE_TIMED | GSB_PROBE_SEED_TABLE;
-  if (window_bytes && window_bytes < d->arena_bytes) {
-    const uint64_t n_win = d->arena_bytes / window_bytes;
-    cfg.window_offset = (cycle_no % n_win) * window_bytes;
-    cfg.window_bytes = window_bytes;
+  if (!transient) {
+    if (window_bytes && window_bytes < d->arena_bytes) {
+      const uint64_t n_win = d->arena_bytes / window_bytes;
+      cfg.window_offset = (cycle_no % n_win) * window_bytes;
+      cfg.window_bytes = window_bytes;
+    }
+    cfg.seed_write = d->next_gen++;
+    if (d->next_gen == 0) d->next_gen = 1;
   }
-  cfg.seed_write = d->next_gen++;
-  if (d->next_gen == 0) d->next_gen = 1;
   // diagnostic knob GSB_CYCLE_ORDER (tools/cycle_breakdown.py): 0 = launch, then inventory while the kernel
-  // runs (shipped); 1 = inventory first, then launch; 2 = no inventory; 3 = a plain 170 us host sleep in
-  // place of the inventory (tells host-side overlap apart from driver-side interference)
+  // runs (shipped); 1 = inventory first, then launch
   static const int order = [] {
     const char *e = getenv("GSB_CYCLE_ORDER");
     return e ? atoi(e) : 0;
   }();
   ProbeFlight fl;
-  int prc = GSB_OK;
-  if (order != 1) prc = probe_begin_locked(d, &cfg, &out->probe, &fl);
+  if (!skip_probe && order != 1) prc = probe_begin_locked(d, &cfg, &out->probe, &fl);
 
-  // 2. inventory while the kernel walks HBM: fresh identity + memory info, slices, S fake devices,
-  //    wire bytes (optimistically with the health this device had going into the cycle)
+  // 2. inventory while the kernel walks HBM: identity + total (policy SNAPSHOT: NVML's (re)start-time answer,
+  //    identity re-validated on the CUDA side; policy LIVE: a fresh NVML query), slices, S fake devices, wire bytes
+  //    (optimistically with the health this device had going into the cycle)
   const uint64_t t0 = now_ns();
-  int rc = GSB_OK;
-  if (order == 2 || order == 3) {
-    if (order == 3) {
-      const uint64_t until = now_ns() + 170000;
-      while (now_ns() < until) __builtin_ia32_pause();
-    }
-    snprintf(out->info.uuid, sizeof out->info.uuid, "%s", d->uuid);
-    out->info.total_mib = 183359;
-  } else {
+  int rc;
+  if (G.inventory_policy.load(std::memory_order_relaxed) == GSB_INVENTORY_LIVE) {
     rc = query_info(d, &out->info);
+    out->inventory_live = 1;
+  } else {
+    rc = snapshot_info(d, &out->info, &out->snapshot_age_ns);
   }
   if (rc == GSB_OK) {
     out->info.index = idx;
     out->slices = gsb_slices(out->info.total_mib, unit_gib);
   }
   const char *uuids[1] = {out->info.uuid};
-  std::vector<uint8_t> bits;
   auto encode = [&](bool unhealthy) -> int64_t {
-    if (unhealthy) bits.assign((out->slices + 7) / 8, 0xFF);  // every fake device of a faulted GPU (nvidia.go:146-150)
-    return gsb_encode_list_and_watch(uuids, 1, out->slices, unhealthy ? bits.data() : nullptr, lw_buf, lw_cap);
+    if (!encode_lw) return 0;
+    const uint8_t *bits = nullptr;
+    if (unhealthy) {  // every fake device of a faulted GPU (nvidia.go:146-150)
+      d->bits_scratch.assign((out->slices + 7) / 8, 0xFF);
+      bits = d->bits_scratch.data();
+    }
+    return gsb_encode_list_and_watch(uuids, 1, out->slices, bits, lw_buf, lw_cap);
   };
   if (rc == GSB_OK) out->lw_len = encode(d->faulted);
   out->inventory_ns = now_ns() - t0;
-  if (order == 1) prc = probe_begin_locked(d, &cfg, &out->probe, &fl);
+  if (!skip_probe && order == 1) prc = probe_begin_locked(d, &cfg, &out->probe, &fl);
 
   // 3. verdict
-  if (prc == GSB_OK) prc = probe_end_locked(d, &fl, &out->probe);
+  if (!skip_probe && prc == GSB_OK) prc = probe_end_locked(d, &fl, &out->probe);
+  if (transient) {
+    if (!skip_probe && prc == GSB_OK) {  // one figure for the window: FILL wrote it, VERIFY read it
+      out->probe.kernel_ns += fill_res.kernel_ns;
+      out->probe.bytes_written = fill_res.bytes_written;
+    }
+    arena_destroy_locked(d);  // a wedged launch keeps it (and the GPU is reported below)
+  }
   if (rc) return rc;
   if (out->lw_len < 0) return (int)out->lw_len;
-  out->healthy = (prc == GSB_OK && out->probe.mismatch_words == 0) ? 1u : 0u;
-  if (!out->healthy && !d->faulted) {
+  out->healthy = (prc == GSB_OK && out->probe.mismatch_words == 0 && !d->faulted) ? 1u : 0u;
+  if (!(prc == GSB_OK && out->probe.mismatch_words == 0) && !d->faulted) {
     d->faulted = true;  // sticky (server.go:180 FIXME): the list this cycle reports already carries it
     out->lw_len = encode(true);
     if (out->lw_len < 0) return (int)out->lw_len;
   }
   return prc;
 }
+
+}  // namespace
+
+extern "C" {
 
 // ---------------------------------------------------------------------- health
 
@@ -1104,8 +1412,12 @@ int gsb_health_start(uint32_t probe_period_ms, uint64_t window_bytes) {
   if (G.health_running) return GSB_OK;
   G.health_stop = false;
   // XID half: one registration per GPU (the reference registers the same GPU once per fake device)
-  if (G.ml.eventSetCreate && G.ml.registerEvents && G.ml.eventSetWait && G.ml.eventSetFree &&
-      G.ml.eventSetCreate(&G.event_set) == NVML_SUCCESS) {
+  if (G.ml.eventSetCreate && G.ml.registerEvents && G.ml.eventSetWait && G.ml.eventSetFree) {
+    nvmlReturn_t cr = G.ml.eventSetCreate(&G.event_set);
+    if (cr != NVML_SUCCESS) {
+      set_error("nvml: %s (nvmlEventSetCreate)", G.ml.errorString(cr));
+      return GSB_ERR_NVML;
+    }
     G.have_event_set = true;
     for (auto &d : G.devs) {
       nvmlReturn_t r = G.ml.registerEvents(d->nvml, nvmlEventTypeXidCriticalError, G.event_set);
@@ -1117,10 +1429,49 @@ int gsb_health_start(uint32_t probe_period_ms, uint64_t window_bytes) {
         ev.etype = GSB_EVENT_XID;
         ev.edata = ~0ull;
         push_event(ev);
+      } else if (r != NVML_SUCCESS) {
+        // nvidia.go:114-116: any other registration error is fatal (log.Fatalf) — a GPU without XID coverage must
+        // not stay silently Healthy. The caller decides what fatal means; nothing is left half started.
+        set_error("nvml: %s (nvmlDeviceRegisterEvents on %s)", G.ml.errorString(r), d->uuid);
+        G.ml.eventSetFree(G.event_set);
+        G.have_event_set = false;
+        std::lock_guard<std::mutex> hl(G.hmu);
+        G.events.clear();
+        return GSB_ERR_NVML;
       }
     }
     G.health_threads.emplace_back([] {
+      uint64_t last_refresh = now_ns();
       while (!G.health_stop.load()) {
+        // low-rate inventory refresh (GSB_OPT_INVENTORY_REFRESH_MS, default 5000 = the reference's WaitForEvent
+        // period; 0 = never): NVML is re-asked off the cycle's path, and an answer that differs from the snapshot
+        // (a different GPU behind the handle, a different total) is reported as an event, not papered over
+        const uint64_t period = G.inventory_refresh_ms.load() * 1000000ull;
+        if (period && now_ns() - last_refresh >= period) {
+          last_refresh = now_ns();
+          for (auto &d : G.devs) {
+            Snapshot before;
+            {
+              std::lock_guard<std::mutex> sl(d->smu);
+              before = d->snap;
+            }
+            gsb_device_info info;
+            const int qrc = query_info(d.get(), &info);
+            uint64_t what = 0;
+            if (qrc == GSB_ERR_IDENTITY_MISMATCH || (qrc == GSB_OK && strcmp(before.uuid, info.uuid) != 0))
+              what = GSB_INVENTORY_IDENTITY_CHANGED;
+            else if (qrc == GSB_OK && before.total != info.total_bytes)
+              what = GSB_INVENTORY_TOTAL_CHANGED;
+            if (what) {
+              gsb_event ev;
+              memset(&ev, 0, sizeof ev);
+              snprintf(ev.uuid, sizeof ev.uuid, "%s", before.uuid);
+              ev.etype = GSB_EVENT_INVENTORY;
+              ev.edata = what;
+              push_event(ev);
+            }
+          }
+        }
         nvmlEventData_t data;
         memset(&data, 0, sizeof data);
         nvmlReturn_t r = G.ml.eventSetWait(G.event_set, &data, 200);
@@ -1142,6 +1493,9 @@ int gsb_health_start(uint32_t probe_period_ms, uint64_t window_bytes) {
   if (probe_period_ms > 0) {
     for (uint32_t i = 0; i < G.devs.size(); i++) {
       G.health_threads.emplace_back([i, probe_period_ms, window_bytes] {
+        // a prober with milliseconds between cycles sleeps through the kernel instead of spinning a core: the
+        // DaemonSet gives the whole plugin one CPU (device-plugin-ds.yaml:34-40)
+        tl_wait_blocking = probe_period_ms >= 10;
         std::vector<uint8_t> buf(1 << 16);
         uint64_t cycle = 0;
         bool reported = false;
@@ -1149,13 +1503,15 @@ int gsb_health_start(uint32_t probe_period_ms, uint64_t window_bytes) {
         while (!G.health_stop.load()) {
           gsb_cycle_result cr;
           int rc = gsb_cycle(i, cycle++, window_bytes, 1, GSB_VARIANT_AUTO, buf.data(), buf.size(), &cr);
+          // with no standing arena the cycle probes a transient window (allocate -> fill -> verify -> free); a
+          // window that could not be allocated (tenants hold the HBM) is silence, not a fault
           const bool this_cycle_clean = rc == GSB_OK && cr.probe.mismatch_words == 0;
           if (rc != GSB_ERR_NO_ARENA && !this_cycle_clean && !reported) {
             gsb_event ev;
             memset(&ev, 0, sizeof ev);
             snprintf(ev.uuid, sizeof ev.uuid, "%s", G.devs[i]->uuid);
             ev.etype = GSB_EVENT_PROBE;
-            ev.edata = rc == GSB_OK ? GSB_PROBE_FAULT_MISMATCH : GSB_PROBE_FAULT_LAUNCH;
+            ev.edata = rc == GSB_OK ? GSB_PROBE_FAULT_MISMATCH : rc == GSB_ERR_TIMEOUT ? GSB_PROBE_FAULT_WEDGED : GSB_PROBE_FAULT_LAUNCH;
             push_event(ev);
             reported = true;
             clean = 0;

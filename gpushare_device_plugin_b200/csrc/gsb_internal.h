@@ -60,6 +60,8 @@ int gsb_kernel_geometry(uint32_t op, uint32_t variant, uint32_t grid_request, in
 /* Enqueue one probe launch on `stream` of the current context. Returns cudaError_t as int. */
 int gsb_kernel_launch(uint32_t op, const gsb_launch_geom *geom, const gsb_kernel_args *args,
                       cudaStream_t stream);
+/* Test hook: one thread spinning on %globaltimer for `ns` nanoseconds on `stream`. Returns cudaError_t as int. */
+int gsb_kernel_stall(unsigned long long ns, cudaStream_t stream);
 /* Upper bound of CTAs any geometry will use on a device with `sm_count` SMs (sizes `partials`). */
 uint32_t gsb_kernel_max_grid(int sm_count);
 

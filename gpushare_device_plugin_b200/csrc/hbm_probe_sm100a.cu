@@ -881,7 +881,22 @@ probe_fn pick(uint32_t op, uint32_t variant, uint32_t *smem, uint32_t *threads) 
   }
 }
 
+// test hook (gsb_test_stall): hold the stream for `ns` nanoseconds
+__global__ void stall_kernel(unsigned long long ns) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    __nanosleep(1000);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  } while (t - t0 < ns);
+}
+
 }  // namespace
+
+int gsb_kernel_stall(unsigned long long ns, cudaStream_t stream) {
+  stall_kernel<<<1, 1, 0, stream>>>(ns);
+  return (int)cudaGetLastError();
+}
 
 uint32_t gsb_kernel_max_grid(int sm_count) { return (uint32_t)(sm_count * kMaxCtasPerSm); }
 

@@ -1,7 +1,7 @@
 """Thin Python face of the C ABI's device layer (inventory, arena, probe, cycle, health events).
 
-Everything here is a direct call into ``libgpushare_b200.so``; nothing is computed in Python and
-nothing is cached. Names follow include/gpushare_b200.h.
+Everything here is a direct call into ``libgpushare_b200.so``; nothing is computed or cached in Python (the
+library keeps NVML's (re)start-time inventory snapshot; see include/gpushare_b200.h). Names follow the header.
 """
 from __future__ import annotations
 
@@ -55,6 +55,36 @@ def device_info(idx: int) -> Info:
     s = DeviceInfo()
     check(lib.gsb_device_info_get(idx, C.byref(s)), f"gsb_device_info_get({idx})")
     return Info.of(s)
+
+
+def inventory_refresh(idx: int = _abi.GSB_ALL_DEVICES) -> None:
+    """Live NVML query -> snapshot; what NewNvidiaDevicePlugin's getDevices does at every (re)start (server.go:39)."""
+    check(lib.gsb_inventory_refresh(idx), f"gsb_inventory_refresh({idx})")
+
+
+def inventory_snapshot(idx: int):
+    """(Info, age_ns): NVML's last answer as the cycle serves it, identity re-validated on the CUDA side."""
+    s, age = DeviceInfo(), C.c_uint64(0)
+    check(lib.gsb_inventory_snapshot(idx, C.byref(s), C.byref(age)), f"gsb_inventory_snapshot({idx})")
+    return Info.of(s), age.value
+
+
+def set_option(key: int, value: int) -> None:
+    check(lib.gsb_set_option(key, value), f"gsb_set_option({key})")
+
+
+def get_option(key: int) -> int:
+    v = C.c_uint64(0)
+    check(lib.gsb_get_option(key, C.byref(v)), f"gsb_get_option({key})")
+    return v.value
+
+
+def test_stall(idx: int, ms: int) -> None:
+    """Test hook: keep the device's probe stream busy for `ms` ms (a stand-in for a wedged GPU)."""
+    check(lib.gsb_test_stall(idx, ms), f"gsb_test_stall({idx})")
+
+
+test_stall.__test__ = False  # not a pytest case
 
 
 def slices(total_mib: int, unit_gib: bool = True) -> int:
@@ -147,10 +177,12 @@ class Cycler:
         self.res = CycleResult()
         self.cycle_no = 0
 
-    def step(self) -> CycleResult:
+    def step(self, raise_on_error: bool = True) -> CycleResult:
         rc = lib.gsb_cycle(self.idx, self.cycle_no, self.window_bytes, 1 if self.unit_gib else 0, self.variant,
                            self.buf, len(self.buf), C.byref(self.res))
-        check(rc, f"gsb_cycle({self.idx})")
+        self.rc = rc
+        if raise_on_error:
+            check(rc, f"gsb_cycle({self.idx})")
         self.cycle_no += 1
         return self.res
 

@@ -134,8 +134,11 @@ def allocate(plugin, req: bytes) -> bytes:
             if not was_cached:
                 cache.load(plugin)
             kind, resp, pidx, pod_req = _decide(actx, cache, req)
-            if kind == _abi.GSB_ALLOC_ERR_RESPONSE and was_cached:
-                cache.load(plugin)  # the cache may simply be older than the pod being started
+            if kind > 0 and kind != _abi.GSB_ALLOC_MATCHED and was_cached:
+                # the cache may simply be older than the pod being started: the error response AND, on a one-GPU node,
+                # the single-GPU shortcut (allocate.go:151-177) are re-decided on a fresh LIST, as the reference —
+                # which LISTs on every call — would have decided them
+                cache.load(plugin)
                 kind, resp, pidx, pod_req = _decide(actx, cache, req)
         except Exception as e:  # noqa: BLE001  allocate.go:62-66
             cache.drop()

@@ -13,7 +13,7 @@ from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Tuple
 
 from .. import device
-from .._abi import GSB_EVENT_PROBE, GSB_EVENT_XID, GSB_PROBE_RECOVERED, GsbError, lib
+from .._abi import GSB_EVENT_INVENTORY, GSB_EVENT_PROBE, GSB_EVENT_XID, GSB_PROBE_RECOVERED, GsbError, lib
 from . import const
 
 log = logging.getLogger("gpushare.nvidia")
@@ -100,7 +100,9 @@ def watchXIDs(stop: threading.Event, devs: List[Device], xids: Callable[[Device]
             e = device.health_wait(5000)  # nvidia.go:126
             if e is None:
                 continue
-            if e.etype not in (GSB_EVENT_XID, GSB_EVENT_PROBE):  # nvidia.go:127-129
+            if e.etype == GSB_EVENT_INVENTORY:  # the low-rate NVML refresh disagrees with what is advertised
+                log.warning("inventory of %s changed under the plugin (%d): marking it unhealthy", e.uuid.decode(), e.edata)
+            elif e.etype not in (GSB_EVENT_XID, GSB_EVENT_PROBE):  # nvidia.go:127-129
                 continue
             if e.etype == GSB_EVENT_XID and lib.gsb_xid_is_benign(e.edata):  # nvidia.go:134-136
                 continue

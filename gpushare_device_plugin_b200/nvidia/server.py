@@ -34,7 +34,7 @@ class NvidiaDevicePlugin:
     def __init__(self, mps: bool, healthCheck: bool, queryKubelet: bool, client, socket: str = const.serverSock,
                  coalesce_health: bool = True, probe_period_ms: int = 1000, window_bytes: int = device.GiB,
                  max_workers: int = 16, pod_cache_ttl: float = 1.0, inventory=None,
-                 probe_arena_bytes: int = 4 * device.GiB, startup_full_walk: bool = False,
+                 probe_arena_bytes: int = 0, startup_full_walk: bool = False,
                  health_recovery_cycles: int = 0):
         # `inventory` = (devs, devNameMap) injects a synthetic node (tests, Allocate benchmark)
         self.devs, self.devNameMap = inventory if inventory is not None else nvidia.getDevices()  # server.go:39
@@ -76,9 +76,20 @@ class NvidiaDevicePlugin:
         name = self.devIndxMap.get(index)
         return name, name is not None
 
-    def _list_bytes(self) -> bytes:
-        bits = bytes(self._bits) if any(self._bits) else None
-        return device.encode_list_and_watch(self._uuids, self._slices, bits)
+    def _list_bytes(self, bits=None) -> bytes:
+        bits = self._bits if bits is None else bits
+        return device.encode_list_and_watch(self._uuids, self._slices, bytes(bits) if any(bits) else None)
+
+    def _apply(self, bits: bytearray, e: int, record: bool) -> None:
+        if e >= 0:  # d.Health = Unhealthy (server.go:181)
+            bits[e >> 3] |= 1 << (e & 7)
+            if record:
+                self.devs[e].Health = const.Unhealthy
+        else:       # optional recovery (not in the reference): ~e is the device index
+            i = ~e
+            bits[i >> 3] &= ~(1 << (i & 7)) & 0xFF
+            if record:
+                self.devs[i].Health = const.Healthy
 
     # ---- RPC handlers (raw bytes in/out) ---------------------------------------------------
     def GetDevicePluginOptions(self, request: bytes, context) -> bytes:  # server.go:85-87
@@ -88,8 +99,14 @@ class NvidiaDevicePlugin:
         return b""
 
     def ListAndWatch(self, request: bytes, context):  # server.go:172-185
+        # The node's health state (self._bits, devs[i].Health) is written by the PRODUCER of an event (unhealthy /
+        # recovered), never by a stream: an event raised while no stream is attached is in the first frame of the
+        # next one (the reference's unbuffered channel blocks the producer until a stream takes the event). Each
+        # stream replays the events it has not sent yet onto its own copy, so the reference-exact mode (one resend
+        # per fake device, each frame the state after that event) does not depend on how far a stream lags.
         with self._cv:
-            first = self._list_bytes()
+            mine = bytearray(self._bits)
+            first = self._list_bytes(mine)
             cursor = len(self._pending)
         yield first  # never yield while holding the condition's lock
         while True:
@@ -100,18 +117,12 @@ class NvidiaDevicePlugin:
                     return
                 frames = []
                 for e in self._pending[cursor:]:
-                    if e >= 0:  # d.Health = Unhealthy (server.go:181)
-                        self._bits[e >> 3] |= 1 << (e & 7)
-                        self.devs[e].Health = const.Unhealthy
-                    else:       # optional recovery (not in the reference): ~e is the device index
-                        i = ~e
-                        self._bits[i >> 3] &= ~(1 << (i & 7)) & 0xFF
-                        self.devs[i].Health = const.Healthy
+                    self._apply(mine, e, False)
                     if not self.coalesce_health:
-                        frames.append(self._list_bytes())
+                        frames.append(self._list_bytes(mine))
                 cursor = len(self._pending)
                 if self.coalesce_health:
-                    frames = [self._list_bytes()]
+                    frames = [self._list_bytes(mine)]
             for f in frames:
                 yield f
 
@@ -125,33 +136,44 @@ class NvidiaDevicePlugin:
     # ---- health plumbing (server.go:187-189, 203-221) ----------------------------------------
     def unhealthy(self, dev: nvidia.Device) -> None:
         with self._cv:
-            self._pending.append(self._index[dev.ID])
+            e = self._index[dev.ID]
+            self._apply(self._bits, e, True)
+            self._pending.append(e)
             self._cv.notify_all()
 
-    def setup_probe_arenas(self) -> None:
-        """The memory the active probe walks. Optionally one whole-device walk at start-up (everything the
-        driver hands out: allocate -> write -> verify -> release, ~0.4 s on an idle B200), then a small
-        steady-state arena per GPU whose 1 GiB windows the prober rotates through. A GPU whose memory is
-        fully taken by tenants simply has no arena: the XID half still watches it."""
-        from .._abi import GSB_OP_VERIFY, GsbError
+    def setup_probe_arenas(self, keep_free_bytes: int = device.GiB) -> None:
+        """The memory the active probe walks. Default (probe_arena_bytes == 0): none is held — each probe cycle
+        allocates its window, walks it and frees it (gsb_cycle's transient window), so the advertised slices are not
+        oversold by the plugin itself. A standing arena (probe_arena_bytes > 0) widens coverage but keeps that HBM
+        from tenants while ListAndWatch still advertises it; the warning says how much. Optionally one walk of
+        everything allocatable at start-up. No probe allocation takes the last `keep_free_bytes`."""
+        from .._abi import GSB_OP_VERIFY, GSB_OPT_TRANSIENT_KEEP_FREE_BYTES, GsbError
+        device.set_option(GSB_OPT_TRANSIENT_KEEP_FREE_BYTES, keep_free_bytes)
         for i, uuid in enumerate(self._uuids):
             try:
                 if self.startup_full_walk:
-                    nbytes = device.arena_create(i)  # FILL of every mapped byte happens inside
+                    nbytes = device.arena_create(i, keep_free_bytes=keep_free_bytes)  # FILL of every mapped byte happens inside
                     r = device.probe(i, GSB_OP_VERIFY, flags=3)  # timed + generation table
-                    log.info("start-up walk of %s: %d bytes allocatable, %d mismatching words, %.1f ms", uuid, nbytes,
-                             r.mismatch_words, r.kernel_ns / 1e6)
+                    log.info("start-up walk of %s: %d bytes actually allocatable, %d mismatching words, %.1f ms", uuid,
+                             nbytes, r.mismatch_words, r.kernel_ns / 1e6)
                     if r.mismatch_words:
                         device.health_inject(uuid, 0x100, 1)
                     device.arena_destroy(i)
-                nbytes = device.arena_create(i, max_bytes=self.probe_arena_bytes, keep_free_bytes=device.GiB)
-                log.info("probe arena on %s: %d bytes", uuid, nbytes)
+                if self.probe_arena_bytes > 0:
+                    nbytes = device.arena_create(i, max_bytes=self.probe_arena_bytes, keep_free_bytes=keep_free_bytes)
+                    log.warning("standing probe arena on %s: %d bytes held by the plugin and NOT available to tenants "
+                                "(%s still advertises %d slices)", uuid, nbytes, const.resourceName, self._slices)
+                else:
+                    log.info("probe of %s: transient %d MiB window per cycle, nothing held between cycles", uuid,
+                             self.window_bytes >> 20)
             except GsbError as e:
                 log.warning("no probe arena on %s: %s", uuid, e)
 
     def recovered(self, dev: nvidia.Device) -> None:
         with self._cv:
-            self._pending.append(~self._index[dev.ID])
+            e = ~self._index[dev.ID]
+            self._apply(self._bits, e, True)
+            self._pending.append(e)
             self._cv.notify_all()
 
     def healthcheck(self) -> None:

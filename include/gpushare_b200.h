@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define GSB_ABI_VERSION 1u
+#define GSB_ABI_VERSION 2u /* 2: inventory snapshot + options, transient window, watchdog; gsb_cycle_result grew */
 
 /* = NVML_DEVICE_UUID_BUFFER_SIZE (vendor/.../nvml/nvml.h:1567), used by bindings.go:20 szUUID */
 #define GSB_UUID_BUFFER_SIZE 80
@@ -90,9 +90,42 @@ typedef struct gsb_device_info {
 } gsb_device_info;
 
 int gsb_device_count(uint32_t *n);
-/* Re-queries the volatile fields (memory info) on every call; identity fields are re-read and
- * re-verified too — nothing is served from a cache. */
+/* ≙ nvml.NewDevice(idx) at plugin (re)start (server.go:39 -> nvidia.go:60): a LIVE query — UUID, minor and
+ * nvmlMemory_t re-read from NVML, identity re-verified against the CUDA driver — nothing served from a cache.
+ * It also rewrites the device's inventory snapshot (below). */
 int gsb_device_info_get(uint32_t idx, gsb_device_info *out);
+
+/*
+ * Inventory snapshot. The reference asks NVML for identity and memory ONCE per plugin (re)start (server.go:39,
+ * nvidia.go:53-89) and never again while serving; its steady state is a blocked nvmlEventSetWait. Here gsb_init
+ * and every gsb_device_info_get / gsb_inventory_refresh store NVML's answer per device, and the steady-state
+ * cycle (gsb_cycle / gsb_cycle_all) reads identity + total from that snapshot, re-validating the identity on every
+ * cycle against the CUDA driver (cuDeviceGetUuid: user-mode, no driver-wide lock). nvmlDeviceGetMemoryInfo on a
+ * 0.3 ms cadence convoys with every other NVML client of the node (nvidia-smi, dcgm-exporter): 6 us idle, up to
+ * 2.3 ms contended (BENCH_r01). While health is running a low-rate refresher (GSB_OPT_INVENTORY_REFRESH_MS) re-asks
+ * NVML off the cycle's path and raises GSB_EVENT_INVENTORY if the answer changed.
+ */
+#define GSB_ALL_DEVICES 0xFFFFFFFFu
+int gsb_inventory_refresh(uint32_t idx);  /* idx or GSB_ALL_DEVICES: live NVML query -> snapshot */
+/* the snapshot as the cycle sees it (identity re-validated), and how old it is */
+int gsb_inventory_snapshot(uint32_t idx, gsb_device_info *out, uint64_t *age_ns);
+
+/* ---- options ------------------------------------------------------------------------------ */
+enum {
+  GSB_OPT_INVENTORY_POLICY = 1,          /* GSB_INVENTORY_SNAPSHOT (default) | GSB_INVENTORY_LIVE */
+  GSB_OPT_WAIT_SPIN_US = 2,              /* completion wait: spin budget before sleeping (default 2000; prober
+                                            threads with a period >= 10 ms never spin) */
+  GSB_OPT_WATCHDOG_MS = 3,               /* completion watchdog of a probe launch (default 2000, + 1 ns per 10
+                                            window bytes); 0 = off (waits for ever) */
+  GSB_OPT_INVENTORY_REFRESH_MS = 4,      /* low-rate NVML refresh while health runs (default 5000; 0 = never) */
+  GSB_OPT_TRANSIENT_KEEP_FREE_BYTES = 5  /* HBM a transient probe window never takes (default 1 GiB) */
+};
+enum {
+  GSB_INVENTORY_SNAPSHOT = 0, /* cycle: NVML's (re)start-time answer + per-cycle CUDA-side identity check */
+  GSB_INVENTORY_LIVE = 1      /* cycle: fresh NVML UUID/minor/MemoryInfo every cycle (round-1 behaviour) */
+};
+int gsb_set_option(uint32_t key, uint64_t value);
+int gsb_get_option(uint32_t key, uint64_t *value);
 /* setGPUMemory (nvidia.go:34-41): unit_gib != 0 -> total_mib / 1024, else total_mib. Pure. */
 uint32_t gsb_slices(uint64_t total_mib, int unit_gib);
 /* "<uuid>-_-<j>" (nvidia.go:26-28). Returns length written (excluding NUL) or negative status. */
@@ -180,20 +213,33 @@ int gsb_probe_all(uint32_t n, const uint32_t *idxs, const gsb_probe_cfg *cfg, gs
 /* test hooks: raw access to arena bytes (fault injection / read-back by the parity tests) */
 int gsb_arena_read(uint32_t idx, uint64_t offset, void *dst, uint64_t bytes);
 int gsb_arena_write(uint32_t idx, uint64_t offset, const void *src, uint64_t bytes);
+/* test hook: enqueue a kernel that keeps the device's probe stream busy for `ms` milliseconds — a stand-in for a
+ * wedged GPU, to exercise the completion watchdog */
+int gsb_test_stall(uint32_t idx, uint32_t ms);
 
 /*
  * One inventory + health-probe cycle of one device (the unit of BASELINE.json's metric):
- * identity + memory info (fresh driver/NVML queries) -> slices -> S fake devices ->
- * ListAndWatchResponse bytes into lw_buf -> VERIFY_REFILL of the arena window that holds slice
- * (cycle_no mod arena_slices) (window_bytes == 0: the whole arena) -> verdict.
+ * identity + total (GSB_OPT_INVENTORY_POLICY: snapshot re-validated on the CUDA side, or a live NVML query)
+ * -> slices -> S fake devices -> ListAndWatchResponse bytes into lw_buf -> HBM walk -> verdict.
+ *   standing arena (gsb_arena_create was called): VERIFY_REFILL of the arena window that holds slice
+ *     (cycle_no mod arena_slices) (window_bytes == 0: the whole arena); traffic 2 * W.
+ *   no arena, window_bytes > 0: TRANSIENT window (SURVEY.md §7 hard-part 2) — allocate up to window_bytes
+ *     (never the last GSB_OPT_TRANSIENT_KEEP_FREE_BYTES), FILL, VERIFY, free; traffic 2 * W; nothing is held
+ *     between cycles. If nothing can be allocated the cycle is inventory-only: rc GSB_OK, healthy unchanged,
+ *     probe.status == GSB_ERR_OUT_OF_MEMORY, probe.bytes_walked == 0.
+ * A launch that outlives the watchdog returns GSB_ERR_TIMEOUT with healthy == 0.
  */
 typedef struct gsb_cycle_result {
   gsb_device_info info;
   uint32_t slices;
-  uint32_t healthy;      /* 1 iff probe status OK and mismatch_words == 0 */
+  uint32_t healthy;      /* 1 iff this cycle's walk was clean AND no earlier cycle faulted (Unhealthy is sticky,
+                            server.go:180) */
   int64_t lw_len;        /* bytes written to lw_buf */
-  uint64_t inventory_ns; /* host time of the identity/memory queries + encode */
+  uint64_t inventory_ns; /* host time of the identity/memory step + encode */
   gsb_probe_result probe;
+  uint64_t snapshot_age_ns; /* policy SNAPSHOT: age of NVML's answer the cycle served */
+  uint32_t inventory_live;  /* 1 = this cycle queried NVML itself */
+  uint32_t transient;       /* 1 = transient window (allocate -> walk -> free) */
 } gsb_cycle_result;
 int gsb_cycle(uint32_t idx, uint64_t cycle_no, uint64_t window_bytes, int unit_gib, uint32_t variant,
               uint8_t *lw_buf, size_t lw_cap, gsb_cycle_result *out);
@@ -213,10 +259,13 @@ int64_t gsb_cycle_all(uint32_t n, const uint32_t *idxs, uint64_t cycle_no, uint6
 /* ---- health events (a10, a11) ------------------------------------------------------------ */
 
 enum {
-  GSB_EVENT_XID = 8,   /* = nvmlEventTypeXidCriticalError (nvml.h:1082); edata = XID */
-  GSB_EVENT_PROBE = 0x100 /* active probe verdict; edata = GSB_PROBE_FAULT_* */
+  GSB_EVENT_XID = 8,        /* = nvmlEventTypeXidCriticalError (nvml.h:1082); edata = XID */
+  GSB_EVENT_PROBE = 0x100,  /* active probe verdict; edata = GSB_PROBE_FAULT_* */
+  GSB_EVENT_INVENTORY = 0x200 /* the low-rate NVML refresh disagrees with the snapshot; edata = GSB_INVENTORY_*_CHANGED */
 };
-enum { GSB_PROBE_FAULT_MISMATCH = 1, GSB_PROBE_FAULT_LAUNCH = 2, GSB_PROBE_RECOVERED = 3 };
+enum { GSB_PROBE_FAULT_MISMATCH = 1, GSB_PROBE_FAULT_LAUNCH = 2, GSB_PROBE_RECOVERED = 3,
+       GSB_PROBE_FAULT_WEDGED = 4 /* the launch outlived the completion watchdog */ };
+enum { GSB_INVENTORY_IDENTITY_CHANGED = 1, GSB_INVENTORY_TOTAL_CHANGED = 2 };
 
 typedef struct gsb_event {
   char uuid[GSB_UUID_BUFFER_SIZE]; /* empty => applies to all devices (nvidia.go:138-144) */
@@ -226,7 +275,10 @@ typedef struct gsb_event {
 
 /* Start: one NVML event set with XidCriticalError registered once per *GPU* (the reference does
  * it once per fake device, nvidia.go:104-117 — same resulting set) plus, if probe_period_ms > 0, a
- * prober thread per device running gsb_cycle-style window probes. */
+ * prober thread per device running gsb_cycle (standing arena if one exists, else transient windows).
+ * A registration that fails with anything but NOT_SUPPORTED fails the call with GSB_ERR_NVML and starts
+ * nothing (the reference: log.Fatalf, nvidia.go:114-116); NOT_SUPPORTED queues an Unhealthy event for
+ * that GPU (nvidia.go:107-112). */
 int gsb_health_start(uint32_t probe_period_ms, uint64_t window_bytes);
 int gsb_health_stop(void);
 /* ≙ nvml.WaitForEvent(set, timeout) (bindings.go:134-146): GSB_OK + event, or GSB_ERR_TIMEOUT. */

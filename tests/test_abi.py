@@ -26,7 +26,7 @@ def test_header_binding_and_library_agree():
     out = subprocess.run(["nm", "-D", "--defined-only", _abi.LIB_PATH], capture_output=True, text=True, check=True).stdout
     exported = sorted(set(re.findall(r" T (gsb_[a-z_0-9]+)", out)))
     assert exported == declared
-    assert _abi.lib.gsb_abi_version() == 1
+    assert _abi.lib.gsb_abi_version() == _abi.GSB_ABI_VERSION
 
 
 def test_no_hard_dependency_on_cuda_or_nvml_libraries():
@@ -107,7 +107,7 @@ def test_plain_c99_client_sees_the_reference_bytes(tmp_path):
     line = {l.split(" ", 1)[0]: l.split(" ", 1)[1] for l in out if l.split(" ", 1)[0] != "allocate"}
     allocs = [l.split(" ") for l in out if l.startswith("allocate ")]
     u0, u1 = "GPU-fef8089b-4820-abfc-e83e-94318197576e", "GPU-fef8089c-4820-abfc-e83e-94318197576f"
-    assert line["abi"] == "1" and line["slices"] == "179 183359 0"
+    assert line["abi"] == str(_abi.GSB_ABI_VERSION) and line["slices"] == "179 183359 0"
     assert line["fake"] == f"46 {wo.generateFakeDeviceID(u0, 178)}" and line["real"] == f"40 {u0}"
     assert line["small-buffer"] == "buffer too small" and line["xid"] == "1 1 1 0 0"
     devs = [[wo.generateFakeDeviceID(u, j), wo.Unhealthy if (u, j) == (u0, 1) else wo.Healthy] for u in (u0, u1) for j in range(3)]

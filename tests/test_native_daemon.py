@@ -684,3 +684,72 @@ def test_serialize_allocate_is_the_reference_locking(world):
         [c.close() for c in chans]
         d.close()
     assert timings["default"] < 0.45 and timings["serialized"] > 0.55, timings  # ~1 vs ~4 PATCH round trips of 0.15 s
+
+
+# ---- round-2 advisor findings ---------------------------------------------------------------------------
+
+def test_health_event_raised_before_any_stream_is_in_the_first_frame(world):
+    """A fault raised while no ListAndWatch stream is attached (start-up walk, NOT_SUPPORTED registration, kubelet
+    reconnect) must be in the next stream's first frame: the producer writes the node state, streams only resend."""
+    d = world.start()
+    ch = d.channel()
+    d.inject(ch, fakes.UUIDS[3], 8, 79)
+    time.sleep(0.6)  # the health loop has taken the event; no stream has ever been open
+    it = Frames(d.kubelet.list_and_watch(ch))
+    assert wo.unmarshal_ListAndWatchResponse(next_frame(it)) == all_devs(unhealthy={3})
+    assert next_frame(it, 0.6) == "timeout"
+    it2 = Frames(d.kubelet.list_and_watch(ch))  # a reconnect starts from the same state
+    assert wo.unmarshal_ListAndWatchResponse(next_frame(it2)) == all_devs(unhealthy={3})
+    d.inject(ch, fakes.UUIDS[6], 0x100, 1)
+    for s in (it, it2):
+        assert wo.unmarshal_ListAndWatchResponse(next_frame(s)) == all_devs(unhealthy={3, 6})
+    assert "unhealthy_slices 179" in _dump(d)
+    ch.close()
+
+
+def _dump(d):
+    d.proc.send_signal(signal.SIGQUIT)
+    deadline = time.time() + 5
+    while time.time() < deadline:
+        files = [f for f in os.listdir(d.dir) if f.startswith("go_")]
+        if files:
+            time.sleep(0.1)
+            return open(os.path.join(d.dir, files[0])).read()
+        time.sleep(0.05)
+    return ""
+
+
+def test_reference_stream_mode_is_exact_for_a_stream_that_attaches_late(world):
+    """coalesce-health=false: one resend per fake device, each frame the state after that event — also for the
+    events that arrive after a stream attached to a node that already had an unhealthy GPU."""
+    d = world.start("--coalesce-health=false")
+    ch = d.channel()
+    d.inject(ch, fakes.UUIDS[0], 8, 79)
+    time.sleep(0.6)
+    it = Frames(d.kubelet.list_and_watch(ch))
+    start = all_devs(unhealthy={0})
+    assert wo.unmarshal_ListAndWatchResponse(next_frame(it)) == start
+    d.inject(ch, fakes.UUIDS[1], 8, 79)
+    ids = [x[0] for x in start]
+    want = wo.list_and_watch_stream(start, wo.xid_event_effects(ids, 8, 79, fakes.UUIDS[1]))
+    assert [next_frame(it) for _ in range(179)] == want[1:]
+    ch.close()
+
+
+def test_single_gpu_node_does_not_answer_a_stale_cache_with_the_shortcut(world):
+    """One GPU + a cached pod table older than the pod being started: the reference (LIST per call) finds the pod,
+    answers with its annotated index and PATCHes it; the single-GPU shortcut must not answer from the stale table."""
+    for k in list(world.kube.pods):
+        world.kube.pods[k]["status"]["phase"] = "Running"
+    d = world.start("--pod-cache-ttl", "60", "--pod-informer=false", n_gpus=1)
+    ch = d.channel()
+    envs = wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, wo.marshal_AllocateRequest([["a", "b", "c"]])))
+    assert envs[0]["NVIDIA_VISIBLE_DEVICES"] == fakes.UUIDS[0]  # nothing pending: the shortcut is right here
+    new = make_pod(99, NODE, gpu_mem=2, idx=fakes.MINORS[0], assume_time=1_800_000_000_000_000_000)
+    with world.kube.lock:
+        world.kube.pods[("default", "pod-99")] = new
+        world.kube.order.append(("default", "pod-99"))
+    envs = wo.unmarshal_AllocateResponse(d.kubelet.allocate(ch, wo.marshal_AllocateRequest([["a", "b"]])))
+    assert envs[0]["NVIDIA_VISIBLE_DEVICES"] == str(fakes.MINORS[0]) == envs[0]["ALIYUN_COM_GPU_MEM_IDX"]
+    assert world.kube.pod("pod-99")["metadata"]["annotations"]["ALIYUN_COM_GPU_MEM_ASSIGNED"] == "true"
+    ch.close()

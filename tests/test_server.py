@@ -439,3 +439,51 @@ def test_optional_recovery_is_off_by_default_and_flag_gated(world):
     device.health_inject(fakes.UUIDS[1], 0x100, 3)
     assert settle(first)  # all Healthy again, byte-identical to the initial list
     ch.close()
+
+
+# ---- round-2 advisor findings ---------------------------------------------------------------------------
+
+def test_health_event_raised_before_any_stream_is_in_the_first_frame(world):
+    """The reference's unbuffered channel blocks the producer until a stream takes the event, so nothing is lost;
+    here the producer writes the node state itself, so a fault raised before the kubelet opens ListAndWatch (a
+    start-up walk fault, a NOT_SUPPORTED registration, a reconnect window) is in that stream's first frame."""
+    p = world.make()
+    p.Serve(world.kubelet.socket)
+    device.health_inject(fakes.UUIDS[3], 8, 79)
+    deadline = time.monotonic() + 5
+    while p.devs[3 * 179].Health != const.Unhealthy and time.monotonic() < deadline:
+        threading.Event().wait(0.02)
+    ch = world.kubelet.channel("aliyungpushare.sock")
+    it = Frames(world.kubelet.list_and_watch(ch))
+    assert wo.unmarshal_ListAndWatchResponse(next_frame(it)) == all_devs(unhealthy={3})
+    assert next_frame(it, 0.6) == "timeout"  # and it is not re-sent as news
+    # a second stream (kubelet reconnect) starts from the same state; a later event reaches both
+    it2 = Frames(world.kubelet.list_and_watch(ch))
+    assert wo.unmarshal_ListAndWatchResponse(next_frame(it2)) == all_devs(unhealthy={3})
+    device.health_inject(fakes.UUIDS[6], 0x100, 1)
+    for s in (it, it2):
+        assert wo.unmarshal_ListAndWatchResponse(next_frame(s)) == all_devs(unhealthy={3, 6})
+    ch.close()
+
+
+def test_single_gpu_node_does_not_answer_a_stale_cache_with_the_shortcut(world, monkeypatch):
+    """One GPU + a cached pod table that pre-dates the pod being started: the reference LISTs on every call, finds
+    the pod, answers with its annotated index and PATCHes it. A cached table must not let the single-GPU shortcut
+    (allocate.go:151-177) answer instead — the pod would stay unassigned and be mis-matched later."""
+    fakes.install(monkeypatch, n_gpus=1)
+    for k in list(world.kube.pods):
+        world.kube.pods[k]["status"]["phase"] = "Running"
+    p = world.make(pod_cache_ttl=60)
+    p.Serve(world.kubelet.socket)
+    ch = world.kubelet.channel("aliyungpushare.sock")
+    # fills the cache; nothing pending -> the shortcut is the right answer here
+    envs = wo.unmarshal_AllocateResponse(world.kubelet.allocate(ch, wo.marshal_AllocateRequest([["a", "b", "c"]])))
+    assert envs[0]["NVIDIA_VISIBLE_DEVICES"] == fakes.UUIDS[0] and _lists(world) == 1  # decided on a fresh LIST
+    new = make_pod(99, NODE, gpu_mem=2, idx=fakes.MINORS[0], assume_time=1_800_000_000_000_000_000)
+    with world.kube.lock:
+        world.kube.pods[("default", "pod-99")] = new
+        world.kube.order.append(("default", "pod-99"))
+    envs = wo.unmarshal_AllocateResponse(world.kubelet.allocate(ch, wo.marshal_AllocateRequest([["a", "b"]])))
+    assert envs[0]["NVIDIA_VISIBLE_DEVICES"] == str(fakes.MINORS[0]) == envs[0]["ALIYUN_COM_GPU_MEM_IDX"]
+    assert world.kube.pod("pod-99")["metadata"]["annotations"]["ALIYUN_COM_GPU_MEM_ASSIGNED"] == "true"
+    ch.close()

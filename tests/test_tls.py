@@ -253,3 +253,42 @@ def test_concurrent_allocates_and_watch_over_tls(pki, tmp_path):
         log.close()
         kubelet.stop()
         kube.close()
+
+
+@pytest.mark.skipif(not os.access(GSBD, os.X_OK), reason="gsbd not built")
+def test_kubelet_pods_client_presents_the_client_certificate(pki, tmp_path):
+    """--query-kubelet with --client-cert/--client-key (cmd/nvidia/main.go:40-46: TLSClientConfig{CertFile, KeyFile},
+    server verification off): the kubelet /pods/ endpoint demands a client certificate; the pending pods must come
+    from it at the first try, not from the apiserver fallback after nine refused handshakes."""
+    import time
+    api = MockKube(make_node(NODE), config4_pods(NODE))
+    kubelet_api = MockKube(make_node(NODE), config4_pods(NODE), tls=(str(pki / "server.crt"), str(pki / "server.key")),
+                           client_ca=str(pki / "ca.crt"))
+    kubelet = FakeKubelet(str(tmp_path))
+    env = dict(os.environ, NODE_NAME=NODE, GPUSHARE_PLUGIN_DIR=str(tmp_path) + "/", GPUSHARE_RETRY_SLEEP_MS="1",
+               GSBD_ALLOW_FAKE_INVENTORY="1")
+    env.pop("KUBECONFIG", None)
+    log = open(tmp_path / "gsbd.log", "w")
+    p = subprocess.Popen([GSBD, "--v=5", "--fake-inventory", "8", "--kube-api-url", api.url, "--query-kubelet",
+                          "--kubelet-address", "127.0.0.1", "--kubelet-port", str(kubelet_api.port),
+                          "--client-cert", str(pki / "client.crt"), "--client-key", str(pki / "client.key")],
+                         env=env, stderr=log, stdout=log)
+    try:
+        kubelet.register_requests.get(timeout=20)
+        ch = kubelet.channel("aliyungpushare.sock")
+        t0 = time.monotonic()
+        envs = wo.unmarshal_AllocateResponse(kubelet.allocate(ch, wo.marshal_AllocateRequest([["a", "b", "c", "d"]])))
+        took = time.monotonic() - t0
+        ch.close()
+        assert envs[0]["ALIYUN_COM_GPU_MEM_IDX"] == "0"
+        assert any(r[:2] == ("GET", "/pods/") for r in kubelet_api.requests)        # served by the kubelet, over mTLS
+        assert not any(r[0] == "GET" and r[1].startswith("/api/v1/pods?") for r in api.requests)  # no apiserver fallback
+        assert took < 0.8  # nine failed tries would have cost 8 x 100 ms
+    finally:
+        if p.poll() is None:
+            p.terminate()
+            p.wait(timeout=10)
+        log.close()
+        kubelet.stop()
+        api.close()
+        kubelet_api.close()
