@@ -1,27 +1,36 @@
 #!/usr/bin/env python
 """bench.py — inventory + health-probe cycles/s (BASELINE.json's metric) on N B200s of one node.
 
-One step = one cycle of ONE device through the C ABI call `gsb_cycle` (include/gpushare_b200.h):
-fresh NVML/driver identity + memory queries -> slice count -> S fake devices -> ListAndWatchResponse
-bytes -> VERIFY_REFILL launch of the sm_100a probe kernel over this cycle's window of the arena ->
-verdict folded into Health. The path does not shard: under torchrun every rank
-is an independent replica on its own GPU, no data-path collective; value = device-cycles all ranks
-completed / max-over-ranks time ("scaling": "weak").
+One step = one cycle of ONE device through the C ABI call `gsb_cycle` (include/gpushare_b200.h): identity + total
+(NVML's (re)start-time answer, identity re-validated against the CUDA driver every cycle — the reference asks NVML
+once per plugin start too, server.go:39) -> slice count -> S fake devices -> ListAndWatchResponse bytes ->
+VERIFY_REFILL launch of the sm_100a probe kernel over this cycle's window of the arena -> verdict folded into
+Health. The path does not shard: under torchrun every rank is an independent replica on its own
+GPU, no data-path collective; value = device-cycles all ranks completed / max-over-ranks time ("scaling": "weak").
 
-Headline workload (config.workload): steady-state rotating window, W = 1 GiB (= one advertised
-aliyun.com/gpu-mem slice) moving across an arena of ALL allocatable HBM (~177.7 GiB), so no window is
-ever L2-resident. The full-arena walk (W = whole arena, one launch) is measured in the same run and
-reported under "full_walk" with its own roofline.
+Headline workload (config.workload): steady state, W = 1 GiB (= one advertised aliyun.com/gpu-mem slice) rotating
+over an arena of ALL allocatable HBM (~177.7 GiB), so no window is ever L2-resident.
 
-  value      cycles/s from CUDA-event time of the probe launches (arena resident in HBM)
-  e2e        cycles/s from host wall time around the gsb_cycle calls (NVML queries, encode, launch,
-             stream sync, result read-back from pinned host memory) — the number to hold against
-             `--impl reference`
+  value      cycles/s from the CUDA-event time of the probe launches ONLY (arena resident in HBM; excludes
+             inventory, encode and every host cost — it is the roofline's companion, not a speed-up claim)
+  e2e        cycles/s from host wall time around the gsb_cycle calls (identity check, encode, launch, completion
+             wait, result read-back from pinned host memory): the number to hold against `--impl reference`;
+             mean-based `value` plus p50/p99 per step
   roofline   algorithmic bytes 2*W per launch / mean CUDA-event duration, vs MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline / --impl reference: the reference's NVML call sequence (oracle/_ref/ref_inventory,
-             built with the reference's own nvml_dl.c) timed on this box's host cores, 1 thread —
-             the reference is sequential by construction (nvidia.go:59) and budgeted 1 CPU
-             (device-plugin-ds.yaml:34-40). It never touches HBM.
+  setup      what is paid once per plugin start and is NOT in any cycle: ours = gsb_init (dlopen, nvmlInit, cuInit,
+             first NVML inventory) + arena (VMM map of all allocatable HBM + FILL); the reference's = nvmlInit +
+             first getDevices + watchXIDs' registration loop. Reported on both arms, timed in neither.
+  legs (same run, outside the headline's timed region, each with its own numbers):
+    live_nvml   the round-1 cycle: a fresh NVML UUID/minor/MemoryInfo query every cycle (GSB_INVENTORY_LIVE)
+    full_walk   W = the whole arena, one launch
+    transient   the tenant-safe daemon default: no standing arena; allocate W -> FILL -> VERIFY -> free per cycle
+    node_cycle  ONE process, all N devices of the run through gsb_cycle_all (what the daemon does; BASELINE
+                config 3): rank 0 alone, after every rank has released its arena
+  cpu_baseline / --impl reference --gpus N: the reference's NVML call sequence (oracle/_ref/ref_inventory, built
+             with the reference's own nvml_dl.c) on this box's host cores, 1 thread — the reference is sequential by
+             construction (nvidia.go:59) and budgeted 1 CPU (device-plugin-ds.yaml:34-40) — over the first N GPUs:
+             one cycle = getDevices (N x 11 NVML getters + fan-out + marshal) + one WaitForEvent(0) on the standing
+             event set. It never touches HBM.
 """
 from __future__ import annotations
 
@@ -160,17 +169,28 @@ def allmax(dist, local, x: float) -> float:
     return float(t.item())
 
 
-def run_reference_cycles(iters: int, warmup: int) -> dict:
-    """oracle/_ref/ref_inventory bench: inventory (11 NVML getters/GPU + fan-out + marshal) +
-    health set-up (RegisterEventForDevice per fake device) + one WaitForEvent(0 ms), per cycle, on 1
-    pinned host thread."""
+def run_reference_cycles(iters: int, warmup: int, gpus: int = 0, setup_iters: int = 3) -> dict:
+    """oracle/_ref/ref_inventory bench over the first `gpus` GPUs (0 = all): health set-up once
+    (RegisterEventForDevice per fake device), then `iters` timed cycles of inventory (11 NVML getters/GPU + fan-out +
+    marshal) + one WaitForEvent(0 ms) on the standing event set, on 1 pinned host thread."""
     if not os.access(REF_BIN, os.X_OK):
         raise RuntimeError("oracle/_ref/ref_inventory missing: run build.sh where /root/reference exists")
-    cmd = [REF_BIN, "bench", "--iters", str(iters + warmup), "--wait-ms", "0"]
+    cmd = [REF_BIN, "bench", "--iters", str(iters), "--warmup", str(warmup), "--wait-ms", "0",
+           "--setup-iters", str(setup_iters)]
+    if gpus:
+        cmd += ["--gpus", str(gpus)]
     if subprocess.run(["taskset", "-c", "0", "true"], capture_output=True).returncode == 0:
         cmd = ["taskset", "-c", "0"] + cmd
     out = subprocess.run(cmd, check=True, capture_output=True, text=True, timeout=600)
     return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def reference_phases(r: dict) -> dict:
+    return {"cycle_us": {"inventory_p50": r["inventory_us"]["p50"], "health_poll_p50": r["health_poll_us"]["p50"],
+                         "cycle_p50": r["cycle_us"]["p50"], "cycle_p99": r["cycle_us"]["p99"], "cycle_mean": r["cycle_us"]["mean"]},
+            "setup_once_per_start_us": {"nvml_init": r["nvml_init_us"], "first_inventory": r["first_inventory_us"],
+                                        "health_setup_p50": r["health_setup_us"]["p50"],
+                                        "register_calls": r["register_calls_per_setup"], "register_rc": r["register_rc"]}}
 
 
 def pynvml_twin(iters: int) -> dict:
@@ -345,6 +365,18 @@ def bench_allocate(impl: str, quick: bool = False) -> dict:
         close()
         out["sweep"].append(r)
     out["p50_us"] = out["config4"]["p50_us"]
+    if impl == "ours":
+        ref_row = [v for k, v in out.get("config4_by_pod_source", {}).items() if "serialize-allocate" in k]
+        out["p50_context"] = {
+            "config4_p50_us": out["p50_us"],
+            "compiled_reference_behaviour_config4_p50_us": ref_row[0] if ref_row else None,
+            "speedup_vs_compiled_reference_behaviour_c1": (ref_row[0] / out["p50_us"]) if ref_row and out["p50_us"] else None,
+            "c16": {"ours_p50_us": next((p["p50_us"] for p in out["sweep"] if p.get("concurrency") == 16 and "p50_us" in p), None),
+                    "compiled_reference_behaviour_p50_us": out.get("compiled_reference_behaviour_c16", {}).get("p50_us")},
+            "note": "the comparison to quote: the same compiled daemon with the reference's behaviour switched back on "
+                    "(--pod-informer=false --pod-cache-ttl 0 --serialize-allocate = LIST per call under one lock held across "
+                    "the PATCH, allocate.go:59-60). The `--impl reference` arm's Allocate is a Python port and flatters us "
+                    "by the interpreter's cost"}
     return out
 
 
@@ -352,7 +384,7 @@ def bench_reference(args) -> None:
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return  # rank 0 alone runs the (sequential, single-process) reference path
-    r = run_reference_cycles(args.steps, args.warmup)
+    r = run_reference_cycles(args.steps, args.warmup, gpus=args.gpus)
     n = r["n_gpus"]
     mean_us = r["cycle_us"]["mean"]
     value = n * 1e6 / mean_us  # one node cycle covers n devices sequentially
@@ -361,32 +393,45 @@ def bench_reference(args) -> None:
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean_us / 1e3 / max(n, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": WORKLOAD,
-                   "reference_path": "N x nvml.NewDevice (11 getters) + fan-out + gogo marshal, RegisterEventForDevice x "
-                                     "S*N, one WaitForEvent(0 ms); sequential, 1 thread; the reference moves no HBM bytes",
+                   "reference_path": f"one cycle = getDevices over the first {n} GPU(s) (11 NVML getters each + fan-out + gogo "
+                                     "marshal, nvidia.go:53-89) + one WaitForEvent(0 ms) on the standing event set "
+                                     "(nvidia.go:126); sequential, 1 thread; the reference moves no HBM bytes. The event-set "
+                                     "registration (S*N RegisterEventForDevice, nvidia.go:104-117) is once per plugin start and "
+                                     "is reported under setup, outside the timed cycles — as our arm's arena set-up is",
                    "devices_seen": n, "fake_devices": r["n_devices"], "lw_bytes": r["lw_len"],
-                   "register_calls_per_cycle": r["register_calls_per_cycle"], "register_rc": r["register_rc"],
-                   "phases_us_p50": {"inventory": r["inventory_us"]["p50"], "health_setup": r["health_setup_us"]["p50"],
-                                     "health_poll": r["health_poll_us"]["p50"]},
-                   "pynvml_twin": pynvml_twin(min(args.steps, 50))},
+                   "value_timing": "host monotonic clock around each cycle inside the C binary",
+                   "phases": reference_phases(r),
+                   "pynvml_twin": pynvml_twin(min(args.steps, 50)),
+                   "host": f"{cpu_model()}, nproc={os.cpu_count()}"},
+        "setup": reference_phases(r)["setup_once_per_start_us"],
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
-                         "sample": f"{args.steps} cycles of oracle/_ref/ref_inventory (reference's nvml_dl.c), "
-                                   f"taskset -c 0, {cpu_model()}, nproc={os.cpu_count()}"},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                         "sample": f"{args.steps} cycles (+{args.warmup} warm-up) of oracle/_ref/ref_inventory (reference's "
+                                   f"nvml_dl.c) over {n} GPU(s), taskset -c 0, {cpu_model()}, nproc={os.cpu_count()}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "p50_value": n * 1e6 / r["cycle_us"]["p50"], "p50_ms_per_step": r["cycle_us"]["p50"] / 1e3 / max(n, 1)},
         "gpu_launches": 0,
     }
     if not args.no_allocate and int(os.environ.get("WORLD_SIZE", 1)) == 1:  # host-only leg: N = 1 runs only
         try:
             line["allocate"] = bench_allocate("reference", args.quick_allocate)
+            line["allocate"]["note"] = ("this arm is the behaviour-faithful Python port (oracle/ref_plugin.py: global lock across "
+                                        "I/O, LIST per call, Python codec, synchronous log lines); the language-fair row is our "
+                                        "arm's allocate.compiled_reference_behaviour")
         except Exception as e:  # noqa: BLE001
             line["allocate"] = {"error": str(e)}
     print(json.dumps(line))
 
 
+def pctl(sorted_ns, q):
+    return sorted_ns[min(len(sorted_ns) - 1, int(q * len(sorted_ns)))]
+
+
 def timed_cycles(cyc, steps: int, warmup: int, dist, local):
+    """W warm-up steps, then exactly `steps` steps bracketed by barrier + synchronize; per-step host times kept."""
     for _ in range(warmup):
         cyc.step()
     barrier_sync(dist, local)
-    kernel_ns, inv_ns, launches = 0, 0, 0
+    kernel_ns, inv_ns = 0, 0
     per_step = []
     t0 = time.perf_counter_ns()
     for _ in range(steps):
@@ -397,68 +442,156 @@ def timed_cycles(cyc, steps: int, warmup: int, dist, local):
             raise RuntimeError(f"probe reported {r.probe.mismatch_words} mismatching words — unhealthy device")
         kernel_ns += r.probe.kernel_ns
         inv_ns += r.inventory_ns
-        launches += 1
     barrier_sync(dist, local)
     wall_ns = time.perf_counter_ns() - t0
     per_step.sort()
-    timed_cycles.last_percentiles = {"p50_ms": per_step[len(per_step) // 2] / 1e6,
-                                     "p99_ms": per_step[min(len(per_step) - 1, int(0.99 * len(per_step)))] / 1e6}
-    return wall_ns, kernel_ns, inv_ns, launches, r
+    return {"wall_ns": wall_ns, "kernel_ns": kernel_ns, "inventory_ns": inv_ns, "launches": steps, "last": r,
+            "p50_ms": pctl(per_step, 0.5) / 1e6, "p99_ms": pctl(per_step, 0.99) / 1e6, "max_ms": per_step[-1] / 1e6}
+
+
+def node_cycle_leg(device, n: int, steps: int, warmup: int, window: int) -> dict:
+    """ONE process, all n devices through gsb_cycle_all (one persistent native thread, primary context and
+    non-blocking stream per device; one joined ListAndWatchResponse) — what the daemon does, and what replaces the
+    reference's sequential loop nvidia.go:59-86. Arena per device: 8 windows (each 1 GiB window >> the 126 MB L2)."""
+    from gpushare_device_plugin_b200 import _abi
+    t0 = time.perf_counter()
+    device.init()
+    arenas = [device.arena_create(i, max_bytes=8 * window, keep_free_bytes=2 * GiB) for i in range(n)]
+    setup_s = time.perf_counter() - t0
+    node = device.NodeCycler(list(range(n)), window_bytes=window)
+    for _ in range(warmup):
+        node.step()
+    per_step, kern, inv = [], [0] * n, [[] for _ in range(n)]
+    t0 = time.perf_counter_ns()
+    for _ in range(steps):
+        ts = time.perf_counter_ns()
+        res = node.step()
+        per_step.append(time.perf_counter_ns() - ts)
+        for i, r in enumerate(res):
+            if not r.healthy:
+                raise RuntimeError(f"node cycle: device {i} unhealthy")
+            kern[i] += r.probe.kernel_ns
+            inv[i].append(r.inventory_ns)
+    wall_ns = time.perf_counter_ns() - t0
+    per_step.sort()
+    out = {"n_gpus": n, "steps": steps, "warmup": warmup, "window_bytes": window, "arena_bytes_per_device": min(arenas),
+           "node_cycles_per_s": steps / (wall_ns / 1e9), "device_cycles_per_s": n * steps / (wall_ns / 1e9),
+           "step_ms": {"min": per_step[0] / 1e6, "p50": pctl(per_step, 0.5) / 1e6, "p99": pctl(per_step, 0.99) / 1e6,
+                       "max": per_step[-1] / 1e6, "mean": wall_ns / 1e6 / steps},
+           "kernel_ms_per_cycle_per_device": [round(k / 1e6 / steps, 4) for k in kern],
+           "inventory_us_p50_per_device": [round(sorted(v)[len(v) // 2] / 1e3, 2) for v in inv],
+           "inventory_us_max_per_device": [round(max(v) / 1e3, 2) for v in inv],
+           "aggregate_hbm_gbs": sum(2 * window * steps / (k / 1e9) / 1e9 for k in kern if k),
+           "lw_bytes": node.lw_len, "devices_advertised": res[0].slices * n,
+           "inventory_policy": "live" if device.get_option(_abi.GSB_OPT_INVENTORY_POLICY) else "snapshot",
+           "setup_s": round(setup_s, 3)}
+    for i in range(n):
+        device.arena_destroy(i)
+    device.shutdown()
+    return out
 
 
 def bench_ours(args) -> None:
     rank, world, local, dist = dist_setup(args.gpus)
+    host_group = None
+    if dist is not None:
+        host_group = dist.new_group(backend="gloo")  # host-side barrier for the node-cycle leg: no kernel parked on a GPU
+    line_cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        # FIRST, before this process owns a CUDA context or any HBM: the same binary, flags and state as
+        # `--impl reference --gpus 1`, so the two numbers agree within host noise
+        try:
+            r = run_reference_cycles(args.cpu_iters, 3, gpus=1)
+            line_cpu = {"value": r["n_gpus"] * 1e6 / r["cycle_us"]["mean"], "unit": UNIT, "cores": 1, "kind": "reference",
+                        "sample": f"{args.cpu_iters} cycles (+3 warm-up) of oracle/_ref/ref_inventory (built with the reference's "
+                                  f"nvml_dl.c) over 1 GPU, before this process created a CUDA context: inventory p50 "
+                                  f"{r['inventory_us']['p50']} us + poll p50 {r['health_poll_us']['p50']} us per cycle; "
+                                  f"set-up once per start {r['health_setup_us']['p50']} us ({r['register_calls_per_setup']} NVML "
+                                  f"calls), not in the cycle; taskset -c 0; no HBM traffic",
+                        "phases": reference_phases(r)}
+        except Exception as e:  # noqa: BLE001
+            line_cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"failed: {e}"}
     from gpushare_device_plugin_b200 import _abi, device
     if dist is not None:  # make NCCL allocate its buffers BEFORE the arena takes all free HBM
         barrier_sync(dist, local)
         allmax(dist, local, 0.0)
+    t_setup = time.perf_counter()
     device.init()
+    init_ms = (time.perf_counter() - t_setup) * 1e3
     n_dev = device.device_count()
     idx = local if world > 1 else 0
     if idx >= n_dev:
         raise RuntimeError(f"rank {rank}: device index {idx} but only {n_dev} GPUs visible")
     keep_free = (2 * GiB) if dist is not None else 0
+    t_arena = time.perf_counter()
     arena = device.arena_create(idx, keep_free_bytes=keep_free)
+    arena_ms = (time.perf_counter() - t_arena) * 1e3
     variant = {"auto": 0, "direct": 1, "cpasync": 2, "bulk": 3, "bulkw": 4, "bulkd": 5}[args.variant]
     peak, peak_src = measured_peak()
     window = args.window_gib * GiB
+    device.set_option(_abi.GSB_OPT_INVENTORY_POLICY, _abi.GSB_INVENTORY_LIVE if args.inventory == "live" else _abi.GSB_INVENTORY_SNAPSHOT)
 
     sampler = ClockSampler(idx)
     sampler.start()
     # ---- headline: steady-state rotating window ------------------------------------------------
     cyc = device.Cycler(idx, window_bytes=window, variant=variant)
-    wall_ns, kernel_ns, inv_ns, launches, last = timed_cycles(cyc, args.steps, args.warmup, dist, local)
-    step_pct = dict(timed_cycles.last_percentiles)
-    # ---- same run: full-arena walk ------------------------------------------------------------------
-    full = device.Cycler(idx, window_bytes=0, variant=variant)
-    f_wall, f_kernel, f_inv, f_launches, f_last = timed_cycles(full, args.full_steps, 3, dist, local)
+    head = timed_cycles(cyc, args.steps, args.warmup, dist, local)
     clocks = sampler.stop()
+    last = head["last"]
+    snapshot_age_ms = last.snapshot_age_ns / 1e6
+    # ---- same run, other legs (each outside the headline's timed region) -----------------------------
+    other = _abi.GSB_INVENTORY_SNAPSHOT if args.inventory == "live" else _abi.GSB_INVENTORY_LIVE
+    device.set_option(_abi.GSB_OPT_INVENTORY_POLICY, other)
+    alt = timed_cycles(cyc, min(args.steps, 100), 3, dist, local)
+    device.set_option(_abi.GSB_OPT_INVENTORY_POLICY, _abi.GSB_INVENTORY_SNAPSHOT)
+    full = device.Cycler(idx, window_bytes=0, variant=variant)
+    fw = timed_cycles(full, args.full_steps, 3, dist, local)
+    device.arena_destroy(idx)
+    tr = None
+    if not args.no_transient:
+        trc = device.Cycler(idx, window_bytes=window, variant=variant)  # no arena: allocate -> fill -> verify -> free
+        tr = timed_cycles(trc, args.transient_steps, 3, dist, local)
 
     if dist is not None:  # every rank sampled its own GPU: report the slowest median and the union of reasons
         allc = [None] * world
-        dist.all_gather_object(allc, clocks)
+        dist.all_gather_object(allc, clocks, group=host_group)
         meds = [c["sm_mhz"] for c in allc if c and c["sm_mhz"] is not None]
         clocks = dict(clocks, sm_mhz=min(meds) if meds else None,
                       reasons=sorted(set(r for c in allc if c for r in c["reasons"])), ranks=world)
-    wall_s = allmax(dist, local, wall_ns / 1e9)
-    kern_s = allmax(dist, local, kernel_ns / 1e9)
-    f_wall_s = allmax(dist, local, f_wall / 1e9)
-    f_kern_s = allmax(dist, local, f_kernel / 1e9)
+    wall_s = allmax(dist, local, head["wall_ns"] / 1e9)
+    kern_s = allmax(dist, local, head["kernel_ns"] / 1e9)
+    p50_s = allmax(dist, local, head["p50_ms"] / 1e3)
+    alt_wall_s = allmax(dist, local, alt["wall_ns"] / 1e9)
+    f_wall_s = allmax(dist, local, fw["wall_ns"] / 1e9)
+    f_kern_s = allmax(dist, local, fw["kernel_ns"] / 1e9)
+    tr_wall_s = allmax(dist, local, tr["wall_ns"] / 1e9) if tr else None
+    device.shutdown()  # arena, streams, NVML released on every rank before the one-process node cycle
+    if dist is not None:
+        dist.barrier(group=host_group)
+    node = None
+    if rank == 0 and not args.no_node_cycle:
+        try:
+            node = node_cycle_leg(device, world, args.node_steps, 5, window)
+        except Exception as e:  # noqa: BLE001
+            node = {"error": str(e)[-300:]}
+    if dist is not None:
+        dist.barrier(group=host_group)
     if rank != 0:
-        device.shutdown()
         return
 
     units = args.steps * world
     f_units = args.full_steps * world
-    achieved = 2 * window * args.steps / (kernel_ns / 1e9) / 1e9  # this rank's kernel, GB/s
-    f_achieved = 2 * arena * args.full_steps / (f_kernel / 1e9) / 1e9
+    achieved = 2 * window * args.steps / (head["kernel_ns"] / 1e9) / 1e9  # this rank's kernel, GB/s
+    f_achieved = 2 * arena * args.full_steps / (fw["kernel_ns"] / 1e9) / 1e9
     prof = {}
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             prof = json.load(f)
     except Exception:
         pass
+    traffic_src = "profiles/ncu_traffic.json: dram__bytes_read+write of this kernel from an `ncu --set full` capture of the same launch shape; NOT measured in this run"
     kname = {1: "probe_direct", 2: "probe_cpasync", 3: "probe_bulk", 4: "probe_bulk_warp", 5: "probe_bulk_dyn"}[last.probe.variant]
+    alt_name = "snapshot" if args.inventory == "live" else "live_nvml"
     line = {
         "metric": METRIC, "value": units / kern_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": kern_s * 1e3 / args.steps, "higher_is_better": True,
@@ -468,45 +601,64 @@ def bench_ours(args) -> None:
                                 f"rotating {args.window_gib} GiB window (one advertised slice) over the whole arena",
                    "window_bytes": window, "arena_bytes": arena, "variant": _abi.VARIANT_NAMES[last.probe.variant],
                    "grid_ctas": last.probe.grid_ctas, "block_threads": last.probe.block_threads,
+                   "inventory_policy": args.inventory,
                    "l2_policy": "inputs larger than L2: the window rotates over the whole arena, no flush needed",
-                   "value_timing": "CUDA events around each probe launch, on the launching stream (inside gsb_probe)",
+                   "value_timing": "`value` = CUDA events around each probe launch on the launching stream (inside gsb_probe): the "
+                                   "KERNEL ONLY. It excludes the inventory step, the encode and every host cost, so value / "
+                                   "reference.value is not a speed-up; `e2e` (host wall time around the C-ABI call) is the "
+                                   "like-for-like figure",
                    "replicas": "one independent replica per GPU, no collective (path does not shard)",
                    "host": f"{cpu_model()}, nproc={os.cpu_count()}"},
         "e2e": {"value": units / wall_s, "unit": UNIT, "ms_per_step": wall_s * 1e3 / args.steps,
+                "p50_value": world / p50_s, "p50_ms_per_step": p50_s * 1e3,
                 "h2d_bytes_per_step": 120, "d2h_bytes_per_step": 56,
-                "note": "gsb_cycle through ctypes: NVML+driver queries, encode, launch, stream sync; h2d = kernel "
-                        "argument block, d2h = gsb_kernel_out written by the last CTA into pinned mapped host memory; "
-                        "the ListAndWatch bytes are produced on the host",
-                "inventory_us_per_step": inv_ns / 1e3 / args.steps,
-                "per_step_rank0": step_pct,
-                "noise_note": "value = steps / total wall (a mean). The per-cycle NVML memory query runs while the kernel "
-                              "walks and is hidden up to the kernel's duration; other tenants hammering NVML on a shared "
-                              "host add rare multi-ms driver-lock stalls that lift the mean but not p50 "
-                              "(profiles/cycle_order_r01.txt)"},
-        "gpu_launches": launches + f_launches,
+                "note": "gsb_cycle through ctypes: identity check against the CUDA driver, slices, encode, launch, completion "
+                        "wait; h2d = kernel argument block, d2h = gsb_kernel_out written by the last CTA into pinned mapped "
+                        "host memory; the ListAndWatch bytes are produced on the host. value = steps / total wall (mean); "
+                        "p50_value = from the median step (max over ranks)",
+                "inventory_us_per_step": head["inventory_ns"] / 1e3 / args.steps,
+                "inventory_source": ("NVML queried inside every cycle" if args.inventory == "live" else
+                                     f"NVML's answer from gsb_init (age {snapshot_age_ms:.0f} ms at the last step), identity "
+                                     "re-validated per cycle via cuDeviceGetUuid; the reference also asks NVML once per start"),
+                "per_step_rank0": {"p50_ms": head["p50_ms"], "p99_ms": head["p99_ms"], "max_ms": head["max_ms"]}},
+        "gpu_launches": head["launches"] * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": prof.get("window_1gib_dram_bytes_per_launch"), "kernel": kname + "<VERIFY_REFILL>",
+                     "traffic": prof.get("window_1gib_dram_bytes_per_launch"), "traffic_source": traffic_src,
+                     "kernel": kname + "<VERIFY_REFILL>",
                      "algorithmic_bytes_per_launch": 2 * window, "peak_source": peak_src},
+        "setup": {"once_per_start_ms": {"gsb_init (dlopen, nvmlInit, cuInit, first NVML inventory)": round(init_ms, 1),
+                                        "arena (VMM map of all allocatable HBM + FILL of every byte)": round(arena_ms, 1)},
+                  "note": "not in any timed cycle; the reference arm reports its own once-per-start work the same way"},
+        alt_name: {"e2e_value": min(args.steps, 100) * world / alt_wall_s, "unit": UNIT, "steps": min(args.steps, 100),
+                   "inventory_us_per_step": alt["inventory_ns"] / 1e3 / min(args.steps, 100),
+                   "per_step_rank0": {"p50_ms": alt["p50_ms"], "p99_ms": alt["p99_ms"], "max_ms": alt["max_ms"]},
+                   "what": "the same cycle with the other inventory policy (live = a fresh NVML UUID/minor/MemoryInfo query "
+                           "inside every cycle, the round-1 behaviour)"},
         "full_walk": {"value": f_units / f_kern_s, "unit": UNIT, "steps": args.full_steps,
                       "ms_per_step": f_kern_s * 1e3 / args.full_steps,
                       "e2e": {"value": f_units / f_wall_s, "unit": UNIT, "ms_per_step": f_wall_s * 1e3 / args.full_steps},
                       "window_bytes": arena,
                       "roofline": {"bound": "hbm", "achieved": f_achieved, "peak": peak, "unit": "GB/s",
                                    "frac": f_achieved / peak, "traffic": prof.get("full_walk_dram_bytes_per_launch"),
-                                   "algorithmic_bytes_per_launch": 2 * arena}},
+                                   "traffic_source": traffic_src, "algorithmic_bytes_per_launch": 2 * arena}},
         "clocks": clocks,
     }
-    if world == 1 and not args.no_cpu_baseline:
-        try:
-            r = run_reference_cycles(args.cpu_iters, 3)
-            line["cpu_baseline"] = {
-                "value": r["n_gpus"] * 1e6 / r["cycle_us"]["mean"], "unit": UNIT, "cores": 1, "kind": "reference",
-                "sample": f"{args.cpu_iters} cycles of oracle/_ref/ref_inventory (built with the reference's nvml_dl.c): "
-                          f"inventory p50 {r['inventory_us']['p50']} us + health set-up p50 {r['health_setup_us']['p50']} us "
-                          f"({r['register_calls_per_cycle']} NVML calls) + poll p50 {r['health_poll_us']['p50']} us; "
-                          f"taskset -c 0; no HBM traffic"}
-        except Exception as e:  # noqa: BLE001
-            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"failed: {e}"}
+    if tr:
+        tl = tr["last"]
+        line["transient"] = {
+            "e2e_value": args.transient_steps * world / tr_wall_s, "unit": UNIT, "steps": args.transient_steps,
+            "ms_per_step": tr_wall_s * 1e3 / args.transient_steps, "kernel_ms_per_step": tr["kernel_ns"] / 1e6 / args.transient_steps,
+            "per_step_rank0": {"p50_ms": tr["p50_ms"], "p99_ms": tr["p99_ms"], "max_ms": tr["max_ms"]},
+            "bytes_walked": tl.probe.bytes_walked, "transient_flag": tl.transient,
+            "what": "no standing arena (the daemon's default): per cycle cuMemCreate + map of one window, FILL, VERIFY, unmap + "
+                    "release; HBM traffic 2*W like VERIFY_REFILL; between cycles the plugin holds no HBM beyond its context"}
+    if node is not None:
+        line["node_cycle"] = node
+        if "step_ms" in node:
+            node["vs_single_gpu_cycle"] = {"single_gpu_e2e_p50_ms": head["p50_ms"],
+                                           "node_p50_over_single_p50": node["step_ms"]["p50"] / head["p50_ms"]}
+    if line_cpu is not None:
+        line["cpu_baseline"] = line_cpu
     if world == 1 and not args.no_allocate:
         try:
             line["allocate"] = bench_allocate("ours", args.quick_allocate)
@@ -514,7 +666,6 @@ def bench_ours(args) -> None:
         except Exception as e:  # noqa: BLE001
             line["allocate"] = {"error": str(e)}
     print(json.dumps(line))
-    device.shutdown()
 
 
 def main():
@@ -528,6 +679,12 @@ def main():
     ap.add_argument("--variant", default="auto", choices=["auto", "direct", "cpasync", "bulk", "bulkw", "bulkd"])
     ap.add_argument("--cpu-iters", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inventory", default="snapshot", choices=["snapshot", "live"],
+                    help="headline cycle's inventory policy (the other one is measured as a side leg)")
+    ap.add_argument("--transient-steps", type=int, default=20)
+    ap.add_argument("--no-transient", action="store_true")
+    ap.add_argument("--node-steps", type=int, default=200)
+    ap.add_argument("--no-node-cycle", action="store_true")
     ap.add_argument("--no-allocate", action="store_true")
     ap.add_argument("--quick-allocate", action="store_true")
     ap.add_argument("--allocate-only", action="store_true", help="host-only: print just the Allocate() leg")

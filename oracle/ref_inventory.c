@@ -26,8 +26,12 @@
  * it flatters the reference.
  *
  * Usage:
- *   ref_inventory inventory [--unit GiB|MiB] [--lw-out FILE]     one pass, JSON on stdout
- *   ref_inventory bench --iters K [--wait-ms T] [--unit GiB]     K timed cycles, JSON on stdout
+ *   ref_inventory inventory [--unit GiB|MiB] [--lw-out FILE] [--gpus N]   one pass, JSON on stdout
+ *   ref_inventory bench --iters K [--warmup W] [--wait-ms T] [--unit GiB] [--gpus N] [--setup-iters M]
+ *       phases as the reference runs them: health SET-UP once per plugin start (NewEventSet + one
+ *       RegisterEventForDevice per FAKE device, nvidia.go:101-117), then K timed cycles of
+ *       inventory (getDevices + marshal) + one health poll (WaitForEvent on the standing event set). JSON on stdout.
+ *   --gpus N: behave as on a node with only the first N GPUs (GetCount is capped to N everywhere it is asked).
  */
 #define _GNU_SOURCE
 #include <ctype.h>
@@ -40,6 +44,15 @@
 #include "nvml_dl.h" /* the reference's header (includes its vendored nvml.h, API v9) */
 
 #define MAX_GPUS 64
+
+static unsigned g_gpu_limit = 0; /* --gpus N: 0 = every GPU NVML reports */
+
+/* nvmlDeviceGetCount as a node with --gpus N devices would answer it */
+static nvmlReturn_t device_count(unsigned *n) {
+  nvmlReturn_t r = nvmlDeviceGetCount(n);
+  if (r == NVML_SUCCESS && g_gpu_limit && *n > g_gpu_limit) *n = g_gpu_limit;
+  return r;
+}
 
 typedef struct {
   char uuid[NVML_DEVICE_UUID_BUFFER_SIZE];
@@ -128,7 +141,7 @@ typedef struct {
 /* getDevices (nvidia.go:53-89) */
 static void get_devices(int unit_gib, ref_device *devs, unsigned *n_out, ref_devs *out) {
   unsigned n = 0;
-  nvmlReturn_t r = nvmlDeviceGetCount(&n);
+  nvmlReturn_t r = device_count(&n);
   if (r != NVML_SUCCESS) die("GetCount", r);
   if (n > MAX_GPUS) n = MAX_GPUS;
   out->ids = NULL;
@@ -215,7 +228,7 @@ static uint8_t *marshal_lw(const ref_devs *d, size_t *len) {
 /* RegisterEventForDevice (bindings.go:97-128) */
 static nvmlReturn_t register_event_for_device(nvmlEventSet_t set, const char *uuid, unsigned long *calls) {
   unsigned n = 0;
-  nvmlReturn_t r = nvmlDeviceGetCount(&n);
+  nvmlReturn_t r = device_count(&n);
   (*calls)++;
   if (r != NVML_SUCCESS) return r;
   for (unsigned i = 0; i < n; i++) {
@@ -255,7 +268,7 @@ static double pct(double *v, int n, double q) {
 /* entry point of libref_inventory.so; oracle/ref_launcher.c dlopen()s it (see Makefile for why) */
 int ref_main(int argc, char **argv) {
   const char *mode = argc > 1 ? argv[1] : "inventory";
-  int unit_gib = 1, iters = 30;
+  int unit_gib = 1, iters = 30, setup_iters = 1, warmup = 0;
   unsigned wait_ms = 0;
   const char *lw_out = NULL;
   for (int i = 2; i < argc; i++) {
@@ -263,6 +276,9 @@ int ref_main(int argc, char **argv) {
     else if (!strcmp(argv[i], "--iters") && i + 1 < argc) iters = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--wait-ms") && i + 1 < argc) wait_ms = (unsigned)atoi(argv[++i]);
     else if (!strcmp(argv[i], "--lw-out") && i + 1 < argc) lw_out = argv[++i];
+    else if (!strcmp(argv[i], "--gpus") && i + 1 < argc) g_gpu_limit = (unsigned)atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--setup-iters") && i + 1 < argc) setup_iters = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--warmup") && i + 1 < argc) warmup = atoi(argv[++i]);
   }
 
   double t0 = now_us();
@@ -300,21 +316,26 @@ int ref_main(int argc, char **argv) {
     free_devs(&fan);
   } else if (!strcmp(mode, "bench")) {
     if (iters < 1) iters = 1;
-    double *t_inv = malloc(sizeof(double) * iters), *t_reg = malloc(sizeof(double) * iters),
-           *t_wait = malloc(sizeof(double) * iters), *t_cyc = malloc(sizeof(double) * iters);
+    if (setup_iters < 1) setup_iters = 1;
+    double *t_inv = malloc(sizeof(double) * iters), *t_wait = malloc(sizeof(double) * iters),
+           *t_cyc = malloc(sizeof(double) * iters), *t_reg = malloc(sizeof(double) * setup_iters);
     unsigned long reg_calls = 0;
     int reg_rc = 0, wait_rc = 0;
     size_t n_dev = 0, lw_len = 0;
-    for (int it = 0; it < iters; it++) {
-      double a = now_us();
-      /* (i) inventory: getDevices + marshal of the first ListAndWatch send */
+    /* ---- set-up, once per plugin start: the first getDevices (server.go:39) and watchXIDs' registration loop,
+     *      once per FAKE device (nvidia.go:101-117). Repeated --setup-iters times only to get a distribution; the
+     *      event set of the last repetition stays registered for the timed cycles. ---- */
+    nvmlEventSet_t set;
+    int have_set = 0;
+    double first_inventory_us = 0;
+    for (int si = 0; si < setup_iters; si++) {
+      double a0 = now_us();
       get_devices(unit_gib, devs, &n, &fan);
-      size_t len = 0;
-      uint8_t *lw = marshal_lw(&fan, &len);
+      if (si == 0) first_inventory_us = now_us() - a0;
+      if (have_set) nvmlEventSetFree(set);
       double b = now_us();
-      /* (ii) health set-up: watchXIDs' registration loop, once per FAKE device (nvidia.go:104-117) */
-      nvmlEventSet_t set;
       nvmlEventSetCreate(&set);
+      have_set = 1;
       reg_calls = 0;
       for (size_t i = 0; i < fan.n; i++) {
         char real[NVML_DEVICE_UUID_BUFFER_SIZE];
@@ -325,8 +346,18 @@ int ref_main(int argc, char **argv) {
         nvmlReturn_t rr = register_event_for_device(set, real, &reg_calls);
         if (rr != NVML_SUCCESS) reg_rc = (int)rr;
       }
-      double c = now_us();
-      /* (iii) one health poll: WaitForEvent(set, wait_ms) incl. its trailing GetUUID (bindings.go:134-146) */
+      t_reg[si] = now_us() - b;
+      free_devs(&fan);
+    }
+    /* ---- steady state: K cycles of inventory + one health poll on the standing event set ---- */
+    for (int it = -warmup; it < iters; it++) { /* it < 0: untimed warm-up cycles */
+      double a = now_us();
+      /* (i) inventory: getDevices + marshal of the ListAndWatch send */
+      get_devices(unit_gib, devs, &n, &fan);
+      size_t len = 0;
+      uint8_t *lw = marshal_lw(&fan, &len);
+      double b = now_us();
+      /* (ii) one health poll: WaitForEvent(set, wait_ms) incl. its trailing GetUUID (bindings.go:134-146) */
       nvmlEventData_t data;
       memset(&data, 0, sizeof data);
       nvmlReturn_t wr = nvmlEventSetWait(set, &data, wait_ms);
@@ -335,33 +366,40 @@ int ref_main(int argc, char **argv) {
         char u[NVML_DEVICE_UUID_BUFFER_SIZE];
         nvmlDeviceGetUUID(data.device, u, sizeof u);
       }
-      nvmlEventSetFree(set);
       double d = now_us();
-      t_inv[it] = b - a;
-      t_reg[it] = c - b;
-      t_wait[it] = d - c;
-      t_cyc[it] = d - a;
+      if (it >= 0) {
+        t_inv[it] = b - a;
+        t_wait[it] = d - b;
+        t_cyc[it] = d - a;
+      }
       n_dev = fan.n;
       lw_len = len;
       free(lw);
       free_devs(&fan);
     }
-    double sum = 0;
-    for (int i = 0; i < iters; i++) sum += t_cyc[i];
+    nvmlEventSetFree(set);
+    double sum = 0, sum_inv = 0, sum_wait = 0;
+    for (int i = 0; i < iters; i++) {
+      sum += t_cyc[i];
+      sum_inv += t_inv[i];
+      sum_wait += t_wait[i];
+    }
     qsort(t_inv, iters, sizeof(double), cmp_double);
-    qsort(t_reg, iters, sizeof(double), cmp_double);
+    qsort(t_reg, setup_iters, sizeof(double), cmp_double);
     qsort(t_wait, iters, sizeof(double), cmp_double);
     qsort(t_cyc, iters, sizeof(double), cmp_double);
-    printf("{\"mode\":\"bench\",\"iters\":%d,\"n_gpus\":%u,\"n_devices\":%zu,\"lw_len\":%zu,\"wait_ms\":%u,"
-           "\"nvml_init_us\":%.1f,\"register_calls_per_cycle\":%lu,\"register_rc\":%d,\"wait_rc\":%d,"
-           "\"inventory_us\":{\"p10\":%.1f,\"p50\":%.1f,\"p90\":%.1f},"
+    printf("{\"mode\":\"bench\",\"iters\":%d,\"setup_iters\":%d,\"n_gpus\":%u,\"gpu_limit\":%u,\"n_devices\":%zu,"
+           "\"lw_len\":%zu,\"wait_ms\":%u,"
+           "\"nvml_init_us\":%.1f,\"first_inventory_us\":%.1f,\"register_calls_per_setup\":%lu,\"register_rc\":%d,\"wait_rc\":%d,"
+           "\"inventory_us\":{\"p10\":%.1f,\"p50\":%.1f,\"p90\":%.1f,\"mean\":%.1f},"
            "\"health_setup_us\":{\"p10\":%.1f,\"p50\":%.1f,\"p90\":%.1f},"
-           "\"health_poll_us\":{\"p10\":%.1f,\"p50\":%.1f,\"p90\":%.1f},"
-           "\"cycle_us\":{\"p10\":%.1f,\"p50\":%.1f,\"p90\":%.1f,\"mean\":%.1f},\"total_us\":%.1f}\n",
-           iters, n, n_dev, lw_len, wait_ms, init_us, reg_calls, reg_rc, wait_rc, pct(t_inv, iters, .1),
-           pct(t_inv, iters, .5), pct(t_inv, iters, .9), pct(t_reg, iters, .1), pct(t_reg, iters, .5),
-           pct(t_reg, iters, .9), pct(t_wait, iters, .1), pct(t_wait, iters, .5), pct(t_wait, iters, .9),
-           pct(t_cyc, iters, .1), pct(t_cyc, iters, .5), pct(t_cyc, iters, .9), sum / iters, sum);
+           "\"health_poll_us\":{\"p10\":%.1f,\"p50\":%.1f,\"p90\":%.1f,\"mean\":%.1f},"
+           "\"cycle_us\":{\"p10\":%.1f,\"p50\":%.1f,\"p90\":%.1f,\"p99\":%.1f,\"mean\":%.1f},\"total_us\":%.1f}\n",
+           iters, setup_iters, n, g_gpu_limit, n_dev, lw_len, wait_ms, init_us, first_inventory_us, reg_calls, reg_rc, wait_rc,
+           pct(t_inv, iters, .1), pct(t_inv, iters, .5), pct(t_inv, iters, .9), sum_inv / iters,
+           pct(t_reg, setup_iters, .1), pct(t_reg, setup_iters, .5), pct(t_reg, setup_iters, .9),
+           pct(t_wait, iters, .1), pct(t_wait, iters, .5), pct(t_wait, iters, .9), sum_wait / iters,
+           pct(t_cyc, iters, .1), pct(t_cyc, iters, .5), pct(t_cyc, iters, .9), pct(t_cyc, iters, .99), sum / iters, sum);
   } else {
     fprintf(stderr, "unknown mode %s\n", mode);
     return 2;

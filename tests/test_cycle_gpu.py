@@ -109,8 +109,16 @@ def test_cycle_flags_corruption_and_unhealthy_is_sticky(gsb, full_arena):
     gsb.init()
 
 
-def test_probe_all_one_thread_per_device(gsb):
+def need_gpus(gsb, k):
     n = gsb.device_count()
+    if n < k:
+        pytest.skip(f"needs >= {k} GPUs in one process, this box has {n} (run under gpurun --gpus {k})")
+    return n
+
+
+@pytest.mark.parametrize("multi", [False, True], ids=["one-device", "all-devices"])
+def test_probe_all_one_thread_per_device(gsb, multi):
+    n = need_gpus(gsb, 2) if multi else 1
     for i in range(n):
         gsb.arena_create(i, max_bytes=2 * GiB)
     gsb.probe_all(list(range(n)), _abi.GSB_OP_FILL, seed_write=1)
@@ -120,10 +128,12 @@ def test_probe_all_one_thread_per_device(gsb):
         gsb.arena_destroy(i)
 
 
-def test_node_cycle_all_devices_in_one_process(gsb):
+@pytest.mark.parametrize("multi", [False, True], ids=["one-device", "all-devices"])
+def test_node_cycle_all_devices_in_one_process(gsb, multi):
     """gsb_cycle_all: every GPU of the box probed concurrently (own thread/context/stream), one joined
-    ListAndWatchResponse — equal to the reference's sequential getDevices + marshal."""
-    n = gsb.device_count()
+    ListAndWatchResponse — equal to the reference's sequential getDevices + marshal. The all-devices case needs a
+    multi-GPU box and SKIPS on a 1-GPU one (it used to pass there vacuously with n == 1)."""
+    n = need_gpus(gsb, 2) if multi else 1
     for i in range(n):
         gsb.arena_create(i, max_bytes=4 * GiB)
     infos = [gsb.device_info(i) for i in range(n)]
@@ -142,6 +152,15 @@ def test_node_cycle_all_devices_in_one_process(gsb):
     devs = wo.unmarshal_ListAndWatchResponse(node.list_and_watch_bytes())
     bad = {wo.extractRealDeviceID(i) for i, h in devs if h == wo.Unhealthy}
     assert bad == {infos[victim].uuid} and len(devs) == 179 * n
+    # sticky in the node cycle too (server.go:180): the next windows are clean, the GPU stays Unhealthy; and the
+    # fake devices of the other GPUs never flip (nvidia.go:146-150)
+    res = node.step()
+    assert res[victim].probe.mismatch_words == 0 and [r.healthy for r in res] == [1] * (n - 1) + [0]
+    devs = wo.unmarshal_ListAndWatchResponse(node.list_and_watch_bytes())
+    assert {wo.extractRealDeviceID(i) for i, h in devs if h == wo.Unhealthy} == {infos[victim].uuid}
+    # a device listed twice is refused, not raced
+    with pytest.raises(_abi.GsbError):
+        gsb.NodeCycler([0, 0], window_bytes=GiB).step()
     for i in range(n):
         gsb.arena_destroy(i)
     gsb.shutdown()

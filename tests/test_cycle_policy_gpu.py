@@ -1,0 +1,145 @@
+"""Round-2 behaviour of the cycle on a real B200, through the C ABI: the inventory snapshot (NVML asked at
+(re)start, identity re-validated per cycle on the CUDA side), the transient probe window (allocate -> fill ->
+verify -> free: nothing held between cycles), and the completion watchdog (a launch that never finishes must not
+keep the GPU Healthy)."""
+import time
+
+import pytest
+
+from oracle import wire_oracle as wo
+
+pytestmark = pytest.mark.gpu
+
+from gpushare_device_plugin_b200 import _abi  # noqa: E402
+
+GiB = 1 << 30
+
+
+def nvml_free(idx=0):
+    import pynvml
+    pynvml.nvmlInit()
+    return pynvml.nvmlDeviceGetMemoryInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).free
+
+
+def test_snapshot_cycle_serves_the_reference_inventory_without_asking_nvml(gsb):
+    gsb.arena_create(0, max_bytes=4 * GiB)
+    live = gsb.device_info(0)  # a live NVML query; also rewrites the snapshot
+    snap, age = gsb.inventory_snapshot(0)
+    assert (snap.uuid, snap.minor, snap.total_bytes, snap.total_mib, snap.bus_id) == \
+        (live.uuid, live.minor, live.total_bytes, live.total_mib, live.bus_id) and age < 5e9
+    assert gsb.get_option(_abi.GSB_OPT_INVENTORY_POLICY) == _abi.GSB_INVENTORY_SNAPSHOT
+    cyc = gsb.Cycler(0, window_bytes=GiB)
+    want = wo.marshal_ListAndWatchResponse(wo.getDevices(
+        [{"uuid": live.uuid, "path": f"/dev/nvidia{live.minor}", "memory_mib": live.total_mib}])[0])
+    inv = []
+    for _ in range(20):
+        r = cyc.step()
+        assert r.healthy == 1 and r.inventory_live == 0 and r.transient == 0 and r.snapshot_age_ns > 0
+        assert (r.info.uuid.decode(), r.info.minor, r.info.total_bytes, r.slices) == (live.uuid, live.minor, live.total_bytes, 179)
+        assert cyc.list_and_watch_bytes() == want  # byte-identical to the reference's list, from the snapshot
+        inv.append(r.inventory_ns)
+    assert sorted(inv)[len(inv) // 2] < 100_000  # no driver round trip on the cycle's path (was 6 us .. 2.3 ms)
+    # the same cycle with the round-1 policy asks NVML itself and agrees bit for bit
+    gsb.set_option(_abi.GSB_OPT_INVENTORY_POLICY, _abi.GSB_INVENTORY_LIVE)
+    try:
+        r = cyc.step()
+        assert r.inventory_live == 1 and r.info.total_bytes == live.total_bytes and cyc.list_and_watch_bytes() == want
+    finally:
+        gsb.set_option(_abi.GSB_OPT_INVENTORY_POLICY, _abi.GSB_INVENTORY_SNAPSHOT)
+    # refresh: the snapshot gets younger, the answer stays
+    time.sleep(0.05)
+    _, age1 = gsb.inventory_snapshot(0)
+    gsb.inventory_refresh()
+    snap2, age2 = gsb.inventory_snapshot(0)
+    assert age2 < age1 and snap2.total_bytes == live.total_bytes and snap2.free_bytes < live.total_bytes
+    gsb.arena_destroy(0)
+
+
+def test_transient_window_holds_nothing_between_cycles(gsb):
+    with pytest.raises(_abi.GsbError):
+        gsb.arena_bytes(0)  # no standing arena
+    free0 = nvml_free()
+    cyc = gsb.Cycler(0, window_bytes=GiB)
+    live = gsb.device_info(0)
+    want = wo.marshal_ListAndWatchResponse(wo.getDevices(
+        [{"uuid": live.uuid, "path": f"/dev/nvidia{live.minor}", "memory_mib": live.total_mib}])[0])
+    for _ in range(5):
+        r = cyc.step()
+        assert r.healthy == 1 and r.transient == 1 and r.slices == 179 and cyc.list_and_watch_bytes() == want
+        assert r.probe.status == 0 and r.probe.mismatch_words == 0
+        assert (r.probe.bytes_walked, r.probe.bytes_read, r.probe.bytes_written) == (GiB, GiB, GiB)
+        assert r.probe.kernel_ns > 0
+        with pytest.raises(_abi.GsbError):
+            gsb.arena_bytes(0)  # given back
+    assert abs(nvml_free() - free0) < 64 << 20  # and NVML agrees: the window is not held
+
+
+def test_transient_window_with_nothing_allocatable_is_silence_not_a_fault(gsb):
+    gsb.set_option(_abi.GSB_OPT_TRANSIENT_KEEP_FREE_BYTES, 1 << 50)  # "tenants hold everything"
+    try:
+        cyc = gsb.Cycler(0, window_bytes=GiB)
+        r = cyc.step()
+        assert cyc.rc == 0 and r.healthy == 1 and r.transient == 1 and r.slices == 179
+        assert r.probe.status == _abi.GSB_ERR_OUT_OF_MEMORY and r.probe.bytes_walked == 0
+        assert len(wo.unmarshal_ListAndWatchResponse(cyc.list_and_watch_bytes())) == 179
+    finally:
+        gsb.set_option(_abi.GSB_OPT_TRANSIENT_KEEP_FREE_BYTES, GiB)
+
+
+def test_prober_runs_transient_windows_silently_and_releases_them(gsb):
+    free0 = nvml_free()
+    gsb.health_start(probe_period_ms=10, window_bytes=GiB)
+    try:
+        assert gsb.health_wait(1000) is None  # clean transient windows: no event
+    finally:
+        gsb.health_stop()
+    assert abs(nvml_free() - free0) < 64 << 20
+
+
+def test_watchdog_turns_a_launch_that_never_finishes_into_a_verdict(gsb):
+    """A stalled stream stands in for a wedged GPU: the probe queued behind it cannot finish inside the watchdog, so
+    the cycle returns GSB_ERR_TIMEOUT with healthy == 0 instead of parking the thread in cudaStreamSynchronize; while
+    the stall lasts nothing more is queued; once the stream drains the device probes clean again."""
+    assert gsb.get_option(_abi.GSB_OPT_WATCHDOG_MS) == 2000  # on by default
+    gsb.arena_create(0, max_bytes=2 * GiB)
+    cyc = gsb.Cycler(0, window_bytes=GiB)
+    assert cyc.step().healthy == 1
+    gsb.set_option(_abi.GSB_OPT_WATCHDOG_MS, 100)
+    try:
+        gsb.test_stall(0, 1500)
+        t0 = time.monotonic()
+        r = cyc.step(raise_on_error=False)
+        took = time.monotonic() - t0
+        assert cyc.rc == _abi.GSB_ERR_TIMEOUT and r.healthy == 0 and r.probe.status == _abi.GSB_ERR_TIMEOUT
+        assert 0.09 < took < 0.6, took
+        assert all(h == wo.Unhealthy for _, h in wo.unmarshal_ListAndWatchResponse(cyc.list_and_watch_bytes()))
+        t0 = time.monotonic()
+        r = gsb.probe(0, _abi.GSB_OP_VERIFY, flags=3, raise_on_error=False)  # still stalled: refused at once
+        assert r.status == _abi.GSB_ERR_TIMEOUT and time.monotonic() - t0 < 0.05
+        time.sleep(1.6)  # the stall (and the probe queued behind it) drain
+        r = gsb.probe(0, _abi.GSB_OP_VERIFY, flags=3)
+        assert r.status == 0 and r.mismatch_words == 0 and r.bytes_walked == 2 * GiB
+    finally:
+        gsb.set_option(_abi.GSB_OPT_WATCHDOG_MS, 2000)
+        gsb.arena_destroy(0)
+        gsb.shutdown()  # drop the sticky Unhealthy
+        gsb.init()
+
+
+def test_prober_reports_a_wedged_device(gsb):
+    gsb.arena_create(0, max_bytes=2 * GiB)
+    gsb.set_option(_abi.GSB_OPT_WATCHDOG_MS, 100)
+    gsb.health_start(probe_period_ms=10, window_bytes=GiB)
+    try:
+        assert gsb.health_wait(300) is None
+        gsb.test_stall(0, 1200)
+        ev = gsb.health_wait(3000)
+        assert ev is not None and (ev.etype, ev.edata) == (_abi.GSB_EVENT_PROBE, _abi.GSB_PROBE_FAULT_WEDGED)
+        assert ev.uuid.decode() == gsb.device_info(0).uuid
+        time.sleep(1.3)
+    finally:
+        gsb.health_stop()
+        gsb.set_option(_abi.GSB_OPT_WATCHDOG_MS, 2000)
+        gsb.arena_destroy(0)
+        gsb.shutdown()
+        gsb.init()

@@ -23,8 +23,15 @@ NODE = "b200-0"
 GSBD = os.path.join(ROOT, "gpushare_device_plugin_b200", "gsbd")
 
 
-@pytest.mark.parametrize("front_end", ["python", "native"])
-def test_daemon_end_to_end(tmp_path, front_end):
+# probe memory: a standing 2 GiB arena after a start-up walk of everything allocatable, or the shipped default — no
+# standing arena, one transient window per cycle
+ARENA = ["--probe-arena-mib", "2048", "--startup-full-walk"]
+DEFAULT = []
+
+
+@pytest.mark.parametrize("front_end,probe_flags", [("python", ARENA), ("native", ARENA), ("native", DEFAULT)],
+                         ids=["python-arena", "native-arena", "native-transient-default"])
+def test_daemon_end_to_end(tmp_path, front_end, probe_flags):
     import pynvml
     pynvml.nvmlInit()
     h = pynvml.nvmlDeviceGetHandleByIndex(0)
@@ -42,7 +49,7 @@ def test_daemon_end_to_end(tmp_path, front_end):
     log = open(tmp_path / "daemon.log", "w")
     argv = [sys.executable, "-m", "gpushare_device_plugin_b200.cmd.nvidia"] if front_end == "python" else [GSBD]
     proc = subprocess.Popen(argv + ["-logtostderr", "--v=5", "--memory-unit=GiB", "--health-check", "--token", "t",
-                                    "--probe-period-ms", "100", "--probe-arena-mib", "2048", "--startup-full-walk"],
+                                    "--probe-period-ms", "100"] + probe_flags,
                             env=env, stderr=log, stdout=log, cwd=ROOT)
     try:
         req = kubelet.register_requests.get(timeout=120)
@@ -57,6 +64,9 @@ def test_daemon_end_to_end(tmp_path, front_end):
         assert kube.pod("pod-00")["metadata"]["annotations"]["ALIYUN_COM_GPU_MEM_ASSIGNED"] == "true"
         # the prober has been rotating clean windows for a while: nothing was re-sent
         time.sleep(1.5)
+        if not probe_flags:  # transient default: between cycles the plugin holds no HBM beyond its CUDA context
+            free = [pynvml.nvmlDeviceGetMemoryInfo(h).free for _ in range(5) if time.sleep(0.03) is None]
+            assert max(free) > pynvml.nvmlDeviceGetMemoryInfo(h).total - 3 * (1 << 30), free
         # SIGQUIT -> thread dump file (gpumanager.go:97-101), daemon keeps running
         proc.send_signal(signal.SIGQUIT)
         deadline = time.time() + 10

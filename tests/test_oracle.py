@@ -107,7 +107,18 @@ class TestReferenceRestatement:
         j = json.loads(out.stdout)
         # per fake device: GetCount + (HandleByIndex + GetUUID) x (gpu index + 1) + RegisterEvents
         want = sum(179 * (1 + 2 * (g + 1) + 1) for g in range(8))
-        assert j["register_calls_per_cycle"] == want == 15752
+        assert j["register_calls_per_setup"] == want == 15752
+
+    def test_bench_arm_sees_only_the_gpus_it_is_asked_for(self):
+        """bench.py --impl reference --gpus N must compare N devices with N devices: --gpus caps GetCount everywhere
+        it is asked (getDevices and RegisterEventForDevice's scan), like a node that has N GPUs."""
+        for n, lw in ((1, 10451), (2, 20902), (4, 41804)):
+            j = json.loads(run_ref(["bench", "--iters", "3", "--warmup", "1", "--gpus", str(n)], {"FAKE_NVML_GPUS": "8"}).stdout)
+            assert (j["n_gpus"], j["n_devices"], j["lw_len"]) == (n, 179 * n, lw)
+            assert j["register_calls_per_setup"] == sum(179 * (1 + 2 * (g + 1) + 1) for g in range(n))
+            assert j["cycle_us"]["mean"] > 0 and j["health_setup_us"]["p50"] > 0
+        j = json.loads(run_ref(["inventory", "--gpus", "2"], {"FAKE_NVML_GPUS": "8"}).stdout)
+        assert j["n_gpus"] == 2 and len(j["devices"]) == 2
 
 
 def test_pynvml_twin_of_the_reference_inventory_runs_against_the_fake_nvml():

@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun call's worth of verification + measurement, in the order that matters if the call is cut short.
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'tools/gpu_session.sh r02'            (1 GPU)
-#   /usr/local/graft/bin/gpurun --gpus 8 --timeout 900 -- 'tools/gpu_session.sh r02 node' (8 GPUs: node-level only)
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'tools/gpu_session.sh r02'              (1 GPU)
+#   /usr/local/graft/bin/gpurun --gpus 8 --timeout 900 -- 'tools/gpu_session.sh r02 node' (N GPUs: node-level only)
 # Everything lands under gpurun_out/<tag>/; copy what should be judged into profiles/.
 set -uo pipefail
 TAG=${1:-rXX}
@@ -9,31 +9,46 @@ MODE=${2:-single}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv > $OUT/clocks_before.csv 2>&1
+N=$(nvidia-smi -L | wc -l)
+
+# what the round-end driver does around bench.py: an nvidia-smi sampler polling NVML while the bench runs (this is what
+# made a per-cycle NVML query cost 2.3 ms in BENCH_r01); ours must hold its e2e with it running
+sampler_start() { nvidia-smi --query-gpu=index,clocks.sm,power.draw,utilization.gpu --format=csv,noheader -lms 100 > $OUT/$1 2>&1 & SAMPLER=$!; }
+sampler_stop() { kill $SAMPLER 2>/dev/null; wait $SAMPLER 2>/dev/null; }
+
 if [ "$MODE" = node ]; then
-  N=$(nvidia-smi -L | wc -l)
-  # all GPUs of the box from ONE process (gsb_cycle_all) next to the reference's sequential NVML walk
-  timeout 300 python tools/node_cycle.py > $OUT/node_cycle_${N}gpu.json 2> $OUT/node_cycle_${N}gpu.err
-  # open item of round 1: the in-process node cycle is bimodal at N = 8; spin budget and launch order as knobs
-  for spin in 0 50 400; do
-    GSB_WORKER_SPIN_US=$spin timeout 300 python tools/node_cycle.py > $OUT/node_cycle_${N}gpu_spin$spin.json 2>> $OUT/node_cycle_${N}gpu.err
-  done
-  # hypothesis: the slow mode is a convoy of concurrent NVML queries on the driver's lock -> one query at a time
-  GSB_NVML_SERIAL=1 timeout 300 python tools/node_cycle.py > $OUT/node_cycle_${N}gpu_nvml_serial.json 2>> $OUT/node_cycle_${N}gpu.err
+  # multi-device correctness under one process: the tests that SKIP on a 1-GPU box
+  timeout 600 python -m pytest tests/test_cycle_gpu.py tests/test_daemon_gpu.py -m gpu -x -q -k "probe_all or node_cycle or daemon" -rs \
+    > $OUT/pytest_multi_${N}gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_multi_${N}gpu.log
+  # both arms at N, with the driver-style sampler running, the reference first (as the driver orders them)
+  sampler_start smi_ref_${N}gpu.csv
+  timeout 300 python bench.py --impl reference --gpus $N --steps 20 --warmup 5 --no-allocate > $OUT/bench_reference_${N}gpu.json 2> $OUT/bench_reference_${N}gpu.err
+  sampler_stop
+  sampler_start smi_ours_${N}gpu.csv
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+    bench.py --gpus $N --steps 20 --warmup 5 > $OUT/bench_${N}gpu_sampled.json 2> $OUT/bench_${N}gpu_sampled.err
+  sampler_stop
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
     bench.py --gpus $N --steps 200 --warmup 5 > $OUT/bench_${N}gpu.json 2> $OUT/bench_${N}gpu.err
+  # the round-1 behaviour for contrast: NVML inside every cycle of all N devices of one process
+  GSB_INVENTORY_POLICY=live timeout 300 python tools/node_cycle.py > $OUT/node_cycle_${N}gpu_live.json 2> $OUT/node_cycle_${N}gpu.err
+  timeout 300 python tools/node_cycle.py > $OUT/node_cycle_${N}gpu_snapshot.json 2>> $OUT/node_cycle_${N}gpu.err
+  tail -3 $OUT/pytest_multi_${N}gpu.log
   exit 0
 fi
-timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log
-# the completion watchdog is off by default until this has passed on a GPU: same tests, watchdog on
-GSB_PROBE_WATCHDOG_MS=20000 timeout 600 python -m pytest tests/test_probe_gpu.py tests/test_cycle_gpu.py -m gpu -x -q > $OUT/pytest_gpu_watchdog.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu_watchdog.log
-timeout 400 python bench.py --impl reference --steps 200 --warmup 5 > $OUT/bench_reference_1gpu.json 2> $OUT/bench_reference_1gpu.err
-timeout 400 python bench.py --steps 200 --warmup 5 > $OUT/bench_1gpu.json 2> $OUT/bench_1gpu.err
+timeout 900 python -m pytest tests -m gpu -x -q -rs > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log
+python __graft_entry__.py smoke > $OUT/smoke.log 2>&1
+# the driver's own command lines (steps 20, warmup 5), reference first, each under a driver-style sampler
+sampler_start smi_ref.csv
+timeout 400 python bench.py --impl reference --steps 20 --warmup 5 > $OUT/bench_reference_1gpu_sampled.json 2> $OUT/bench_reference_1gpu.err
+sampler_stop
+sampler_start smi_ours.csv
+timeout 400 python bench.py --steps 20 --warmup 5 > $OUT/bench_1gpu_sampled.json 2> $OUT/bench_1gpu_sampled.err
+sampler_stop
+# longer, quiet run: the numbers DESIGN.md quotes
+timeout 400 python bench.py --steps 200 --warmup 5 --quick-allocate > $OUT/bench_1gpu.json 2> $OUT/bench_1gpu.err
 # launch list of the same command (shares, not absolutes: ncu serialises and runs cold)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
-  python bench.py --steps 20 --warmup 3 --no-allocate > $OUT/bench_under_ncu.log 2>&1
-# one full capture of the shipped refill kernel on a 1 GiB window
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:probe_bulk_dyn -c 2 -o $OUT/ncu_window_dyn \
-  python tools/profile_target.py 5 4 > $OUT/ncu_full.log 2>&1
-timeout 300 python tools/sweep2.py > $OUT/sweep.log 2>&1; cp gpurun_out/sweep2.json $OUT/ 2>/dev/null
+  python bench.py --steps 20 --warmup 3 --no-allocate --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv > $OUT/clocks_after.csv 2>&1
 tail -3 $OUT/pytest_gpu.log

@@ -46,14 +46,14 @@ out = {"n_gpus": n, "steps": steps, "window_bytes": w, "node_cycles_per_s": step
                    "p99": per_step[min(len(per_step) - 1, int(len(per_step) * 0.99))] / 1e6, "max": per_step[-1] / 1e6},
        "inventory_us_p50_per_device": [sorted(v)[len(v) // 2] / 1e3 for v in inv],
        "inventory_us_max_per_device": [max(v) / 1e3 for v in inv],
-       "knobs": {k: os.environ[k] for k in ("GSB_WORKER_SPIN_US", "GSB_NVML_SERIAL", "GSB_CYCLE_ORDER") if k in os.environ},
+       "knobs": {k: os.environ[k] for k in ("GSB_WORKER_SPIN_US", "GSB_NVML_SERIAL", "GSB_CYCLE_ORDER", "GSB_INVENTORY_POLICY") if k in os.environ},
        "cpus_allowed": len(os.sched_getaffinity(0))}
 ref = subprocess.run(["taskset", "-c", "0", os.path.join(ROOT, "oracle", "_ref", "ref_inventory"), "bench", "--iters", "50"],
                      capture_output=True, text=True)
 if ref.returncode == 0:
     r = json.loads(ref.stdout.strip().splitlines()[-1])
-    out["reference_node_cycles_per_s"] = 1e6 / r["cycle_us"]["mean"]
+    out["reference_node_cycles_per_s"] = 1e6 / r["cycle_us"]["mean"]  # inventory + poll; set-up is once per start
     out["reference_phases_us_p50"] = {k: r[k]["p50"] for k in ("inventory_us", "health_setup_us", "health_poll_us")}
-    out["reference_register_calls_per_cycle"] = r["register_calls_per_cycle"]
+    out["reference_register_calls_per_setup"] = r["register_calls_per_setup"]
 print(json.dumps(out))
 device.shutdown()
