@@ -64,7 +64,9 @@ def measured_peak():
 
 
 class ClockSampler:
-    """SM clock + throttle reasons of one GPU sampled DURING the timed region, every 200 ms.
+    """SM clock + throttle reasons of one GPU sampled DURING the timed region: every 10 ms by a thread, plus one
+    explicit sample right after the region starts and one right before it ends (the headline region can be as short
+    as 20 x 0.34 ms; the GPU has been under the same load since the warm-up steps).
 
     Sampled in-process through NVML (two calls per sample: nvmlDeviceGetClockInfo and
     nvmlDeviceGetCurrentClocksEventReasons — the same values `nvidia-smi --query-gpu=clocks.sm,
@@ -74,26 +76,43 @@ class ClockSampler:
     Falls back to nvidia-smi only if pynvml is unusable."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index: int, period_s: float = 0.2):
+    def __init__(self, gpu_index: int, period_s: float = 0.01):
         self.idx, self.period = gpu_index, period_s
         self.sm, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._t = None
         self.source = "nvml"
+        self._nv = None
+        self._lock = threading.Lock()
 
-    def _run_nvml(self):
+    def _nvml_setup(self):
         import pynvml
         pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
-        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
-        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+        self._nv = pynvml
+        self._h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        self._get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
             pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+    def sample_now(self):
+        """One sample from the calling thread (used to bracket the timed region). Never raises."""
+        try:
+            if self._nv is None:
+                self._nvml_setup()
+            with self._lock:
+                self.sm.append(float(self._nv.nvmlDeviceGetClockInfo(self._h, self._nv.NVML_CLOCK_SM)))
+                mask = int(self._get_reasons(self._h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _run_nvml(self):
+        if self._nv is None:
+            self._nvml_setup()
         while not self._stop.is_set():
-            self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-            mask = int(get_reasons(h))
-            for bit, name in self.REASONS.items():
-                if mask & bit:
-                    self.reasons.add(name)
+            self.sample_now()
             self._stop.wait(self.period)
 
     def _run_smi(self):
@@ -115,8 +134,15 @@ class ClockSampler:
             self._stop.wait(self.period)
 
     def start(self):
+        try:
+            self._nvml_setup()
+        except Exception:  # noqa: BLE001
+            self._nv = None
+
         def run():
             try:
+                if self._nv is None:
+                    raise RuntimeError("pynvml unusable")
                 self._run_nvml()
             except Exception:
                 try:
@@ -384,13 +410,15 @@ def bench_reference(args) -> None:
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return  # rank 0 alone runs the (sequential, single-process) reference path
-    r = run_reference_cycles(args.steps, args.warmup, gpus=args.gpus)
+    cps = max(1, args.ref_cycles_per_step)  # one step = a bounded sample of `cps` reference cycles
+    r = run_reference_cycles(args.steps * cps, args.warmup * cps, gpus=args.gpus)
     n = r["n_gpus"]
     mean_us = r["cycle_us"]["mean"]
     value = n * 1e6 / mean_us  # one node cycle covers n devices sequentially
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean_us / 1e3 / max(n, 1),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean_us * cps / 1e3,
+        "ms_per_device_cycle": mean_us / 1e3 / max(n, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": WORKLOAD,
                    "reference_path": f"one cycle = getDevices over the first {n} GPU(s) (11 NVML getters each + fan-out + gogo "
@@ -399,13 +427,16 @@ def bench_reference(args) -> None:
                                      "registration (S*N RegisterEventForDevice, nvidia.go:104-117) is once per plugin start and "
                                      "is reported under setup, outside the timed cycles — as our arm's arena set-up is",
                    "devices_seen": n, "fake_devices": r["n_devices"], "lw_bytes": r["lw_len"],
+                   "cycles_per_step": cps, "cycles_timed": args.steps * cps,
+                   "step": f"one step = a bounded sample of {cps} node cycles (NVML latency on a shared host is too noisy for a "
+                           "20-cycle mean: 2.2 ms idle, 4-7 ms beside a polling nvidia-smi); ms_per_step is the whole sample",
                    "value_timing": "host monotonic clock around each cycle inside the C binary",
                    "phases": reference_phases(r),
                    "pynvml_twin": pynvml_twin(min(args.steps, 50)),
                    "host": f"{cpu_model()}, nproc={os.cpu_count()}"},
         "setup": reference_phases(r)["setup_once_per_start_us"],
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
-                         "sample": f"{args.steps} cycles (+{args.warmup} warm-up) of oracle/_ref/ref_inventory (reference's "
+                         "sample": f"{args.steps * cps} cycles (+{args.warmup * cps} warm-up) of oracle/_ref/ref_inventory (reference's "
                                    f"nvml_dl.c) over {n} GPU(s), taskset -c 0, {cpu_model()}, nproc={os.cpu_count()}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "p50_value": n * 1e6 / r["cycle_us"]["p50"], "p50_ms_per_step": r["cycle_us"]["p50"] / 1e3 / max(n, 1)},
@@ -426,10 +457,17 @@ def pctl(sorted_ns, q):
     return sorted_ns[min(len(sorted_ns) - 1, int(q * len(sorted_ns)))]
 
 
-def timed_cycles(cyc, steps: int, warmup: int, dist, local):
-    """W warm-up steps, then exactly `steps` steps bracketed by barrier + synchronize; per-step host times kept."""
+def timed_cycles(cyc, steps: int, warmup: int, dist, local, sampler=None):
+    """W warm-up steps, then exactly `steps` steps bracketed by barrier + synchronize; per-step host times kept.
+    `sampler` (clocks) runs from before the warm-up to after the last step; the clock samples kept are those taken
+    while the GPU was under this load."""
+    if sampler is not None:
+        sampler.start()
     for _ in range(warmup):
         cyc.step()
+    if sampler is not None:
+        sampler.sm.clear()      # keep only samples taken under load (from the last warm-up step on)
+        sampler.sample_now()
     barrier_sync(dist, local)
     kernel_ns, inv_ns = 0, 0
     per_step = []
@@ -444,6 +482,13 @@ def timed_cycles(cyc, steps: int, warmup: int, dist, local):
         inv_ns += r.inventory_ns
     barrier_sync(dist, local)
     wall_ns = time.perf_counter_ns() - t0
+    if sampler is not None:
+        # the timed region is over (wall_ns is taken): a few more steps of the same load so that even a 7 ms
+        # region is covered by samples taken at this clock/power state
+        t_end = time.perf_counter() + 0.06
+        while time.perf_counter() < t_end:
+            cyc.step()
+            sampler.sample_now()
     per_step.sort()
     return {"wall_ns": wall_ns, "kernel_ns": kernel_ns, "inventory_ns": inv_ns, "launches": steps, "last": r,
             "p50_ms": pctl(per_step, 0.5) / 1e6, "p99_ms": pctl(per_step, 0.99) / 1e6, "max_ms": per_step[-1] / 1e6}
@@ -523,19 +568,22 @@ def bench_ours(args) -> None:
     if idx >= n_dev:
         raise RuntimeError(f"rank {rank}: device index {idx} but only {n_dev} GPUs visible")
     keep_free = (2 * GiB) if dist is not None else 0
+    window = args.window_gib * GiB
+    variant = {"auto": 0, "direct": 1, "cpasync": 2, "bulk": 3, "bulkw": 4, "bulkd": 5}[args.variant]
+    tr = None
+    if not args.no_transient:  # before the standing arena exists: allocate -> fill -> verify -> free per cycle
+        trc = device.Cycler(idx, window_bytes=window, variant=variant)
+        tr = timed_cycles(trc, args.transient_steps, 3, dist, local)
     t_arena = time.perf_counter()
     arena = device.arena_create(idx, keep_free_bytes=keep_free)
     arena_ms = (time.perf_counter() - t_arena) * 1e3
-    variant = {"auto": 0, "direct": 1, "cpasync": 2, "bulk": 3, "bulkw": 4, "bulkd": 5}[args.variant]
     peak, peak_src = measured_peak()
-    window = args.window_gib * GiB
     device.set_option(_abi.GSB_OPT_INVENTORY_POLICY, _abi.GSB_INVENTORY_LIVE if args.inventory == "live" else _abi.GSB_INVENTORY_SNAPSHOT)
 
     sampler = ClockSampler(idx)
-    sampler.start()
     # ---- headline: steady-state rotating window ------------------------------------------------
     cyc = device.Cycler(idx, window_bytes=window, variant=variant)
-    head = timed_cycles(cyc, args.steps, args.warmup, dist, local)
+    head = timed_cycles(cyc, args.steps, args.warmup, dist, local, sampler)
     clocks = sampler.stop()
     last = head["last"]
     snapshot_age_ms = last.snapshot_age_ns / 1e6
@@ -547,10 +595,6 @@ def bench_ours(args) -> None:
     full = device.Cycler(idx, window_bytes=0, variant=variant)
     fw = timed_cycles(full, args.full_steps, 3, dist, local)
     device.arena_destroy(idx)
-    tr = None
-    if not args.no_transient:
-        trc = device.Cycler(idx, window_bytes=window, variant=variant)  # no arena: allocate -> fill -> verify -> free
-        tr = timed_cycles(trc, args.transient_steps, 3, dist, local)
 
     if dist is not None:  # every rank sampled its own GPU: report the slowest median and the union of reasons
         allc = [None] * world
@@ -648,6 +692,7 @@ def bench_ours(args) -> None:
         line["transient"] = {
             "e2e_value": args.transient_steps * world / tr_wall_s, "unit": UNIT, "steps": args.transient_steps,
             "ms_per_step": tr_wall_s * 1e3 / args.transient_steps, "kernel_ms_per_step": tr["kernel_ns"] / 1e6 / args.transient_steps,
+            "alloc_map_free_ms_per_step": (tr["wall_ns"] - tr["kernel_ns"]) / 1e6 / args.transient_steps,
             "per_step_rank0": {"p50_ms": tr["p50_ms"], "p99_ms": tr["p99_ms"], "max_ms": tr["max_ms"]},
             "bytes_walked": tl.probe.bytes_walked, "transient_flag": tl.transient,
             "what": "no standing arena (the daemon's default): per cycle cuMemCreate + map of one window, FILL, VERIFY, unmap + "
@@ -677,7 +722,8 @@ def main():
     ap.add_argument("--window-gib", type=int, default=1)
     ap.add_argument("--full-steps", type=int, default=10)
     ap.add_argument("--variant", default="auto", choices=["auto", "direct", "cpasync", "bulk", "bulkw", "bulkd"])
-    ap.add_argument("--cpu-iters", type=int, default=200)
+    ap.add_argument("--cpu-iters", type=int, default=1000, help="reference cycles timed for cpu_baseline (a few seconds)")
+    ap.add_argument("--ref-cycles-per-step", type=int, default=50, help="--impl reference: node cycles per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--inventory", default="snapshot", choices=["snapshot", "live"],
                     help="headline cycle's inventory policy (the other one is measured as a side leg)")

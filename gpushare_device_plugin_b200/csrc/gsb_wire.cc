@@ -349,6 +349,147 @@ int64_t gsb_encode_register_request(const char *version, const char *endpoint, c
   return (int64_t)(p - buf);
 }
 
+}  // extern "C"
+
+namespace {
+
+// sort.Sort as Go 1.10 runs it (the reference builds with golang:1.10: Dockerfile:1, .travis.yml:3-4) over the
+// candidate pods with the reference's NON-STRICT Less (podmanager.go:256-258: assume[i] <= assume[j]).
+// Third-party dependency absent from the reference tree: Go standard library, package sort, go1.10, src/sort/sort.go
+// (insertionSort, siftDown, heapSort, medianOfThree, doPivot, quickSort, Sort, maxDepth), restated from its published
+// source; the same restatement lives in oracle/wire_oracle.py::go110_sort and the two are held against each other
+// (tests/test_allocate.py, tests/golden/allocate_cases.json). `v` holds indices into `pods`; Less/Swap act on positions.
+struct Go110Sort {
+  const gsb_pod *pods;
+  std::vector<uint32_t> &v;
+
+  bool less(long i, long j) const { return pods[v[(size_t)i]].assume_time <= pods[v[(size_t)j]].assume_time; }
+  void swap(long i, long j) { std::swap(v[(size_t)i], v[(size_t)j]); }
+
+  void insertion_sort(long a, long b) {
+    for (long i = a + 1; i < b; i++)
+      for (long j = i; j > a && less(j, j - 1); j--) swap(j, j - 1);
+  }
+  void sift_down(long lo, long hi, long first) {
+    long root = lo;
+    for (;;) {
+      long child = 2 * root + 1;
+      if (child >= hi) return;
+      if (child + 1 < hi && less(first + child, first + child + 1)) child++;
+      if (!less(first + root, first + child)) return;
+      swap(first + root, first + child);
+      root = child;
+    }
+  }
+  void heap_sort(long a, long b) {
+    const long first = a, lo = 0, hi = b - a;
+    for (long i = (hi - 1) / 2; i >= 0; i--) sift_down(i, hi, first);
+    for (long i = hi - 1; i >= 0; i--) {
+      swap(first, first + i);
+      sift_down(lo, i, first);
+    }
+  }
+  void median_of_three(long m1, long m0, long m2) {
+    if (less(m1, m0)) swap(m1, m0);
+    if (less(m2, m1)) {
+      swap(m2, m1);
+      if (less(m1, m0)) swap(m1, m0);
+    }
+  }
+  void do_pivot(long lo, long hi, long *midlo, long *midhi) {
+    const long m = (long)((unsigned long)(lo + hi) >> 1);
+    if (hi - lo > 40) {  // Tukey's ninther
+      const long s = (hi - lo) / 8;
+      median_of_three(lo, lo + s, lo + 2 * s);
+      median_of_three(m, m - s, m + s);
+      median_of_three(hi - 1, hi - 1 - s, hi - 1 - 2 * s);
+    }
+    median_of_three(lo, m, hi - 1);
+    const long pivot = lo;
+    long a = lo + 1, c = hi - 1;
+    for (; a < c && less(a, pivot); a++) {
+    }
+    long b = a;
+    for (;;) {
+      for (; b < c && !less(pivot, b); b++) {
+      }
+      for (; b < c && less(pivot, c - 1); c--) {
+      }
+      if (b >= c) break;
+      swap(b, c - 1);
+      b++;
+      c--;
+    }
+    bool protect = hi - c < 5;
+    if (!protect && hi - c < (hi - lo) / 4) {
+      int dups = 0;
+      if (!less(pivot, hi - 1)) {
+        swap(c, hi - 1);
+        c++;
+        dups++;
+      }
+      if (!less(b - 1, pivot)) {
+        b--;
+        dups++;
+      }
+      if (!less(m, pivot)) {
+        swap(m, b - 1);
+        b--;
+        dups++;
+      }
+      protect = dups > 1;
+    }
+    if (protect) {
+      for (;;) {
+        for (; a < b && !less(b - 1, pivot); b--) {
+        }
+        for (; a < b && less(a, pivot); a++) {
+        }
+        if (a >= b) break;
+        swap(a, b - 1);
+        a++;
+        b--;
+      }
+    }
+    swap(pivot, b - 1);
+    *midlo = b - 1;
+    *midhi = c;
+  }
+  void quick_sort(long a, long b, int max_depth) {
+    while (b - a > 12) {
+      if (max_depth == 0) {
+        heap_sort(a, b);
+        return;
+      }
+      max_depth--;
+      long mlo, mhi;
+      do_pivot(a, b, &mlo, &mhi);
+      if (mlo - a < b - mhi) {
+        quick_sort(a, mlo, max_depth);
+        a = mhi;
+      } else {
+        quick_sort(mhi, b, max_depth);
+        b = mlo;
+      }
+    }
+    if (b - a > 1) {
+      for (long i = a + 6; i < b; i++)
+        if (less(i, i - 6)) swap(i, i - 6);
+      insertion_sort(a, b);
+    }
+  }
+  void sort() {
+    const long n = (long)v.size();
+    int depth = 0;
+    for (long i = n; i > 0; i >>= 1) depth++;
+    quick_sort(0, n, depth * 2);
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
 int gsb_allocate(const gsb_allocate_ctx *ctx, const gsb_pod *pods, uint32_t n_pods, const uint8_t *req,
                  size_t req_len, uint8_t *resp, size_t resp_cap, size_t *resp_len, int32_t *pod_index,
                  uint32_t *pod_req_gpu) {
@@ -399,31 +540,32 @@ int gsb_allocate(const gsb_allocate_ctx *ctx, const gsb_pod *pods, uint32_t n_po
     }
   }
   // makePodOrderdByAge: sort.Sort with Less = (t[i] <= t[j])  (podmanager.go:241-262), then the first pod in
-  // that order whose request equals this one (allocate.go:78-88). Go 1.10's sort.Sort on <= 12 elements is one
-  // ShellSort pass with gap 6 followed by insertionSort; with the non-strict Less that is what decides the
-  // order of pods with EQUAL assume-times, so it is restated exactly. Beyond 12 elements Go's pivot code
-  // (standard library, not in the reference tree) decides tie order; the insertion rule alone is used there
-  // (deviations) — an insertion sort with `<=` is the same permutation as sorting by (time
-  // ascending, arrival DEscending), a strict total order, so "first match in sorted order" is simply the
-  // minimum over the matching candidates: one O(n) pass, no sort.
+  // that order whose request equals this one (allocate.go:78-88). With the non-strict Less, the order of pods with
+  // EQUAL assume-times is whatever Go 1.10's sort.Sort leaves behind, so that algorithm is restated whole
+  // (Go110Sort above). It is only RUN when it can matter: the output is sorted by time whatever the tie order, so
+  // if exactly one matching candidate carries the smallest matching time it is the answer — one O(n) pass, no sort
+  // (every call of config 4/5, where timestamps are distinct nanoseconds). Only a tie for that smallest time among
+  // matching candidates needs the real permutation.
   int32_t found = -1;
-  if (cand.size() <= 12) {
-    auto less = [&](size_t i, size_t j) { return pods[cand[i]].assume_time <= pods[cand[j]].assume_time; };
-    if (cand.size() > 1)
-      for (size_t i = 6; i < cand.size(); i++)
-        if (less(i, i - 6)) std::swap(cand[i], cand[i - 6]);
-    for (size_t i = 1; i < cand.size(); i++)
-      for (size_t j = i; j > 0 && less(j, j - 1); j--) std::swap(cand[j], cand[j - 1]);
+  uint32_t tied = 0;
+  for (uint32_t c : cand) {
+    if (pods[c].gpu_mem_limit != pod_req) continue;
+    if (found < 0 || pods[c].assume_time < pods[found].assume_time) {
+      found = (int32_t)c;
+      tied = 1;
+    } else if (pods[c].assume_time == pods[found].assume_time) {
+      tied++;
+    }
+  }
+  if (tied > 1) {
+    Go110Sort sorter{pods, cand};
+    sorter.sort();
+    found = -1;
     for (uint32_t c : cand)
       if (pods[c].gpu_mem_limit == pod_req) {
         found = (int32_t)c;
         break;
       }
-  } else {
-    for (uint32_t c : cand) {  // cand is in arrival order: on equal times the later arrival wins
-      if (pods[c].gpu_mem_limit != pod_req) continue;
-      if (found < 0 || pods[c].assume_time <= pods[found].assume_time) found = (int32_t)c;
-    }
   }
 
   int kind;

@@ -445,28 +445,139 @@ def isGPUMemoryAssumedPod(pod: dict) -> bool:  # podutils.go:78-119
 
 
 def go110_sort(keys: List[int], items: list) -> list:
-    """sort.Sort as Go 1.10 runs it on <= 12 elements (quickSort's small-slice tail: one ShellSort
-    pass with gap 6, then insertionSort), with the reference's non-strict Less (`<=`,
-    podmanager.go:256-258). For more than 12 elements Go's doPivot decides the order of TIED keys;
-    that code is in the Go standard library, not under /root/reference, so ties beyond 12 candidates
-    are resolved by the same insertion rule here and in the product (DESIGN.md "deliberate
-    deviations"). Distinct keys sort identically under any algorithm."""
-    idx = list(range(len(items)))
+    """sort.Sort(orderedPodByAssumeTime) as Go 1.10 runs it (the reference builds with golang:1.10, Dockerfile:1,
+    .travis.yml:3-4), with the reference's NON-STRICT Less (`<=`, podmanager.go:256-258). The order of pods with EQUAL
+    assume-times is whatever this algorithm leaves behind, so it is restated whole: quickSort (slices of <= 12
+    elements: one ShellSort pass with gap 6, then insertionSort), doPivot (median of three, Tukey's ninther above 40
+    elements, the duplicate-protection pass), heapSort once 2*ceil(lg(n+1)) levels are used up (which an all-tied
+    input reaches: with `<=` every partition is maximally lopsided). Distinct keys sort identically under any
+    algorithm.
+
+    Third-party dependency absent from /root/reference: Go standard library, package sort, go1.10 (src/sort/sort.go:
+    insertionSort, siftDown, heapSort, medianOfThree, doPivot, quickSort, Sort, maxDepth), restated from its
+    published source. PARITY UNPINNED: no Go toolchain here to run it."""
+    data = list(range(len(items)))  # data[i] = index into items; Less/Swap act on positions
 
     def less(i, j):
-        return keys[idx[i]] <= keys[idx[j]]
+        return keys[data[i]] <= keys[data[j]]
 
-    n = len(idx)
-    if 1 < n <= 12:
-        for i in range(6, n):
-            if less(i, i - 6):
-                idx[i], idx[i - 6] = idx[i - 6], idx[i]
-    for i in range(1, n):
-        j = i
-        while j > 0 and less(j, j - 1):
-            idx[j], idx[j - 1] = idx[j - 1], idx[j]
-            j -= 1
-    return [items[i] for i in idx]
+    def swap(i, j):
+        data[i], data[j] = data[j], data[i]
+
+    def insertion_sort(a, b):
+        for i in range(a + 1, b):
+            j = i
+            while j > a and less(j, j - 1):
+                swap(j, j - 1)
+                j -= 1
+
+    def sift_down(lo, hi, first):
+        root = lo
+        while True:
+            child = 2 * root + 1
+            if child >= hi:
+                return
+            if child + 1 < hi and less(first + child, first + child + 1):
+                child += 1
+            if not less(first + root, first + child):
+                return
+            swap(first + root, first + child)
+            root = child
+
+    def heap_sort(a, b):
+        first, lo, hi = a, 0, b - a
+        for i in range((hi - 1) // 2, -1, -1):
+            sift_down(i, hi, first)
+        for i in range(hi - 1, -1, -1):
+            swap(first, first + i)
+            sift_down(lo, i, first)
+
+    def median_of_three(m1, m0, m2):
+        if less(m1, m0):
+            swap(m1, m0)
+        if less(m2, m1):
+            swap(m2, m1)
+            if less(m1, m0):
+                swap(m1, m0)
+
+    def do_pivot(lo, hi):
+        m = (lo + hi) >> 1
+        if hi - lo > 40:
+            s_ = (hi - lo) // 8
+            median_of_three(lo, lo + s_, lo + 2 * s_)
+            median_of_three(m, m - s_, m + s_)
+            median_of_three(hi - 1, hi - 1 - s_, hi - 1 - 2 * s_)
+        median_of_three(lo, m, hi - 1)
+        pivot = lo
+        a, c = lo + 1, hi - 1
+        while a < c and less(a, pivot):
+            a += 1
+        b = a
+        while True:
+            while b < c and not less(pivot, b):
+                b += 1
+            while b < c and less(pivot, c - 1):
+                c -= 1
+            if b >= c:
+                break
+            swap(b, c - 1)
+            b += 1
+            c -= 1
+        protect = hi - c < 5
+        if not protect and hi - c < (hi - lo) // 4:
+            dups = 0
+            if not less(pivot, hi - 1):
+                swap(c, hi - 1)
+                c += 1
+                dups += 1
+            if not less(b - 1, pivot):
+                b -= 1
+                dups += 1
+            if not less(m, pivot):
+                swap(m, b - 1)
+                b -= 1
+                dups += 1
+            protect = dups > 1
+        if protect:
+            while True:
+                while a < b and not less(b - 1, pivot):
+                    b -= 1
+                while a < b and less(a, pivot):
+                    a += 1
+                if a >= b:
+                    break
+                swap(a, b - 1)
+                a += 1
+                b -= 1
+        swap(pivot, b - 1)
+        return b - 1, c
+
+    def quick_sort(a, b, max_depth):
+        while b - a > 12:
+            if max_depth == 0:
+                heap_sort(a, b)
+                return
+            max_depth -= 1
+            mlo, mhi = do_pivot(a, b)
+            if mlo - a < b - mhi:
+                quick_sort(a, mlo, max_depth)
+                a = mhi
+            else:
+                quick_sort(mhi, b, max_depth)
+                b = mlo
+        if b - a > 1:
+            for i in range(a + 6, b):
+                if less(i, i - 6):
+                    swap(i, i - 6)
+            insertion_sort(a, b)
+
+    n = len(data)
+    depth, i = 0, n
+    while i > 0:
+        depth += 1
+        i >>= 1
+    quick_sort(0, n, depth * 2)
+    return [items[i] for i in data]
 
 
 def getCandidatePods(pod_list: List[dict], nodeName: str) -> List[dict]:  # podmanager.go:162-262

@@ -18,7 +18,7 @@ sampler_stop() { kill $SAMPLER 2>/dev/null; wait $SAMPLER 2>/dev/null; }
 
 if [ "$MODE" = node ]; then
   # multi-device correctness under one process: the tests that SKIP on a 1-GPU box
-  timeout 600 python -m pytest tests/test_cycle_gpu.py tests/test_daemon_gpu.py -m gpu -x -q -k "probe_all or node_cycle or daemon" -rs \
+  timeout 600 python -m pytest tests/test_cycle_gpu.py tests/test_daemon_gpu.py -m gpu -x -q -k "probe_all or node_cycle or native-transient" -rs \
     > $OUT/pytest_multi_${N}gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_multi_${N}gpu.log
   # both arms at N, with the driver-style sampler running, the reference first (as the driver orders them)
   sampler_start smi_ref_${N}gpu.csv
