@@ -480,8 +480,13 @@ def timed_cycles(cyc, steps: int, warmup: int, dist, local, sampler=None):
             raise RuntimeError(f"probe reported {r.probe.mismatch_words} mismatching words — unhealthy device")
         kernel_ns += r.probe.kernel_ns
         inv_ns += r.inventory_ns
-    barrier_sync(dist, local)
+    # every step ends device-synchronised (gsb_cycle returns after the kernel's results are in host memory), so this
+    # is a synchronised end-of-region time on this rank; the closing barrier brackets the region but its own latency
+    # and the ranks' exit skew from the OPENING barrier (which a wall clock taken after the closing barrier would add
+    # to every rank that started early) are not part of the K steps. MAX over ranks is taken by the caller.
     wall_ns = time.perf_counter_ns() - t0
+    barrier_sync(dist, local)
+    close_ns = time.perf_counter_ns() - t0 - wall_ns
     if sampler is not None:
         # the timed region is over (wall_ns is taken): a few more steps of the same load so that even a 7 ms
         # region is covered by samples taken at this clock/power state
@@ -490,7 +495,7 @@ def timed_cycles(cyc, steps: int, warmup: int, dist, local, sampler=None):
             cyc.step()
             sampler.sample_now()
     per_step.sort()
-    return {"wall_ns": wall_ns, "kernel_ns": kernel_ns, "inventory_ns": inv_ns, "launches": steps, "last": r,
+    return {"wall_ns": wall_ns, "closing_barrier_ns": close_ns, "kernel_ns": kernel_ns, "inventory_ns": inv_ns, "launches": steps, "last": r,
             "p50_ms": pctl(per_step, 0.5) / 1e6, "p99_ms": pctl(per_step, 0.99) / 1e6, "max_ms": per_step[-1] / 1e6}
 
 
@@ -602,6 +607,12 @@ def bench_ours(args) -> None:
         meds = [c["sm_mhz"] for c in allc if c and c["sm_mhz"] is not None]
         clocks = dict(clocks, sm_mhz=min(meds) if meds else None,
                       reasons=sorted(set(r for c in allc if c for r in c["reasons"])), ranks=world)
+    per_rank = None
+    if dist is not None:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, {"wall_ms": round(head["wall_ns"] / 1e6, 3), "p50_ms": round(head["p50_ms"], 4),
+                                          "p99_ms": round(head["p99_ms"], 4), "max_ms": round(head["max_ms"], 4),
+                                          "closing_barrier_ms": round(head["closing_barrier_ns"] / 1e6, 3)}, group=host_group)
     wall_s = allmax(dist, local, head["wall_ns"] / 1e9)
     kern_s = allmax(dist, local, head["kernel_ns"] / 1e9)
     p50_s = allmax(dist, local, head["p50_ms"] / 1e3)
@@ -664,7 +675,12 @@ def bench_ours(args) -> None:
                 "inventory_source": ("NVML queried inside every cycle" if args.inventory == "live" else
                                      f"NVML's answer from gsb_init (age {snapshot_age_ms:.0f} ms at the last step), identity "
                                      "re-validated per cycle via cuDeviceGetUuid; the reference also asks NVML once per start"),
-                "per_step_rank0": {"p50_ms": head["p50_ms"], "p99_ms": head["p99_ms"], "max_ms": head["max_ms"]}},
+                "per_step_rank0": {"p50_ms": head["p50_ms"], "p99_ms": head["p99_ms"], "max_ms": head["max_ms"]},
+                "timed_region": "per rank: opening barrier + synchronize, t0, K synchronous steps, t1, closing barrier + "
+                                "synchronize; value uses MAX over ranks of (t1 - t0). Each step ends device-synchronised, so "
+                                "t1 is a synchronised time; the closing barrier's latency and the ranks' exit skew from the "
+                                "opening barrier are reported (per_rank.closing_barrier_ms), not charged to the K steps",
+                "per_rank": per_rank},
         "gpu_launches": head["launches"] * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": prof.get("window_1gib_dram_bytes_per_launch"), "traffic_source": traffic_src,

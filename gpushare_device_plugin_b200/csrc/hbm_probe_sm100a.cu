@@ -15,6 +15,13 @@
  *            st.shared.v4 -> cp.async.bulk shared->global
  * All are persistent grid-stride kernels over fixed-size tiles, grid = resident CTAs/SM x #SMs.
  *
+ * What ships (default build): the two kernels GSB_VARIANT_AUTO ever launches — BULKD 32 KiB x 3 (FILL,
+ * VERIFY_REFILL) and BULK 32 KiB x 3 (VERIFY) — plus ONE shape each of DIRECT, CPASYNC and BULKW, kept as
+ * independent data paths for the parity tests (five implementations, one answer). The tile-shape / cache-operator /
+ * L2-hint sweeps of round 1 (profiles/sweep_r01_*.json: 72 kernel instantiations, a 3.9 MB library) are compiled only
+ * with -DGSB_LAB=1 (build.sh lab -> libgpushare_b200_lab.so, used by tools/sweep_r02.py); in the default build the
+ * GSB_*_CFG / GSB_DIRECT_FLAVOR / GSB_L2_HINT / GSB_DYN_FILL knobs are ignored.
+ *
  * Reduction: per-thread registers -> warp shuffles -> one gsb_partial slot per CTA (plain stores,
  * no atomics on the data path) -> a self-resetting ticket elects the last CTA, which folds all
  * slots into the pinned host-mapped gsb_kernel_out. Checksums are XOR / wrapping-add, so the
@@ -26,6 +33,10 @@
 
 #include "gsb_internal.h"
 #include "gsb_pattern.h"
+
+#ifndef GSB_LAB
+#define GSB_LAB 0
+#endif
 
 namespace {
 
@@ -742,15 +753,22 @@ typedef void (*probe_fn)(const gsb_kernel_args);
 
 // knob GSB_DYN_FILL=0: FILL under GSB_VARIANT_BULKD falls back to the static kernel (32 KiB x 6)
 bool dyn_fill() {
+#if GSB_LAB
   static const bool f = [] {
     const char *e = getenv("GSB_DYN_FILL");
     return !e || atoi(e) != 0;
   }();
   return f;
+#else
+  return true;
+#endif
 }
 
 // experiment knob GSB_BULKW_CFG: warp-tile size x ring depth x warps per CTA of the per-warp TMA path
 int bulkw_cfg() {
+#if !GSB_LAB
+  return 0;
+#endif
   static const int f = [] {
     const char *e = getenv("GSB_BULKW_CFG");
     const int v = e ? atoi(e) : 0;
@@ -761,16 +779,22 @@ int bulkw_cfg() {
 
 // experiment knob GSB_BULK_CFG: tile size x ring depth of the TMA path (unset = per-op default)
 int bulk_cfg() {
+#if !GSB_LAB
+  return -1;
+#endif
   static const int f = [] {
     const char *e = getenv("GSB_BULK_CFG");
     const int v = e ? atoi(e) : -1;
-    return v < 0 || v > 5 ? -1 : v;
+    return v < 0 || v > 8 ? -1 : v;
   }();
   return f;
 }
 
 // experiment knob GSB_L2_HINT: bit0 loads / bit1 stores of the TMA paths carry L2::evict_first
 uint32_t l2_hint_knob() {
+#if !GSB_LAB
+  return 0u;
+#endif
   static const uint32_t f = [] {
     const char *e = getenv("GSB_L2_HINT");
     return e ? (uint32_t)atoi(e) & 3u : 0u;
@@ -779,6 +803,9 @@ uint32_t l2_hint_knob() {
 }
 
 int direct_flavor() {
+#if !GSB_LAB
+  return 0;
+#endif
   static const int f = [] {
     const char *e = getenv("GSB_DIRECT_FLAVOR");
     const int v = e ? atoi(e) : 0;
@@ -800,9 +827,11 @@ probe_fn pick(uint32_t op, uint32_t variant, uint32_t *smem, uint32_t *threads) 
     if (op == GSB_OP_VERIFY_REFILL) return probe_direct<GSB_OP_VERIFY_REFILL, kDirectU, F>;  \
     return nullptr;
         GSB_DIRECT_CASE(0)
+#if GSB_LAB
         GSB_DIRECT_CASE(1)
         GSB_DIRECT_CASE(2)
         GSB_DIRECT_CASE(3)
+#endif
 #undef GSB_DIRECT_CASE
       }
       return nullptr;
@@ -816,7 +845,7 @@ probe_fn pick(uint32_t op, uint32_t variant, uint32_t *smem, uint32_t *threads) 
     case GSB_VARIANT_BULK:
       // shipped defaults (profiles/sweep_r01_knobs2.json): 32 KiB tiles; a pure-store FILL wants one fat
       // CTA per SM with a deep ring, the loading ops want 2 CTAs/SM x 3 stages
-      switch (bulk_cfg() >= 0 ? bulk_cfg() : (op == GSB_OP_FILL ? 5 : 1)) {
+      switch (bulk_cfg() >= 0 ? bulk_cfg() : ((GSB_LAB && op == GSB_OP_FILL) ? 5 : 1)) {
 #define GSB_BULK_CASE(ID, U, S)                                                              \
   case ID:                                                                                   \
     *smem = U * kThreads * 16 * S;                                                           \
@@ -824,21 +853,28 @@ probe_fn pick(uint32_t op, uint32_t variant, uint32_t *smem, uint32_t *threads) 
     if (op == GSB_OP_VERIFY) return probe_bulk<GSB_OP_VERIFY, U, S>;                         \
     if (op == GSB_OP_VERIFY_REFILL) return probe_bulk<GSB_OP_VERIFY_REFILL, U, S>;           \
     return nullptr;
+        GSB_BULK_CASE(1, 8, 3)            // 32 KiB x 3 = 96 KiB (2 CTAs/SM)   <- shipped
+#if GSB_LAB
         GSB_BULK_CASE(0, kBulkU, kBulkS)  // 16 KiB x 4 stages = 64 KiB/CTA (3 CTAs/SM)
-        GSB_BULK_CASE(1, 8, 3)            // 32 KiB x 3 = 96 KiB (2 CTAs/SM)
         GSB_BULK_CASE(2, 4, 6)            // 16 KiB x 6 = 96 KiB (2 CTAs/SM)
         GSB_BULK_CASE(3, 2, 8)            //  8 KiB x 8 = 64 KiB (3 CTAs/SM)
         GSB_BULK_CASE(4, 4, 3)            // 16 KiB x 3 = 48 KiB (4 CTAs/SM)
         GSB_BULK_CASE(5, 8, 6)            // 32 KiB x 6 = 192 KiB (1 CTA/SM)
+        GSB_BULK_CASE(6, 16, 3)           // 64 KiB x 3 = 192 KiB (1 CTA/SM)
+        GSB_BULK_CASE(7, 16, 2)           // 64 KiB x 2 = 128 KiB (1 CTA/SM)
+        GSB_BULK_CASE(8, 8, 4)            // 32 KiB x 4 = 128 KiB (1 CTA/SM)
+#endif
 #undef GSB_BULK_CASE
       }
       return nullptr;
     case GSB_VARIANT_BULKD:
       // dynamic schedule for the loading ops; FILL keeps the static BULK kernel (32 KiB x 6, 1 CTA/SM)
+#if GSB_LAB
       if (op == GSB_OP_FILL && !dyn_fill()) {
         *smem = 8 * kThreads * 16 * 6;
         return probe_bulk<GSB_OP_FILL, 8, 6>;
       }
+#endif
       switch (bulk_cfg() >= 0 ? bulk_cfg() : 1) {  // 32 KiB x 3, 2 CTAs/SM for all three ops
 #define GSB_BULKD_CASE(ID, U, S)                                                             \
   case ID:                                                                                   \
@@ -846,12 +882,17 @@ probe_fn pick(uint32_t op, uint32_t variant, uint32_t *smem, uint32_t *threads) 
     if (op == GSB_OP_FILL) return probe_bulk_dyn<GSB_OP_FILL, U, S>;                         \
     if (op == GSB_OP_VERIFY) return probe_bulk_dyn<GSB_OP_VERIFY, U, S>;                     \
     return probe_bulk_dyn<GSB_OP_VERIFY_REFILL, U, S>;
+        GSB_BULKD_CASE(1, 8, 3)  // <- shipped
+#if GSB_LAB
         GSB_BULKD_CASE(0, 4, 4)
-        GSB_BULKD_CASE(1, 8, 3)
         GSB_BULKD_CASE(2, 4, 6)
         GSB_BULKD_CASE(3, 2, 8)
         GSB_BULKD_CASE(4, 4, 3)
         GSB_BULKD_CASE(5, 8, 6)
+        GSB_BULKD_CASE(6, 16, 3)  // 64 KiB x 3 = 192 KiB (1 CTA/SM)
+        GSB_BULKD_CASE(7, 16, 2)  // 64 KiB x 2 = 128 KiB (1 CTA/SM)
+        GSB_BULKD_CASE(8, 8, 4)   // 32 KiB x 4 = 128 KiB (1 CTA/SM)
+#endif
 #undef GSB_BULKD_CASE
       }
       return nullptr;
@@ -866,6 +907,7 @@ probe_fn pick(uint32_t op, uint32_t variant, uint32_t *smem, uint32_t *threads) 
     if (op == GSB_OP_VERIFY_REFILL) return probe_bulk_warp<GSB_OP_VERIFY_REFILL, WPL, S, WARPS>; \
     return nullptr;
         GSB_BULKW_CASE(0, 8, 3, 8)    //  4 KiB x 3 x 8 warps =  96 KiB/CTA (2 CTAs/SM, 16 warps/SM)
+#if GSB_LAB
         GSB_BULKW_CASE(1, 8, 6, 4)    //  4 KiB x 6 x 4 warps =  96 KiB     (2 CTAs/SM,  8 warps/SM)
         GSB_BULKW_CASE(2, 16, 3, 4)   //  8 KiB x 3 x 4 warps =  96 KiB     (2 CTAs/SM,  8 warps/SM)
         GSB_BULKW_CASE(3, 4, 6, 8)    //  2 KiB x 6 x 8 warps =  96 KiB     (2 CTAs/SM, 16 warps/SM)
@@ -873,6 +915,7 @@ probe_fn pick(uint32_t op, uint32_t variant, uint32_t *smem, uint32_t *threads) 
         GSB_BULKW_CASE(5, 16, 3, 8)   //  8 KiB x 3 x 8 warps = 192 KiB     (1 CTA/SM,   8 warps/SM)
         GSB_BULKW_CASE(6, 8, 3, 16)   //  4 KiB x 3 x 16 warps = 192 KiB    (1 CTA/SM,  16 warps/SM)
         GSB_BULKW_CASE(7, 8, 2, 8)    //  4 KiB x 2 x 8 warps =  64 KiB     (3 CTAs/SM, 24 warps/SM)
+#endif
 #undef GSB_BULKW_CASE
       }
       return nullptr;

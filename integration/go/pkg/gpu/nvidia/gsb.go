@@ -60,6 +60,17 @@ func gsbNewDevice(idx uint) (*gsbDevice, error) {
 	}, nil
 }
 
+// gsbRefreshInventory re-reads every GPU's identity + memory from NVML into the library's snapshot. gsbNewDevice does
+// that per device already, so a plugin that builds its list through gsbNewDevice at every (re)start — as
+// NewNvidiaDevicePlugin does (server.go:39) — needs it only to force a refresh outside a restart.
+func gsbRefreshInventory() error { return gsbErr(C.gsb_inventory_refresh(C.GSB_ALL_DEVICES)) }
+
+// Options (include/gpushare_b200.h, GSB_OPT_*): inventory policy of the cycle, completion-wait spin budget, probe
+// watchdog, off-path NVML refresh period, HBM a transient probe window never takes.
+func gsbSetOption(key uint32, value uint64) error {
+	return gsbErr(C.gsb_set_option(C.uint32_t(key), C.uint64_t(value)))
+}
+
 // gsbSlices is setGPUMemory's arithmetic (nvidia.go:34-41).
 func gsbSlices(totalMiB uint64, gib bool) uint {
 	unit := C.int(0)
@@ -76,8 +87,9 @@ type gsbEvent struct {
 }
 
 const (
-	gsbEventXID   = uint64(C.GSB_EVENT_XID)   // == nvml.XidCriticalError
-	gsbEventProbe = uint64(C.GSB_EVENT_PROBE) // verdict of the active HBM probe
+	gsbEventXID       = uint64(C.GSB_EVENT_XID)       // == nvml.XidCriticalError
+	gsbEventProbe     = uint64(C.GSB_EVENT_PROBE)     // verdict of the active HBM probe (mismatch, failed launch, wedged)
+	gsbEventInventory = uint64(C.GSB_EVENT_INVENTORY) // the off-path NVML refresh disagrees with what is advertised
 )
 
 // gsbHealthStart replaces NewEventSet + the RegisterEventForDevice loop (nvidia.go:101-117).
@@ -110,7 +122,8 @@ func gsbArenaCreate(idx uint, maxBytes, keepFreeBytes uint64) (uint64, error) {
 	return uint64(got), err
 }
 
-// gsbCycle runs one inventory + health-probe cycle of one device; lw receives the ListAndWatchResponse bytes.
+// gsbCycle runs one inventory + health-probe cycle of one device; lw receives the ListAndWatchResponse bytes. With no
+// arena on the device and windowBytes > 0 the cycle probes a transient window (allocate -> fill -> verify -> free).
 func gsbCycle(idx uint, cycle uint64, windowBytes uint64, lw []byte) (healthy bool, lwLen int, err error) {
 	var res C.gsb_cycle_result
 	rc := C.gsb_cycle(C.uint32_t(idx), C.uint64_t(cycle), C.uint64_t(windowBytes), 1, C.GSB_VARIANT_AUTO,

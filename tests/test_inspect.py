@@ -83,3 +83,15 @@ def test_single_node_details_and_pending_column(cluster):
     assert rows["pod-71"][2:] == ["0", "2", "3", "0", "0", "0", "0", "0", "0"]
     assert "Allocated :  267 (18%)" in det and "Total :      1432" in det
     assert det.endswith("Allocated/Total GPU Memory In Cluster:  267/1432 (18%)  \n")  # trailing tab => padded cell
+
+
+def test_output_text_matches_the_frozen_fixture():
+    """tests/golden/inspect_cases.json (tests/golden/make_inspect_golden.py): regression freeze of the whole output
+    text — parity unpinned, see the generator's header."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "golden", "make_inspect_golden.py"), "--check"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr

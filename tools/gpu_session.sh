@@ -36,6 +36,18 @@ if [ "$MODE" = node ]; then
   tail -3 $OUT/pytest_multi_${N}gpu.log
   exit 0
 fi
+if [ "$MODE" = lab ]; then
+  # kernel lab work (needs ./build.sh lab and build/direct_anomaly, both built on the builder and shipped)
+  timeout 120 build/direct_anomaly > $OUT/direct_anomaly.json 2> $OUT/direct_anomaly.err
+  timeout 600 python tools/sweep_r02.py > $OUT/sweep_r02.log 2>&1; cp gpurun_out/sweep_r02.json $OUT/ 2>/dev/null
+  # one full capture of the shipped refill kernel on a 1 GiB window (profiles/ncu_window_r02_*), and of the shipped VERIFY
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:probe_bulk_dyn -c 2 -o $OUT/ncu_window_dyn_r02 \
+    python tools/profile_target.py 5 4 > $OUT/ncu_full.log 2>&1
+  ncu -i $OUT/ncu_window_dyn_r02.ncu-rep --page raw --csv > $OUT/ncu_window_dyn_r02_raw.csv 2>/dev/null
+  ncu -i $OUT/ncu_window_dyn_r02.ncu-rep --page details --csv > $OUT/ncu_window_dyn_r02_details.csv 2>/dev/null
+  tail -5 $OUT/sweep_r02.log
+  exit 0
+fi
 timeout 900 python -m pytest tests -m gpu -x -q -rs > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log
 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1
 # the driver's own command lines (steps 20, warmup 5), reference first, each under a driver-style sampler
