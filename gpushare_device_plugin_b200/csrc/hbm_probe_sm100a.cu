@@ -82,12 +82,18 @@ __device__ __forceinline__ uint4 ld_flavor(const uint4 *p) {
   }
   return v;
 }
-// A refill stores to the address it has just loaded from, and the stored value does not depend on
-// the loaded one. Left alone, the store issues while the load is still in flight and the memory
-// system serialises the pair: measured 0.12 of HBM peak (profiles/sweep_r01_variants.json, "direct"
-// "refill"). Naming the loaded register as an (unused) asm input makes the store wait for the data.
-__device__ __forceinline__ uint4 after_load(uint4 nw, uint32_t loaded) {
-  asm volatile("// order after load %1" : "+r"(nw.x) : "r"(loaded));
+// A refill stores to the address it has just loaded from, and the stored value (the next generation's pattern) does
+// not depend on the loaded one. Left alone, the four stores of a thread issue right behind its four loads, while
+// those loads are still in flight, and the memory system then orders every same-line load/store pair one at a time:
+// 0.12-0.16 of the HBM copy peak in rounds 1 and 2 (profiles/sweep_r01_variants.json, sweep_r02.json "direct refill")
+// against 0.93-0.97 for VERIFY or FILL alone. tools/lab/direct_anomaly.cu isolates it (profiles/direct_anomaly_r02.json):
+// the same in-place walk runs at 6.1 TB/s when the stored value really depends on the loaded one or when the store
+// trails its load by a tile, and at 1.8-3.0 TB/s when it does not. Round 1's remedy — naming the loaded register as
+// an input of an EMPTY inline-asm statement — did nothing: a comment is not an instruction, so the dependency was gone
+// before ptxas scheduled the store. A real one costs two integer ops per word: the loaded lanes are AND-ed with a
+// kernel argument that is always 0 (the compiler cannot know) and XOR-ed into the value to store.
+__device__ __forceinline__ uint4 after_load(uint4 nw, uint32_t loaded, uint32_t opaque_zero) {
+  nw.x ^= loaded & opaque_zero;
   return nw;
 }
 template <int F>
@@ -353,7 +359,7 @@ __global__ void __launch_bounds__(kThreads) probe_direct(const gsb_kernel_args a
       for (int u = 0; u < U; u++) {
         const unsigned long long l = l0 + (unsigned long long)u * kThreads;
         uint4 nw = process_word<OP>(v[u], a.first_word + l, key_expect, key_write, acc);
-        if (OP == GSB_OP_VERIFY_REFILL) nw = after_load(nw, v[u].x ^ v[u].y ^ v[u].z ^ v[u].w);
+        if (OP == GSB_OP_VERIFY_REFILL) nw = after_load(nw, v[u].x ^ v[u].y ^ v[u].z ^ v[u].w, a.opaque_zero);
         if (OP != GSB_OP_VERIFY) st_flavor<F>(win + l, nw);
       }
     } else {  // ragged last tile
@@ -363,7 +369,7 @@ __global__ void __launch_bounds__(kThreads) probe_direct(const gsb_kernel_args a
         if (l < a.n_words) {
           if (OP != GSB_OP_FILL) v[u] = ld_flavor<F>(win + l);
           uint4 nw = process_word<OP>(v[u], a.first_word + l, key_expect, key_write, acc);
-          if (OP == GSB_OP_VERIFY_REFILL) nw = after_load(nw, v[u].x ^ v[u].y ^ v[u].z ^ v[u].w);
+          if (OP == GSB_OP_VERIFY_REFILL) nw = after_load(nw, v[u].x ^ v[u].y ^ v[u].z ^ v[u].w, a.opaque_zero);
           if (OP != GSB_OP_VERIFY) st_flavor<F>(win + l, nw);
         }
       }
@@ -971,6 +977,7 @@ int gsb_kernel_launch(uint32_t op, const gsb_launch_geom *geom, const gsb_kernel
   if (!fn) return (int)cudaErrorInvalidValue;
   gsb_kernel_args a = *args;
   a.l2_hint = l2_hint_knob();
+  a.opaque_zero = 0u;
   fn<<<geom->grid, threads, smem, stream>>>(a);
   return (int)cudaGetLastError();
 }
