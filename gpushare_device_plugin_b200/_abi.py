@@ -56,7 +56,7 @@ SYMBOLS = [
     "gsb_set_option", "gsb_get_option", "gsb_slices", "gsb_fake_device_id", "gsb_real_device_id",
     "gsb_encode_list_and_watch", "gsb_encode_register_request",
     "gsb_arena_create", "gsb_arena_destroy", "gsb_arena_bytes", "gsb_probe", "gsb_probe_all",
-    "gsb_arena_read", "gsb_arena_write", "gsb_test_stall", "gsb_cycle", "gsb_cycle_all",
+    "gsb_arena_read", "gsb_arena_write", "gsb_test_stall", "gsb_test_skew_snapshot", "gsb_cycle", "gsb_cycle_all",
     "gsb_health_start", "gsb_health_stop", "gsb_health_wait", "gsb_health_inject", "gsb_health_set_recovery", "gsb_xid_is_benign",
     "gsb_allocate", "gsb_allocate_err_response", "gsb_patch_assigned_body",
 ]
@@ -185,6 +185,7 @@ def _load() -> C.CDLL:
         "gsb_set_option": (C.c_int, [C.c_uint32, C.c_uint64]),
         "gsb_get_option": (C.c_int, [C.c_uint32, u64p]),
         "gsb_test_stall": (C.c_int, [C.c_uint32, C.c_uint32]),
+        "gsb_test_skew_snapshot": (C.c_int, [C.c_uint32, C.c_uint64]),
         "gsb_slices": (C.c_uint32, [C.c_uint64, C.c_int]),
         "gsb_fake_device_id": (C.c_int, [C.c_char_p, C.c_uint32, C.c_char_p, C.c_size_t]),
         "gsb_real_device_id": (C.c_int, [C.c_char_p, C.c_char_p, C.c_size_t]),

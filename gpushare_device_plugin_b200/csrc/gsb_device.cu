@@ -1259,6 +1259,15 @@ int gsb_test_stall(uint32_t idx, uint32_t ms) {
   return GSB_OK;
 }
 
+int gsb_test_skew_snapshot(uint32_t idx, uint64_t total_bytes) {
+  std::shared_lock<std::shared_mutex> api_lk(G.api_mu);
+  Device *d = device_at(idx);
+  if (!d) return G.inited ? GSB_ERR_NO_DEVICE : GSB_ERR_NOT_INITIALIZED;
+  std::lock_guard<std::mutex> lk(d->smu);
+  d->snap.total = total_bytes;
+  return GSB_OK;
+}
+
 }  // extern "C"
 
 namespace {

@@ -216,6 +216,9 @@ int gsb_arena_write(uint32_t idx, uint64_t offset, const void *src, uint64_t byt
 /* test hook: enqueue a kernel that keeps the device's probe stream busy for `ms` milliseconds — a stand-in for a
  * wedged GPU, to exercise the completion watchdog */
 int gsb_test_stall(uint32_t idx, uint32_t ms);
+/* test hook: overwrite the snapshot's total (as if NVML had answered differently at the last (re)start), to exercise the
+ * off-path refresher: its next pass must raise GSB_EVENT_INVENTORY / GSB_INVENTORY_TOTAL_CHANGED for this device */
+int gsb_test_skew_snapshot(uint32_t idx, uint64_t total_bytes);
 
 /*
  * One inventory + health-probe cycle of one device (the unit of BASELINE.json's metric):

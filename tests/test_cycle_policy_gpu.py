@@ -143,3 +143,26 @@ def test_prober_reports_a_wedged_device(gsb):
         gsb.arena_destroy(0)
         gsb.shutdown()
         gsb.init()
+
+
+def test_offpath_refresher_reports_an_inventory_that_changed_under_the_snapshot(gsb):
+    """While health runs, NVML is re-asked off the cycle's path every GSB_OPT_INVENTORY_REFRESH_MS; an answer that
+    differs from the snapshot is an event, never silently absorbed. (The snapshot is skewed by a test hook: a real
+    box will not change its memory size on request.)"""
+    from gpushare_device_plugin_b200._abi import lib
+    info = gsb.device_info(0)
+    gsb.set_option(_abi.GSB_OPT_INVENTORY_REFRESH_MS, 100)
+    gsb.health_start(probe_period_ms=0, window_bytes=0)
+    try:
+        assert gsb.health_wait(400) is None  # refreshes that agree with the snapshot are silent
+        assert lib.gsb_test_skew_snapshot(0, info.total_bytes - (1 << 30)) == 0
+        cyc = gsb.Cycler(0, window_bytes=64 << 20)
+        assert cyc.step().slices == 178  # the cycle serves the (skewed) snapshot ...
+        ev = gsb.health_wait(3000)       # ... until the refresher sees NVML disagree
+        assert ev is not None and (ev.etype, ev.edata) == (_abi.GSB_EVENT_INVENTORY, _abi.GSB_INVENTORY_TOTAL_CHANGED)
+        assert ev.uuid.decode() == info.uuid
+        snap, _ = gsb.inventory_snapshot(0)
+        assert snap.total_bytes == info.total_bytes and cyc.step().slices == 179  # and the snapshot is NVML's answer again
+    finally:
+        gsb.health_stop()
+        gsb.set_option(_abi.GSB_OPT_INVENTORY_REFRESH_MS, 5000)

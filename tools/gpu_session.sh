@@ -49,7 +49,7 @@ if [ "$MODE" = lab ]; then
   exit 0
 fi
 timeout 900 python -m pytest tests -m gpu -x -q -rs > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log
-python __graft_entry__.py smoke > $OUT/smoke.log 2>&1
+python __graft_entry__.py smoke-only > $OUT/smoke.log 2>&1
 # the driver's own command lines (steps 20, warmup 5), reference first, each under a driver-style sampler
 sampler_start smi_ref.csv
 timeout 400 python bench.py --impl reference --steps 20 --warmup 5 > $OUT/bench_reference_1gpu_sampled.json 2> $OUT/bench_reference_1gpu.err
@@ -62,5 +62,10 @@ timeout 400 python bench.py --steps 200 --warmup 5 --quick-allocate > $OUT/bench
 # launch list of the same command (shares, not absolutes: ncu serialises and runs cold)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
   python bench.py --steps 20 --warmup 3 --no-allocate --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
+# the DIRECT control after its refill fix (lab library: same source, all shapes)
+SWEEP_ONLY=direct timeout 200 python tools/sweep_r02.py > $OUT/sweep_direct.log 2>&1; cp gpurun_out/sweep_r02_direct.json $OUT/ 2>/dev/null
+# memcheck + racecheck of every data path on a small arena (the smoke), this round's kernels
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 3 python __graft_entry__.py smoke-only > $OUT/memcheck_smoke.log 2>&1; echo "memcheck rc=$?" >> $OUT/memcheck_smoke.log
+timeout 600 compute-sanitizer --tool racecheck --error-exitcode 3 python tools/profile_target.py 5 2 > $OUT/racecheck_bulkd.log 2>&1; echo "racecheck rc=$?" >> $OUT/racecheck_bulkd.log
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv > $OUT/clocks_after.csv 2>&1
 tail -3 $OUT/pytest_gpu.log

@@ -61,6 +61,9 @@ def main():
             print(name, " | ".join(f"{r['bytes'] >> 20}MiB {r['op']} {r['median_us']:.0f}us {r['frac']:.3f}" for r in rows), flush=True)
     sizes = [64 << 20, 256 << 20, GiB, 0]
     show("direct", run({}, 1, sizes))
+    if os.environ.get("SWEEP_ONLY") == "direct":
+        json.dump(res, open(os.path.join(ROOT, "gpurun_out", "sweep_r02_direct.json"), "w"), indent=1)
+        return
     for vname, v in (("bulk_static", 3), ("bulk_dynamic", 5)):
         for cfg, shape in SHAPES.items():
             show(f"{vname} {shape}", run({"GSB_BULK_CFG": str(cfg), "GSB_DYN_FILL": "1"}, v, sizes))
