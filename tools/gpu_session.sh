@@ -65,7 +65,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 # the DIRECT control after its refill fix (lab library: same source, all shapes)
 SWEEP_ONLY=direct timeout 200 python tools/sweep_r02.py > $OUT/sweep_direct.log 2>&1; cp gpurun_out/sweep_r02_direct.json $OUT/ 2>/dev/null
 # memcheck + racecheck of every data path on a small arena (the smoke), this round's kernels
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 3 python __graft_entry__.py smoke-only > $OUT/memcheck_smoke.log 2>&1; echo "memcheck rc=$?" >> $OUT/memcheck_smoke.log
-timeout 600 compute-sanitizer --tool racecheck --error-exitcode 3 python tools/profile_target.py 5 2 > $OUT/racecheck_bulkd.log 2>&1; echo "racecheck rc=$?" >> $OUT/racecheck_bulkd.log
+GSB_PROBE_WATCHDOG_MS=0 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 3 python __graft_entry__.py smoke-only > $OUT/memcheck_smoke.log 2>&1; echo "memcheck rc=$?" >> $OUT/memcheck_smoke.log
+GSB_PROBE_WATCHDOG_MS=0 timeout 600 compute-sanitizer --tool racecheck --error-exitcode 3 python tools/profile_target.py 5 2 > $OUT/racecheck_bulkd.log 2>&1; echo "racecheck rc=$?" >> $OUT/racecheck_bulkd.log
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv > $OUT/clocks_after.csv 2>&1
 tail -3 $OUT/pytest_gpu.log
