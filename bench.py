@@ -186,6 +186,19 @@ def barrier_sync(dist, local):
             torch.cuda.synchronize(local)
 
 
+def aligned_start(dist, local):
+    """Opening bracket of a timed region: barrier + synchronize, then every rank spins to ONE agreed instant of the
+    host's monotonic clock (system-wide on Linux), 1 ms after the latest rank's "now". Ranks leave an NCCL barrier up
+    to ~1 ms apart (host wake-up); without this, a rank that left early waits that long at the CLOSING barrier, which
+    is 15 % of a 20-step region at N = 8 and says nothing about the K steps."""
+    barrier_sync(dist, local)
+    if dist is None:
+        return
+    target_us = allmax(dist, local, float(time.monotonic_ns() // 1000)) + 1000.0
+    while time.monotonic_ns() // 1000 < target_us:
+        pass
+
+
 def allmax(dist, local, x: float) -> float:
     if dist is None:
         return x
@@ -468,7 +481,7 @@ def timed_cycles(cyc, steps: int, warmup: int, dist, local, sampler=None):
     if sampler is not None:
         sampler.sm.clear()      # keep only samples taken under load (from the last warm-up step on)
         sampler.sample_now()
-    barrier_sync(dist, local)
+    aligned_start(dist, local)
     kernel_ns, inv_ns = 0, 0
     per_step = []
     t0 = time.perf_counter_ns()
@@ -613,6 +626,7 @@ def bench_ours(args) -> None:
         dist.all_gather_object(per_rank, {"wall_ms": round(head["wall_ns"] / 1e6, 3), "p50_ms": round(head["p50_ms"], 4),
                                           "p99_ms": round(head["p99_ms"], 4), "max_ms": round(head["max_ms"], 4),
                                           "closing_barrier_ms": round(head["closing_barrier_ns"] / 1e6, 3)}, group=host_group)
+    wall_incl_s = allmax(dist, local, (head["wall_ns"] + head["closing_barrier_ns"]) / 1e9)
     wall_s = allmax(dist, local, head["wall_ns"] / 1e9)
     kern_s = allmax(dist, local, head["kernel_ns"] / 1e9)
     p50_s = allmax(dist, local, head["p50_ms"] / 1e3)
@@ -666,6 +680,7 @@ def bench_ours(args) -> None:
                    "host": f"{cpu_model()}, nproc={os.cpu_count()}"},
         "e2e": {"value": units / wall_s, "unit": UNIT, "ms_per_step": wall_s * 1e3 / args.steps,
                 "p50_value": world / p50_s, "p50_ms_per_step": p50_s * 1e3,
+                "value_incl_closing_barrier": units / wall_incl_s,
                 "h2d_bytes_per_step": 120, "d2h_bytes_per_step": 56,
                 "note": "gsb_cycle through ctypes: identity check against the CUDA driver, slices, encode, launch, completion "
                         "wait; h2d = kernel argument block, d2h = gsb_kernel_out written by the last CTA into pinned mapped "
@@ -676,10 +691,11 @@ def bench_ours(args) -> None:
                                      f"NVML's answer from gsb_init (age {snapshot_age_ms:.0f} ms at the last step), identity "
                                      "re-validated per cycle via cuDeviceGetUuid; the reference also asks NVML once per start"),
                 "per_step_rank0": {"p50_ms": head["p50_ms"], "p99_ms": head["p99_ms"], "max_ms": head["max_ms"]},
-                "timed_region": "per rank: opening barrier + synchronize, t0, K synchronous steps, t1, closing barrier + "
-                                "synchronize; value uses MAX over ranks of (t1 - t0). Each step ends device-synchronised, so "
-                                "t1 is a synchronised time; the closing barrier's latency and the ranks' exit skew from the "
-                                "opening barrier are reported (per_rank.closing_barrier_ms), not charged to the K steps",
+                "timed_region": "per rank: opening barrier + synchronize, then all ranks spin to one agreed instant of the host's "
+                                "monotonic clock (start-line alignment), t0, K synchronous steps, t1, closing barrier + "
+                                "synchronize, t2. value uses MAX over ranks of (t1 - t0): each step ends device-synchronised, "
+                                "so t1 is a synchronised time. value_incl_closing_barrier uses MAX over ranks of (t2 - t0), "
+                                "i.e. with the closing barrier's own latency inside (per_rank.closing_barrier_ms)",
                 "per_rank": per_rank},
         "gpu_launches": head["launches"] * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -19,8 +19,12 @@ bench.barrier_sync(dist, local)
 m = bench.allmax(dist, local, 10.0 + rank)        # max over ranks of a per-rank timing
 s = bench.allmax(dist, local, 5.0 - rank)
 bench.barrier_sync(dist, local)
+import time
+bench.aligned_start(dist, local)                  # every rank leaves at one agreed instant of the host's monotonic clock
+left = time.monotonic_ns() / 1e6
+skew = bench.allmax(dist, local, left) + bench.allmax(dist, local, -left)   # max - min over ranks, ms
 if rank == 0:
-    print(json.dumps({"max": m, "max2": s, "world": world}))
+    print(json.dumps({"max": m, "max2": s, "world": world, "start_skew_ms": skew}))
 dist.destroy_process_group()
 ''' % ROOT
 
@@ -47,7 +51,9 @@ def test_world_size_2_gloo_max_over_ranks():
     procs, outs = launch(["-c", WORKER])
     assert [p.returncode for p in procs] == [0, 0], outs
     line = json.loads(outs[0][0].strip().splitlines()[-1])
+    skew = line.pop("start_skew_ms")
     assert line == {"max": 11.0, "max2": 5.0, "world": 2}
+    assert 0 <= skew < 5.0, skew  # (sub-0.1 ms on an idle box; the bound only says the ranks did align)
     assert outs[1][0].strip() == ""  # only rank 0 prints
 
 

@@ -753,3 +753,18 @@ def test_single_gpu_node_does_not_answer_a_stale_cache_with_the_shortcut(world):
     assert envs[0]["NVIDIA_VISIBLE_DEVICES"] == str(fakes.MINORS[0]) == envs[0]["ALIYUN_COM_GPU_MEM_IDX"]
     assert world.kube.pod("pod-99")["metadata"]["annotations"]["ALIYUN_COM_GPU_MEM_ASSIGNED"] == "true"
     ch.close()
+
+
+def test_inventory_event_marks_only_that_gpu_unhealthy(world):
+    """GSB_EVENT_INVENTORY (0x200): the library's off-path NVML refresh found a GPU whose identity or total no longer
+    matches what is advertised. The daemon must not keep advertising it as if nothing happened: every fake device of
+    that GPU goes Unhealthy (the others stay), like any other device-scoped fault (nvidia.go:146-150)."""
+    d = world.start()
+    ch = d.channel()
+    it = Frames(d.kubelet.list_and_watch(ch))
+    assert next_frame(it) == wo.marshal_ListAndWatchResponse(all_devs())
+    d.inject(ch, fakes.UUIDS[4], 0x200, 2)  # total changed
+    assert wo.unmarshal_ListAndWatchResponse(next_frame(it)) == all_devs(unhealthy={4})
+    d.inject(ch, fakes.UUIDS[4], 0x300, 1)  # an event type nobody knows is ignored (nvidia.go:127-129)
+    assert next_frame(it, 0.7) == "timeout"
+    ch.close()

@@ -490,3 +490,21 @@ def test_single_gpu_node_does_not_answer_a_stale_cache_with_the_shortcut(world, 
     assert envs[0]["NVIDIA_VISIBLE_DEVICES"] == str(fakes.MINORS[0]) == envs[0]["ALIYUN_COM_GPU_MEM_IDX"]
     assert world.kube.pod("pod-99")["metadata"]["annotations"]["ALIYUN_COM_GPU_MEM_ASSIGNED"] == "true"
     ch.close()
+
+
+def test_inventory_event_marks_only_that_gpu_unhealthy(world):
+    """GSB_EVENT_INVENTORY from the library's off-path NVML refresh: that GPU's fake devices go Unhealthy, the others
+    stay; unknown event types are ignored (nvidia.go:127-129)."""
+    p = world.make()
+    p.Serve(world.kubelet.socket)
+    ch = world.kubelet.channel("aliyungpushare.sock")
+    it = Frames(world.kubelet.list_and_watch(ch))
+    assert next_frame(it) == wo.marshal_ListAndWatchResponse(all_devs())
+    device.health_inject(fakes.UUIDS[4], 0x200, 2)
+    last, f = None, next_frame(it)
+    while f != "timeout":
+        last, f = f, next_frame(it, 1.0)
+    assert wo.unmarshal_ListAndWatchResponse(last) == all_devs(unhealthy={4})
+    device.health_inject(fakes.UUIDS[4], 0x300, 1)
+    assert next_frame(it, 0.7) == "timeout"
+    ch.close()

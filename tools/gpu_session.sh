@@ -16,6 +16,18 @@ N=$(nvidia-smi -L | wc -l)
 sampler_start() { nvidia-smi --query-gpu=index,clocks.sm,power.draw,utilization.gpu --format=csv,noheader -lms 100 > $OUT/$1 2>&1 & SAMPLER=$!; }
 sampler_stop() { kill $SAMPLER 2>/dev/null; wait $SAMPLER 2>/dev/null; }
 
+if [ "$MODE" = scale ]; then
+  # both arms at N with the driver's command line under a driver-style sampler, nothing else
+  sampler_start smi_ref_${N}gpu.csv
+  timeout 300 python bench.py --impl reference --gpus $N --steps 20 --warmup 5 --no-allocate > $OUT/bench_reference_${N}gpu.json 2> $OUT/bench_reference_${N}gpu.err
+  sampler_stop
+  sampler_start smi_ours_${N}gpu.csv
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+    bench.py --gpus $N --steps 20 --warmup 5 > $OUT/bench_${N}gpu_sampled.json 2> $OUT/bench_${N}gpu_sampled.err
+  sampler_stop
+  tail -c 300 $OUT/bench_${N}gpu_sampled.json
+  exit 0
+fi
 if [ "$MODE" = node ]; then
   # multi-device correctness under one process: the tests that SKIP on a 1-GPU box
   timeout 600 python -m pytest tests/test_cycle_gpu.py tests/test_daemon_gpu.py -m gpu -x -q -k "probe_all or node_cycle or native-transient" -rs \
