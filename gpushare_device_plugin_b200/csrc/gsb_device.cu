@@ -601,7 +601,7 @@ int probe_end_locked(Device *d, ProbeFlight *fl, gsb_probe_result *out) {
     if (spin_ns) {
       const uint64_t deadline = now_ns() + spin_ns;
       while (*flag != a.launch_seq) {
-        for (int i = 0; i < 64; i++) __builtin_ia32_pause();
+        for (int i = 0; i < 8; i++) __builtin_ia32_pause();
         if (now_ns() > deadline) break;
       }
     }
