@@ -171,6 +171,7 @@ struct Device {
   uint32_t next_gen = 1;
   bool faulted = false;  // prober: sticky
   std::vector<uint8_t> bits_scratch;  // Unhealthy bit string of this device's own list (faulted devices only)
+  bool transient_arena = false;  // the mapped arena is a transient window that could not be given back yet (wedged launch)
   bool wedged = false;   // a launch outlived the watchdog and is still on the stream: no new launches until it drains
 
   // inventory snapshot: what NVML said at the last (re)start-time query (server.go:39 -> nvidia.go:53-89 queries
@@ -1285,7 +1286,14 @@ int cycle_impl(Device *d, uint32_t idx, uint64_t cycle_no, uint64_t window_bytes
   // allocates the window, fills it, verifies it and gives it back, so between cycles the plugin holds no HBM beyond
   // its CUDA context and the 179 advertised slices are not oversold. "Nothing free to probe" (tenants hold the
   // HBM) is not a GPU fault.
-  const bool transient = !d->va;
+  if (d->va && d->transient_arena) {
+    // a transient window that a wedged launch kept mapped: give it back now if the stream has drained, otherwise this
+    // cycle's verdict is the same wedge (nothing new is queued, nothing more is allocated)
+    if (d->wedged && cudaStreamQuery(d->stream) != cudaErrorNotReady) d->wedged = false;
+    if (arena_destroy_locked(d) == GSB_OK) d->transient_arena = false;
+  }
+  const bool leftover = d->va && d->transient_arena;
+  const bool transient = !d->va || leftover;
   gsb_probe_result fill_res;
   memset(&fill_res, 0, sizeof fill_res);
   int prc = GSB_OK;
@@ -1297,7 +1305,13 @@ int cycle_impl(Device *d, uint32_t idx, uint64_t cycle_no, uint64_t window_bytes
     }
     out->transient = 1;
     uint64_t got = 0;
-    prc = arena_create_locked(d, window_bytes, G.transient_keep_free.load(), &got, &fill_res);
+    if (leftover) {
+      set_error("%s: the previous transient window is still held by a wedged launch", d->uuid);
+      prc = GSB_ERR_TIMEOUT;
+    } else {
+      prc = arena_create_locked(d, window_bytes, G.transient_keep_free.load(), &got, &fill_res);
+      if (prc != GSB_OK && d->va) d->transient_arena = true;  // could not be unmapped under a wedged launch: retried next cycle
+    }
     if (prc == GSB_ERR_OUT_OF_MEMORY) {
       out->probe.status = GSB_ERR_OUT_OF_MEMORY;
       prc = GSB_OK;
@@ -1369,7 +1383,7 @@ int cycle_impl(Device *d, uint32_t idx, uint64_t cycle_no, uint64_t window_bytes
       out->probe.kernel_ns += fill_res.kernel_ns;
       out->probe.bytes_written = fill_res.bytes_written;
     }
-    arena_destroy_locked(d);  // a wedged launch keeps it (and the GPU is reported below)
+    if (!leftover && d->va && arena_destroy_locked(d) != GSB_OK) d->transient_arena = true;  // wedged: kept, retried next cycle
   }
   if (rc) return rc;
   if (out->lw_len < 0) return (int)out->lw_len;

@@ -172,3 +172,34 @@ def test_offpath_refresher_reports_an_inventory_that_changed_under_the_snapshot(
     finally:
         gsb.health_stop()
         gsb.set_option(_abi.GSB_OPT_INVENTORY_REFRESH_MS, 5000)
+
+
+def test_transient_window_kept_by_a_wedged_launch_is_given_back_once_the_stream_drains(gsb):
+    """The transient window cannot be unmapped under a launch that has not finished: it is kept, the cycle's verdict is
+    the wedge, nothing more is allocated or queued while the wedge lasts — and the first cycle after the stream drains
+    gives the window back and probes a fresh one (it must not live on as a standing arena)."""
+    with pytest.raises(_abi.GsbError):
+        gsb.arena_bytes(0)
+    free0 = nvml_free()
+    gsb.set_option(_abi.GSB_OPT_WATCHDOG_MS, 100)
+    cyc = gsb.Cycler(0, window_bytes=GiB)
+    try:
+        assert cyc.step().healthy == 1
+        gsb.test_stall(0, 1200)
+        r = cyc.step(raise_on_error=False)  # the window's FILL queues behind the stall and outlives the watchdog
+        assert cyc.rc == _abi.GSB_ERR_TIMEOUT and r.healthy == 0 and r.transient == 1
+        assert gsb.arena_bytes(0) == GiB    # kept: it cannot be unmapped under the launch
+        t0 = time.monotonic()
+        r = cyc.step(raise_on_error=False)  # still wedged: refused at once, nothing more taken
+        assert cyc.rc == _abi.GSB_ERR_TIMEOUT and time.monotonic() - t0 < 0.05 and gsb.arena_bytes(0) == GiB
+        time.sleep(1.5)
+        r = cyc.step(raise_on_error=False)  # drained: the old window is released, a fresh one is walked clean
+        assert cyc.rc == 0 and r.transient == 1 and r.probe.status == 0 and r.probe.mismatch_words == 0
+        assert r.probe.bytes_walked == GiB and r.healthy == 0  # (Unhealthy stays sticky, server.go:180)
+        with pytest.raises(_abi.GsbError):
+            gsb.arena_bytes(0)
+        assert abs(nvml_free() - free0) < 64 << 20
+    finally:
+        gsb.set_option(_abi.GSB_OPT_WATCHDOG_MS, 2000)
+        gsb.shutdown()
+        gsb.init()
