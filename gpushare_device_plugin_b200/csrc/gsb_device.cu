@@ -383,6 +383,7 @@ int arena_destroy_locked(Device *d) {
   d->va = 0;
   d->va_size = 0;
   d->arena_bytes = 0;
+  d->transient_arena = false;
   if (d->seed_table) cudaFree(d->seed_table);
   d->seed_table = nullptr;
   d->gen.clear();
