@@ -754,7 +754,7 @@ def main():
     ap.add_argument("--window-gib", type=int, default=1)
     ap.add_argument("--full-steps", type=int, default=10)
     ap.add_argument("--variant", default="auto", choices=["auto", "direct", "cpasync", "bulk", "bulkw", "bulkd"])
-    ap.add_argument("--cpu-iters", type=int, default=1000, help="reference cycles timed for cpu_baseline (a few seconds)")
+    ap.add_argument("--cpu-iters", type=int, default=3000, help="reference cycles timed for cpu_baseline (about 10 s of CPU work)")
     ap.add_argument("--ref-cycles-per-step", type=int, default=50, help="--impl reference: node cycles per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--inventory", default="snapshot", choices=["snapshot", "live"],

@@ -43,22 +43,49 @@ def gpuMemoryInPod(pod: dict) -> int:  # podinfo.go:124-134 == display.go:247-25
     return total
 
 
+def _parse_int64(s) -> Optional[int]:  # strconv.ParseInt(s, 10, 64) / strconv.Atoi
+    v = _atoi(s) if isinstance(s, str) else None
+    return v if v is not None and -(1 << 63) <= v < (1 << 63) else None
+
+
 def GetAllocation(pod: dict) -> Dict[int, int]:  # nodeinfo.go:244-271
+    """json.Unmarshal into map[int]map[string]int, then strconv.Atoi of every inner key. ANY decoding error — an outer
+    key that is not an integer, a value whose JSON literal is not a plain integer (2.0 and 2e0 are refused for a Go
+    int), a non-object where an object is expected — makes the reference return the empty map, and the caller then
+    falls back to the IDX annotation (nodeinfo.go:168-196). null is accepted where Go accepts it (nil map / zero)."""
     ann = (pod.get("metadata") or {}).get("annotations")
     if ann is None or gpushareAllocationFlag not in ann:
         return {}
     try:
-        allocation = json.loads(ann[gpushareAllocationFlag])
-        out: Dict[int, int] = {}
-        for _, containerAllocation in allocation.items():
-            for id_, gpuMem in containerAllocation.items():
-                idx = _atoi(id_)
-                if idx is None:
-                    return {}
-                out[idx] = out.get(idx, 0) + int(gpuMem)
-        return out
-    except (ValueError, AttributeError, TypeError):
+        doc = json.loads(ann[gpushareAllocationFlag], parse_int=lambda lit: ("i", lit), parse_float=lambda lit: ("f", lit))
+    except ValueError:
         return {}
+    if doc is None:
+        return {}
+    if not isinstance(doc, dict):
+        return {}
+    decoded = []
+    for outer_key, containerAllocation in doc.items():
+        if _parse_int64(outer_key) is None:
+            return {}
+        if containerAllocation is None:
+            continue
+        if not isinstance(containerAllocation, dict):
+            return {}
+        for id_, gpuMem in containerAllocation.items():
+            if gpuMem is None:
+                decoded.append((id_, 0))
+            elif isinstance(gpuMem, tuple) and gpuMem[0] == "i" and not gpuMem[1].startswith("+") and _parse_int64(gpuMem[1]) is not None:
+                decoded.append((id_, int(gpuMem[1])))
+            else:
+                return {}
+    out: Dict[int, int] = {}
+    for id_, gpuMem in decoded:
+        idx = _parse_int64(id_)
+        if idx is None:
+            return {}  # nodeinfo.go:263-266
+        out[idx] = out.get(idx, 0) + gpuMem
+    return out
 
 
 class DeviceInfo:

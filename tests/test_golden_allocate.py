@@ -90,3 +90,109 @@ def test_tie_order_of_go110_sort_product_vs_oracle_randomised():
         got = pods[pidx.value]["metadata"]["uid"] if pidx.value >= 0 else None
         assert got == (matched["metadata"]["uid"] if matched else None), (trial, n, times, sizes)
         assert wo.unmarshal_AllocateResponse(buf.raw[: nn.value]) == envs
+
+
+# ---- the same frozen answers through the DAEMONS, end to end -------------------------------------------------------
+# gsbd turns the apiserver's pod JSON into the gsb_pod table with its own C++ code (csrc/daemon/gsbd_pods.hpp: Atoi,
+# ParseUint, quantity values, node filter) — a third implementation of podutils.go next to the oracle's and the Python
+# front end's. Every frozen case that fits the synthetic 8-GPU node (default ctx: 179 GiB slices, minors 2,3,0,1,6,7,4,5)
+# is replayed through a real gsbd: mock apiserver holding the case's pods -> gRPC Allocate -> decoded envs and the
+# annotation PATCH on exactly the pod the oracle matched.
+
+def _daemon_cases():
+    from tests import fakes
+    want_map = dict(zip(fakes.UUIDS, fakes.MINORS))
+    return [c for c in GOLD["cases"]
+            if c["ctx"]["devNameMap"] == want_map and c["ctx"]["slices"] == 179 and c["ctx"]["unit"] == "GiB"
+            and not c["ctx"]["disable_cgpu_isolation"]]
+
+
+def _load_case(kube, case, tag=""):
+    """`tag` makes the UIDs of this case unique for the daemon's lifetime: a pod this daemon handed out is never a
+    candidate again under the same UID (its double-hand-out guard), and the fixture reuses uid-0, uid-1 ... per case."""
+    with kube.lock:
+        kube.pods.clear()
+        kube.order.clear()
+        for i, p in enumerate(copy.deepcopy(case["pods"])):
+            if "uid" in p["metadata"]:
+                p["metadata"]["uid"] = tag + p["metadata"]["uid"]
+            key = (p["metadata"].get("namespace", "default"), p["metadata"]["name"])
+            if key in kube.pods:  # duplicate-UID cases reuse nothing else; names are unique in the fixture
+                key = (key[0], key[1] + "-%d" % i)
+            kube.pods[key] = p
+            kube.order.append(key)
+
+
+def _check_case(kube, case, envs):
+    want = case["want"]
+    assert envs == want["envs"], case["name"]
+    patched = sorted(k[1] for k, p in kube.pods.items()
+                     if (p["metadata"].get("annotations") or {}).get(wo.EnvAssignedFlag) == "true"
+                     and not any((q["metadata"].get("annotations") or {}).get(wo.EnvAssignedFlag) == "true"
+                                 and q["metadata"]["name"] == p["metadata"]["name"] for q in case["pods"]))
+    if want["matched_uid"] is None:
+        assert patched == [], (case["name"], patched)
+    else:
+        matched_name = next(p["metadata"]["name"] for p in case["pods"] if p["metadata"]["uid"] == want["matched_uid"])
+        assert patched == [matched_name], (case["name"], patched, matched_name)
+
+
+def test_native_daemon_gives_the_frozen_answers_end_to_end(tmp_path):
+    import signal
+    from gpushare_device_plugin_b200.testing.fake_kubelet import FakeKubelet
+    from gpushare_device_plugin_b200.testing.mock_kube import MockKube, make_node
+    gsbd = os.environ.get("GSBD_BINARY") or os.path.join(ROOT, "gpushare_device_plugin_b200", "gsbd")
+    if not os.access(gsbd, os.X_OK):
+        pytest.skip("gsbd not built")
+    cases = _daemon_cases()
+    assert len(cases) >= 45
+    kube = MockKube(make_node("b200-0"), [])
+    kubelet = FakeKubelet(str(tmp_path))
+    env = dict(os.environ, NODE_NAME="b200-0", GPUSHARE_PLUGIN_DIR=str(tmp_path) + "/", GPUSHARE_RETRY_SLEEP_MS="1",
+               GSBD_ALLOW_FAKE_INVENTORY="1")
+    env.pop("KUBECONFIG", None)
+    log = open(tmp_path / "gsbd.log", "w")
+    # LIST per call (the reference's behaviour): the table is rebuilt from the case's pods on every request
+    proc = subprocess.Popen([gsbd, "--v=5", "--fake-inventory", "8", "--kube-api-url", kube.url, "--pod-informer=false",
+                             "--pod-cache-ttl", "0"], env=env, stderr=log, stdout=log)
+    try:
+        kubelet.register_requests.get(timeout=20)
+        ch = kubelet.channel("aliyungpushare.sock")
+        for n, case in enumerate(cases):
+            _load_case(kube, case, "c%d-" % n)
+            raw = kubelet.allocate(ch, wo.marshal_AllocateRequest(case["container_requests"]))
+            _check_case(kube, case, wo.unmarshal_AllocateResponse(raw))
+            assert raw.hex() == case["want"]["response_hex"]
+        ch.close()
+    finally:
+        proc.send_signal(signal.SIGTERM)
+        proc.wait(timeout=10)
+        log.close()
+        kubelet.stop()
+        kube.close()
+
+
+def test_python_front_end_gives_the_frozen_answers_end_to_end(tmp_path, monkeypatch):
+    import time
+    from gpushare_device_plugin_b200.nvidia import kubeclient, podmanager, server
+    from gpushare_device_plugin_b200.testing.fake_kubelet import FakeKubelet
+    from gpushare_device_plugin_b200.testing.mock_kube import MockKube, make_node
+    from tests import fakes
+    fakes.install(monkeypatch)
+    monkeypatch.setattr(time, "sleep", lambda s: None)
+    kube = MockKube(make_node("b200-0", labels={}), [])
+    podmanager.kubeInit(kubeclient.Clientset(kube.url), "b200-0")
+    kubelet = FakeKubelet(str(tmp_path))
+    p = server.NewNvidiaDevicePlugin(False, False, False, None, socket=str(tmp_path / "aliyungpushare.sock"), pod_cache_ttl=0)
+    try:
+        p.Serve(kubelet.socket)
+        ch = kubelet.channel("aliyungpushare.sock")
+        for n, case in enumerate(_daemon_cases()):
+            _load_case(kube, case, "c%d-" % n)
+            raw = kubelet.allocate(ch, wo.marshal_AllocateRequest(case["container_requests"]))
+            _check_case(kube, case, wo.unmarshal_AllocateResponse(raw))
+        ch.close()
+    finally:
+        p.Stop()
+        kubelet.stop()
+        kube.close()
