@@ -989,7 +989,12 @@ int gsb_shutdown(void) {
   for (auto &d : G.devs) {
     worker_stop(d.get());
     std::lock_guard<std::mutex> dl(d->mu);
-    arena_destroy_locked(d.get());
+    const bool still_wedged = arena_destroy_locked(d.get()) == GSB_ERR_TIMEOUT;
+    if (d->ready && still_wedged) {
+      // cudaFree and cudaStreamDestroy wait for the device: under a launch that never ends they would hang the
+      // shutdown for ever. The resources go with the process / the context instead.
+      d->ready = false;
+    }
     if (d->ready) {
       cudaSetDevice(d->ordinal);
       cudaStreamDestroy(d->stream);

@@ -380,7 +380,9 @@ def list_and_watch_stream(devs: List[List[str]], unhealthy_events: List[int]) ->
 
 def quantity_value(q) -> int:
     """resource.Quantity.Value() for the forms a gpu-mem limit takes: integers, optionally with a
-    decimal-SI or binary-SI suffix; fractional values round up (Value() rounds away from zero)."""
+    decimal-SI or binary-SI suffix; fractional values round up. (Value() rounds AWAY FROM ZERO; this restatement — and
+    the product's — rounds up, which differs only for negative fractional quantities; the apiserver refuses negative
+    resource limits at admission, so no pod the plugin can see carries one.)"""
     if isinstance(q, int):
         return q
     s = str(q).strip()
