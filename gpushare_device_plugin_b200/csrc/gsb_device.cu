@@ -989,7 +989,12 @@ int gsb_shutdown(void) {
   for (auto &d : G.devs) {
     worker_stop(d.get());
     std::lock_guard<std::mutex> dl(d->mu);
-    const bool still_wedged = arena_destroy_locked(d.get()) == GSB_ERR_TIMEOUT;
+    bool still_wedged = false;
+    if (d->ready && d->wedged) {
+      cudaSetDevice(d->ordinal);
+      still_wedged = cudaStreamQuery(d->stream) == cudaErrorNotReady;
+    }
+    if (!still_wedged) arena_destroy_locked(d.get());
     if (d->ready && still_wedged) {
       // cudaFree and cudaStreamDestroy wait for the device: under a launch that never ends they would hang the
       // shutdown for ever. The resources go with the process / the context instead.
