@@ -203,3 +203,26 @@ def test_transient_window_kept_by_a_wedged_launch_is_given_back_once_the_stream_
         gsb.set_option(_abi.GSB_OPT_WATCHDOG_MS, 2000)
         gsb.shutdown()
         gsb.init()
+
+
+def test_shutdown_does_not_wait_for_a_wedged_device(gsb):
+    """cudaFree / cudaStreamDestroy wait for the device; under a launch that never ends they would hang the daemon's
+    shutdown (SIGTERM, SIGHUP restart) for ever. A wedged device's resources are left to the process instead."""
+    gsb.arena_create(0, max_bytes=128 << 20)
+    gsb.set_option(_abi.GSB_OPT_WATCHDOG_MS, 100)
+    cyc = gsb.Cycler(0, window_bytes=64 << 20)
+    assert cyc.step().healthy == 1
+    gsb.test_stall(0, 2500)
+    cyc.step(raise_on_error=False)
+    assert cyc.rc == _abi.GSB_ERR_TIMEOUT
+    t0 = time.monotonic()
+    gsb.shutdown()
+    took = time.monotonic() - t0
+    gsb.init()
+    assert took < 1.0, took  # the stall had ~2.3 s to go
+    assert gsb.get_option(_abi.GSB_OPT_WATCHDOG_MS) == 100  # options are process-wide, not per init
+    gsb.set_option(_abi.GSB_OPT_WATCHDOG_MS, 2000)
+    time.sleep(2.5)  # let the orphaned stall drain before the next test touches the device
+    gsb.arena_create(0, max_bytes=64 << 20)
+    assert gsb.probe(0, _abi.GSB_OP_VERIFY, flags=3).mismatch_words == 0
+    gsb.arena_destroy(0)
