@@ -50,6 +50,9 @@ def parse(argv):
     add("probe-period-ms", default=1000, type=int)
     add("probe-window-mib", default=1024, type=int)
     add("probe-arena-mib", default=0, type=int)  # 0 = transient window per cycle, nothing held
+    add("probe-keep-free-mib", default=1024, type=int)
+    add("probe-watchdog-ms", default=2000, type=int)
+    add("inventory-refresh-ms", default=5000, type=int)
     add("startup-full-walk", default=False, **b)
     add("health-recovery-cycles", default=0, type=int)
     return p.parse_args(argv)
@@ -88,7 +91,9 @@ def main(argv=None) -> None:  # main.go:55-65
                               dumpDir=os.environ.get("GPUSHARE_DUMP_DIR", "/etc/kubernetes/"),
                               probe_period_ms=a.probe_period_ms, window_bytes=a.probe_window_mib << 20,
                               probe_arena_bytes=a.probe_arena_mib << 20, startup_full_walk=a.startup_full_walk,
-                              health_recovery_cycles=a.health_recovery_cycles)
+                              health_recovery_cycles=a.health_recovery_cycles,
+                              probe_keep_free_bytes=a.probe_keep_free_mib << 20, probe_watchdog_ms=a.probe_watchdog_ms,
+                              inventory_refresh_ms=a.inventory_refresh_ms)
     ngm.Run()
 
 

@@ -35,7 +35,8 @@ class NvidiaDevicePlugin:
                  coalesce_health: bool = True, probe_period_ms: int = 1000, window_bytes: int = device.GiB,
                  max_workers: int = 16, pod_cache_ttl: float = 1.0, inventory=None,
                  probe_arena_bytes: int = 0, startup_full_walk: bool = False,
-                 health_recovery_cycles: int = 0):
+                 health_recovery_cycles: int = 0, probe_keep_free_bytes: int = device.GiB,
+                 probe_watchdog_ms: int = 2000, inventory_refresh_ms: int = 5000):
         # `inventory` = (devs, devNameMap) injects a synthetic node (tests, Allocate benchmark)
         self.devs, self.devNameMap = inventory if inventory is not None else nvidia.getDevices()  # server.go:39
         devList = list(self.devNameMap)
@@ -51,6 +52,8 @@ class NvidiaDevicePlugin:
         self.probe_period_ms, self.window_bytes = probe_period_ms, window_bytes
         self.probe_arena_bytes, self.startup_full_walk = probe_arena_bytes, startup_full_walk
         self.health_recovery_cycles = health_recovery_cycles
+        self.probe_keep_free_bytes, self.probe_watchdog_ms = probe_keep_free_bytes, probe_watchdog_ms
+        self.inventory_refresh_ms = inventory_refresh_ms
         self.max_workers = max_workers
         self.stop = threading.Event()
         self.lock = threading.RLock()  # sync.RWMutex of server.go:34; Allocate takes it exclusively
@@ -179,7 +182,10 @@ class NvidiaDevicePlugin:
     def healthcheck(self) -> None:
         if self.healthCheck:
             if self.probe_period_ms > 0:
-                self.setup_probe_arenas()
+                self.setup_probe_arenas(self.probe_keep_free_bytes)
+            from .._abi import GSB_OPT_INVENTORY_REFRESH_MS, GSB_OPT_WATCHDOG_MS
+            device.set_option(GSB_OPT_WATCHDOG_MS, self.probe_watchdog_ms)
+            device.set_option(GSB_OPT_INVENTORY_REFRESH_MS, self.inventory_refresh_ms)
             nvidia.watchXIDs(self.stop, self.devs, self.unhealthy, self.probe_period_ms, self.window_bytes,
                              self.recovered, self.health_recovery_cycles)
         else:
