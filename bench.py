@@ -725,6 +725,10 @@ def bench_ours(args) -> None:
             "e2e_value": args.transient_steps * world / tr_wall_s, "unit": UNIT, "steps": args.transient_steps,
             "ms_per_step": tr_wall_s * 1e3 / args.transient_steps, "kernel_ms_per_step": tr["kernel_ns"] / 1e6 / args.transient_steps,
             "alloc_map_free_ms_per_step": (tr["wall_ns"] - tr["kernel_ns"]) / 1e6 / args.transient_steps,
+            "roofline": {"bound": "hbm", "achieved": 2 * window * args.transient_steps / (tr["kernel_ns"] / 1e9) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": 2 * window * args.transient_steps / (tr["kernel_ns"] / 1e9) / 1e9 / peak,
+                         "kernels": "probe_bulk_dyn<FILL> (W written) + probe_bulk<VERIFY> (W read), two launches",
+                         "algorithmic_bytes_per_cycle": 2 * window},
             "per_step_rank0": {"p50_ms": tr["p50_ms"], "p99_ms": tr["p99_ms"], "max_ms": tr["max_ms"]},
             "bytes_walked": tl.probe.bytes_walked, "transient_flag": tl.transient,
             "what": "no standing arena (the daemon's default): per cycle cuMemCreate + map of one window, FILL, VERIFY, unmap + "

@@ -55,6 +55,9 @@ if [ "$MODE" = lab ]; then
   # one full capture of the shipped refill kernel on a 1 GiB window (profiles/ncu_window_r02_*), and of the shipped VERIFY
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:probe_bulk_dyn -c 2 -o $OUT/ncu_window_dyn_r02 \
     python tools/profile_target.py 5 4 > $OUT/ncu_full.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:probe_bulk -c 4 -o $OUT/ncu_transient_r02 \
+    python tools/profile_target.py 0 2 transient > $OUT/ncu_transient.log 2>&1
+  ncu -i $OUT/ncu_transient_r02.ncu-rep --page raw --csv > $OUT/ncu_transient_r02_raw.csv 2>/dev/null
   ncu -i $OUT/ncu_window_dyn_r02.ncu-rep --page raw --csv > $OUT/ncu_window_dyn_r02_raw.csv 2>/dev/null
   ncu -i $OUT/ncu_window_dyn_r02.ncu-rep --page details --csv > $OUT/ncu_window_dyn_r02_details.csv 2>/dev/null
   tail -5 $OUT/sweep_r02.log
