@@ -44,7 +44,7 @@ GSB_INVENTORY_IDENTITY_CHANGED, GSB_INVENTORY_TOTAL_CHANGED = 1, 2
 GSB_ABI_VERSION = 2
 GSB_ALL_DEVICES = 0xFFFFFFFF
 GSB_OPT_INVENTORY_POLICY, GSB_OPT_WAIT_SPIN_US, GSB_OPT_WATCHDOG_MS, GSB_OPT_INVENTORY_REFRESH_MS, \
-    GSB_OPT_TRANSIENT_KEEP_FREE_BYTES = 1, 2, 3, 4, 5
+    GSB_OPT_TRANSIENT_KEEP_FREE_BYTES, GSB_OPT_SWEEP_EVERY_CYCLES = 1, 2, 3, 4, 5, 6
 GSB_INVENTORY_SNAPSHOT, GSB_INVENTORY_LIVE = 0, 1
 GSB_ALLOC_MATCHED, GSB_ALLOC_SINGLE_GPU, GSB_ALLOC_ERR_RESPONSE = 1, 2, 3
 UINT64_MAX = (1 << 64) - 1
@@ -57,7 +57,8 @@ SYMBOLS = [
     "gsb_encode_list_and_watch", "gsb_encode_register_request",
     "gsb_arena_create", "gsb_arena_destroy", "gsb_arena_bytes", "gsb_probe", "gsb_probe_all",
     "gsb_arena_read", "gsb_arena_write", "gsb_test_stall", "gsb_test_skew_snapshot", "gsb_cycle", "gsb_cycle_all",
-    "gsb_health_start", "gsb_health_stop", "gsb_health_wait", "gsb_health_inject", "gsb_health_set_recovery", "gsb_xid_is_benign",
+    "gsb_health_start", "gsb_health_stop", "gsb_health_wait", "gsb_health_inject", "gsb_health_set_recovery", "gsb_health_stats_get",
+    "gsb_xid_is_benign",
     "gsb_allocate", "gsb_allocate_err_response", "gsb_patch_assigned_body",
 ]
 
@@ -124,6 +125,11 @@ class CycleResult(C.Structure):
         ("inventory_live", C.c_uint32),
         ("transient", C.c_uint32),
     ]
+
+
+class HealthStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("cycles", "sweeps", "skipped", "faults", "last_bytes_walked", "last_kernel_ns",
+                                          "last_sweep_bytes", "last_sweep_ns")]
 
 
 class Event(C.Structure):
@@ -205,6 +211,7 @@ def _load() -> C.CDLL:
         "gsb_health_wait": (C.c_int, [C.c_uint32, C.POINTER(Event)]),
         "gsb_health_inject": (C.c_int, [C.POINTER(Event)]),
         "gsb_health_set_recovery": (C.c_int, [C.c_uint32]),
+        "gsb_health_stats_get": (C.c_int, [C.c_uint32, C.POINTER(HealthStats)]),
         "gsb_xid_is_benign": (C.c_int, [C.c_uint64]),
         "gsb_allocate": (C.c_int, [C.POINTER(AllocateCtx), C.POINTER(Pod), C.c_uint32, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int32), u32p]),
         "gsb_allocate_err_response": (C.c_int, [C.POINTER(AllocateCtx), C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),

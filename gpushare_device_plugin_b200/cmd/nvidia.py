@@ -53,6 +53,7 @@ def parse(argv):
     add("probe-keep-free-mib", default=1024, type=int)
     add("probe-watchdog-ms", default=2000, type=int)
     add("inventory-refresh-ms", default=5000, type=int)
+    add("probe-sweep-every", default=0, type=int)
     add("startup-full-walk", default=False, **b)
     add("health-recovery-cycles", default=0, type=int)
     return p.parse_args(argv)
@@ -93,7 +94,7 @@ def main(argv=None) -> None:  # main.go:55-65
                               probe_arena_bytes=a.probe_arena_mib << 20, startup_full_walk=a.startup_full_walk,
                               health_recovery_cycles=a.health_recovery_cycles,
                               probe_keep_free_bytes=a.probe_keep_free_mib << 20, probe_watchdog_ms=a.probe_watchdog_ms,
-                              inventory_refresh_ms=a.inventory_refresh_ms)
+                              inventory_refresh_ms=a.inventory_refresh_ms, probe_sweep_every=a.probe_sweep_every)
     ngm.Run()
 
 

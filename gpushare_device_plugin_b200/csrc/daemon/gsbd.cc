@@ -335,6 +335,7 @@ class Plugin {
       gsb_health_set_recovery((uint32_t)f_.health_recovery_cycles);
       gsb_set_option(GSB_OPT_WATCHDOG_MS, (uint64_t)f_.probe_watchdog_ms);
       gsb_set_option(GSB_OPT_INVENTORY_REFRESH_MS, (uint64_t)f_.inventory_refresh_ms);
+      gsb_set_option(GSB_OPT_SWEEP_EVERY_CYCLES, (uint64_t)(f_.probe_sweep_every > 0 ? f_.probe_sweep_every : 0));
       if (gsb_health_start((uint32_t)f_.probe_period_ms, (uint64_t)f_.probe_window_mib << 20) != GSB_OK) {
         // nvidia.go:114-116: a registration error other than "Not Supported" is log.Fatalf
         logf('F', "Fatal error: %s", last_error().c_str());
@@ -342,9 +343,21 @@ class Plugin {
         _exit(255);
       }
     }
+    std::vector<uint64_t> sweeps_seen(uuids_.size(), 0);
     while (!stopping_) {
       gsb_event ev;
       const int rc = gsb_health_wait(5000, &ev);  // nvidia.go:126
+      if (f_.fake_inventory == 0 && f_.probe_sweep_every > 0) {  // what each sweep found actually allocatable
+        for (uint32_t i = 0; i < uuids_.size(); i++) {
+          gsb_health_stats st;
+          if (gsb_health_stats_get(i, &st) == GSB_OK && st.sweeps > sweeps_seen[i]) {
+            sweeps_seen[i] = st.sweeps;
+            INFO("sweep %llu of %s: %llu bytes actually allocatable walked clean-or-not in %.1f ms (%llu faults so far)",
+                 (unsigned long long)st.sweeps, uuids_[i].c_str(), (unsigned long long)st.last_sweep_bytes,
+                 st.last_sweep_ns / 1e6, (unsigned long long)st.faults);
+          }
+        }
+      }
       if (rc != GSB_OK) continue;                 // timeout / stopped
       if (ev.etype == GSB_EVENT_INVENTORY) {  // the low-rate NVML refresh no longer agrees with what is advertised
         WARN("inventory of %s changed under the plugin (%s): marking it unhealthy; SIGHUP re-reads it", ev.uuid,

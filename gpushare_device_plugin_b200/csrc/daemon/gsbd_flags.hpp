@@ -20,7 +20,7 @@ struct Flags {
   int kubelet_port = 10250, timeout = 10;
   // additions (active probe, test hooks); none changes the wire contract
   int probe_period_ms = 1000, probe_window_mib = 1024, probe_arena_mib = 0, probe_keep_free_mib = 1024, fake_inventory = 0;
-  int probe_watchdog_ms = 2000, inventory_refresh_ms = 5000;
+  int probe_watchdog_ms = 2000, inventory_refresh_ms = 5000, probe_sweep_every = 0;
   int health_recovery_cycles = 0;  // 0 = the reference's sticky Unhealthy
   bool startup_full_walk = false, coalesce_health = true, pod_informer = true;
   bool serialize_allocate = false;  // the reference's plugin-wide lock across the whole Allocate, PATCH included
@@ -52,6 +52,7 @@ void usage(const char *prog) {
       {"-probe-arena-mib int", "Standing HBM probe arena per GPU in MiB, held by the plugin and not available to tenants; 0 = hold nothing, probe a transient window per cycle (default 0)"},
       {"-probe-keep-free-mib int", "Free HBM per GPU that no probe allocation (window, arena or start-up walk) ever takes (default 1024)"},
       {"-probe-period-ms int", "Period of the HBM health probe per GPU (default 1000)"},
+      {"-probe-sweep-every int", "Every Nth probe cycle of a GPU without a standing arena walks ALL HBM that is allocatable at that moment (minus -probe-keep-free-mib) instead of one window, then gives it back; 0 = never (default 0)"},
       {"-probe-watchdog-ms int", "A probe launch still running after this long (+1 ms per 10 MB of window) marks the GPU unhealthy; 0 = wait for ever (default 2000)"},
       {"-probe-window-mib int", "HBM bytes verified and re-written per probe cycle (default 1024)"},
       {"-query-kubelet", "Query pending pods from kubelet instead of kube-apiserver"},
@@ -117,6 +118,7 @@ int parse_flags(int argc, char **argv, Flags *f) {
     else if (name == "probe-window-mib") { if (!need()) return 3; f->probe_window_mib = atoi(val.c_str()); }
     else if (name == "probe-arena-mib") { if (!need()) return 3; f->probe_arena_mib = atoi(val.c_str()); }
     else if (name == "probe-keep-free-mib") { if (!need()) return 3; f->probe_keep_free_mib = atoi(val.c_str()); }
+    else if (name == "probe-sweep-every") { if (!need()) return 3; f->probe_sweep_every = atoi(val.c_str()); }
     else if (name == "probe-watchdog-ms") { if (!need()) return 3; f->probe_watchdog_ms = atoi(val.c_str()); }
     else if (name == "inventory-refresh-ms") { if (!need()) return 3; f->inventory_refresh_ms = atoi(val.c_str()); }
     else if (name == "health-recovery-cycles") { if (!need()) return 3; f->health_recovery_cycles = atoi(val.c_str()); }

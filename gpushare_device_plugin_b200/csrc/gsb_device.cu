@@ -179,6 +179,7 @@ struct Device {
   // the CUDA side; gsb_device_info_get / gsb_inventory_refresh / the low-rate refresher rewrite it.
   std::mutex smu;
   Snapshot snap;
+  gsb_health_stats hstats{};  // prober thread of this device; guarded by smu
 
   // persistent worker (gsb_cycle_all / gsb_probe_all): one host thread per device
   std::thread worker;
@@ -206,6 +207,7 @@ struct Global {
   std::atomic<uint64_t> watchdog_ms{2000};
   std::atomic<uint64_t> inventory_refresh_ms{5000};
   std::atomic<uint64_t> transient_keep_free{1ull << 30};
+  std::atomic<uint64_t> sweep_every{0};
 
   // node cycle (gsb_cycle_all / gsb_probe_all): one at a time; scratch of the join lives here, not on the heap per call
   std::mutex all_mu;
@@ -1214,6 +1216,7 @@ int gsb_set_option(uint32_t key, uint64_t value) {
     case GSB_OPT_WATCHDOG_MS: G.watchdog_ms = value; return GSB_OK;
     case GSB_OPT_INVENTORY_REFRESH_MS: G.inventory_refresh_ms = value; return GSB_OK;
     case GSB_OPT_TRANSIENT_KEEP_FREE_BYTES: G.transient_keep_free = value; return GSB_OK;
+    case GSB_OPT_SWEEP_EVERY_CYCLES: G.sweep_every = value; return GSB_OK;
     default: set_error("unknown option %u", key); return GSB_ERR_INVALID_ARGUMENT;
   }
 }
@@ -1226,8 +1229,19 @@ int gsb_get_option(uint32_t key, uint64_t *value) {
     case GSB_OPT_WATCHDOG_MS: *value = G.watchdog_ms; return GSB_OK;
     case GSB_OPT_INVENTORY_REFRESH_MS: *value = G.inventory_refresh_ms; return GSB_OK;
     case GSB_OPT_TRANSIENT_KEEP_FREE_BYTES: *value = G.transient_keep_free; return GSB_OK;
+    case GSB_OPT_SWEEP_EVERY_CYCLES: *value = G.sweep_every; return GSB_OK;
     default: set_error("unknown option %u", key); return GSB_ERR_INVALID_ARGUMENT;
   }
+}
+
+int gsb_health_stats_get(uint32_t idx, gsb_health_stats *out) {
+  std::shared_lock<std::shared_mutex> api_lk(G.api_mu);
+  if (!out) return GSB_ERR_INVALID_ARGUMENT;
+  Device *d = device_at(idx);
+  if (!d) return G.inited ? GSB_ERR_NO_DEVICE : GSB_ERR_NOT_INITIALIZED;
+  std::lock_guard<std::mutex> lk(d->smu);
+  *out = d->hstats;
+  return GSB_OK;
 }
 
 int gsb_inventory_refresh(uint32_t idx) {
@@ -1534,9 +1548,33 @@ int gsb_health_start(uint32_t probe_period_ms, uint64_t window_bytes) {
         uint64_t cycle = 0;
         bool reported = false;
         uint32_t clean = 0;
+        {
+          std::lock_guard<std::mutex> sl(G.devs[i]->smu);
+          G.devs[i]->hstats = gsb_health_stats{};
+        }
         while (!G.health_stop.load()) {
           gsb_cycle_result cr;
-          int rc = gsb_cycle(i, cycle++, window_bytes, 1, GSB_VARIANT_AUTO, buf.data(), buf.size(), &cr);
+          // every Nth cycle of a device WITHOUT a standing arena is a sweep: a transient window as large as whatever is
+          // allocatable right now (minus the keep-free margin) — all free HBM walked, then given back (SURVEY §7
+          // hard-part 2: "full walk only at start-up / idle"). With a standing arena the request is just a whole-arena cycle.
+          const uint64_t every = G.sweep_every.load(std::memory_order_relaxed);
+          const bool sweep = every > 0 && window_bytes > 0 && (cycle + 1) % every == 0;
+          const uint64_t t_cycle = now_ns();
+          int rc = gsb_cycle(i, cycle++, sweep ? (1ull << 46) : window_bytes, 1, GSB_VARIANT_AUTO, buf.data(), buf.size(), &cr);
+          {
+            std::lock_guard<std::mutex> sl(G.devs[i]->smu);
+            gsb_health_stats &st = G.devs[i]->hstats;
+            st.cycles++;
+            st.last_bytes_walked = cr.probe.bytes_walked;
+            st.last_kernel_ns = cr.probe.kernel_ns;
+            if (cr.probe.status == GSB_ERR_OUT_OF_MEMORY) st.skipped++;
+            if (!(rc == GSB_OK && cr.probe.mismatch_words == 0) && rc != GSB_ERR_NO_ARENA) st.faults++;
+            if (sweep && cr.transient) {
+              st.sweeps++;
+              st.last_sweep_bytes = cr.probe.bytes_walked;
+              st.last_sweep_ns = now_ns() - t_cycle;
+            }
+          }
           // with no standing arena the cycle probes a transient window (allocate -> fill -> verify -> free); a
           // window that could not be allocated (tenants hold the HBM) is silence, not a fault
           const bool this_cycle_clean = rc == GSB_OK && cr.probe.mismatch_words == 0;

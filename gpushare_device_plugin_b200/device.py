@@ -232,6 +232,13 @@ def health_wait(timeout_ms: int) -> Optional[Event]:
     return ev
 
 
+def health_stats(idx: int) -> "_abi.HealthStats":
+    """What the prober thread of device `idx` has done since health_start: cycles, sweeps, skips, faults, last sizes."""
+    st = _abi.HealthStats()
+    check(lib.gsb_health_stats_get(idx, C.byref(st)), f"gsb_health_stats_get({idx})")
+    return st
+
+
 def health_inject(uuid: str, etype: int, edata: int) -> None:
     ev = Event(uuid.encode(), etype, edata)
     check(lib.gsb_health_inject(C.byref(ev)), "gsb_health_inject")

@@ -36,7 +36,7 @@ class NvidiaDevicePlugin:
                  max_workers: int = 16, pod_cache_ttl: float = 1.0, inventory=None,
                  probe_arena_bytes: int = 0, startup_full_walk: bool = False,
                  health_recovery_cycles: int = 0, probe_keep_free_bytes: int = device.GiB,
-                 probe_watchdog_ms: int = 2000, inventory_refresh_ms: int = 5000):
+                 probe_watchdog_ms: int = 2000, inventory_refresh_ms: int = 5000, probe_sweep_every: int = 0):
         # `inventory` = (devs, devNameMap) injects a synthetic node (tests, Allocate benchmark)
         self.devs, self.devNameMap = inventory if inventory is not None else nvidia.getDevices()  # server.go:39
         devList = list(self.devNameMap)
@@ -53,7 +53,7 @@ class NvidiaDevicePlugin:
         self.probe_arena_bytes, self.startup_full_walk = probe_arena_bytes, startup_full_walk
         self.health_recovery_cycles = health_recovery_cycles
         self.probe_keep_free_bytes, self.probe_watchdog_ms = probe_keep_free_bytes, probe_watchdog_ms
-        self.inventory_refresh_ms = inventory_refresh_ms
+        self.inventory_refresh_ms, self.probe_sweep_every = inventory_refresh_ms, probe_sweep_every
         self.max_workers = max_workers
         self.stop = threading.Event()
         self.lock = threading.RLock()  # sync.RWMutex of server.go:34; Allocate takes it exclusively
@@ -183,7 +183,8 @@ class NvidiaDevicePlugin:
         if self.healthCheck:
             if self.probe_period_ms > 0:
                 self.setup_probe_arenas(self.probe_keep_free_bytes)
-            from .._abi import GSB_OPT_INVENTORY_REFRESH_MS, GSB_OPT_WATCHDOG_MS
+            from .._abi import GSB_OPT_INVENTORY_REFRESH_MS, GSB_OPT_SWEEP_EVERY_CYCLES, GSB_OPT_WATCHDOG_MS
+            device.set_option(GSB_OPT_SWEEP_EVERY_CYCLES, max(0, self.probe_sweep_every))
             device.set_option(GSB_OPT_WATCHDOG_MS, self.probe_watchdog_ms)
             device.set_option(GSB_OPT_INVENTORY_REFRESH_MS, self.inventory_refresh_ms)
             nvidia.watchXIDs(self.stop, self.devs, self.unhealthy, self.probe_period_ms, self.window_bytes,

@@ -118,7 +118,11 @@ enum {
   GSB_OPT_WATCHDOG_MS = 3,               /* completion watchdog of a probe launch (default 2000, + 1 ns per 10
                                             window bytes); 0 = off (waits for ever) */
   GSB_OPT_INVENTORY_REFRESH_MS = 4,      /* low-rate NVML refresh while health runs (default 5000; 0 = never) */
-  GSB_OPT_TRANSIENT_KEEP_FREE_BYTES = 5  /* HBM a transient probe window never takes (default 1 GiB) */
+  GSB_OPT_TRANSIENT_KEEP_FREE_BYTES = 5, /* HBM a transient probe window never takes (default 1 GiB) */
+  GSB_OPT_SWEEP_EVERY_CYCLES = 6         /* prober, devices without a standing arena: every Nth cycle walks ALL the HBM
+                                            that is allocatable at that moment (minus the keep-free margin) instead of
+                                            one window, then gives it back — SURVEY §7 hard-part 2's "full walk at idle";
+                                            0 = never (default) */
 };
 enum {
   GSB_INVENTORY_SNAPSHOT = 0, /* cycle: NVML's (re)start-time answer + per-cycle CUDA-side identity check */
@@ -286,6 +290,18 @@ int gsb_health_start(uint32_t probe_period_ms, uint64_t window_bytes);
 int gsb_health_stop(void);
 /* ≙ nvml.WaitForEvent(set, timeout) (bindings.go:134-146): GSB_OK + event, or GSB_ERR_TIMEOUT. */
 int gsb_health_wait(uint32_t timeout_ms, gsb_event *ev);
+/* What the prober thread of one device has done since gsb_health_start (counters restart with it). */
+typedef struct gsb_health_stats {
+  uint64_t cycles;            /* probe cycles run */
+  uint64_t sweeps;            /* of which: whole-free-HBM sweeps (GSB_OPT_SWEEP_EVERY_CYCLES) */
+  uint64_t skipped;           /* cycles that found nothing allocatable to probe */
+  uint64_t faults;            /* cycles whose walk was not clean (mismatch, failed or wedged launch) */
+  uint64_t last_bytes_walked; /* of the most recent cycle */
+  uint64_t last_kernel_ns;
+  uint64_t last_sweep_bytes;  /* bytes the most recent sweep walked = what was actually allocatable then */
+  uint64_t last_sweep_ns;     /* host time of that sweep, allocation and release included */
+} gsb_health_stats;
+int gsb_health_stats_get(uint32_t idx, gsb_health_stats *out);
 /* SURVEY.md §8(f) rank 1, optional: after `clean_cycles` consecutive clean probe cycles a GPU that a PROBE
  * verdict had marked unhealthy is reported again with edata = GSB_PROBE_RECOVERED. 0 (default) keeps the
  * reference's behaviour: Unhealthy is sticky (server.go:180 FIXME). XID faults never recover. */

@@ -39,9 +39,9 @@ def test_struct_layouts_match_the_header(tmp_path):
     prog = tmp_path / "layout.c"
     prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "gpushare_b200.h"\n'
                     "int main(void){\n"
-                    'printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(gsb_device_info), sizeof(gsb_probe_cfg), '
+                    'printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(gsb_device_info), sizeof(gsb_probe_cfg), '
                     "sizeof(gsb_probe_result), sizeof(gsb_cycle_result), sizeof(gsb_event), sizeof(gsb_pod), "
-                    "sizeof(gsb_allocate_ctx));\n"
+                    "sizeof(gsb_allocate_ctx), sizeof(gsb_health_stats));\n"
                     'printf("%zu %zu %zu %zu %zu\\n", offsetof(gsb_device_info,total_bytes), offsetof(gsb_probe_result,kernel_ns), '
                     "offsetof(gsb_cycle_result,probe), offsetof(gsb_pod,gpu_idx), offsetof(gsb_allocate_ctx,slices));\n"
                     "return 0;}\n")
@@ -50,7 +50,7 @@ def test_struct_layouts_match_the_header(tmp_path):
     a, b = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()
     assert [int(x) for x in a.split()] == [C.sizeof(t) for t in (_abi.DeviceInfo, _abi.ProbeCfg, _abi.ProbeResult,
                                                                   _abi.CycleResult, _abi.Event, _abi.Pod,
-                                                                  _abi.AllocateCtx)]
+                                                                  _abi.AllocateCtx, _abi.HealthStats)]
     assert [int(x) for x in b.split()] == [_abi.DeviceInfo.total_bytes.offset, _abi.ProbeResult.kernel_ns.offset,
                                            _abi.CycleResult.probe.offset, _abi.Pod.gpu_idx.offset,
                                            _abi.AllocateCtx.slices.offset]

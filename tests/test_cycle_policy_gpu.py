@@ -226,3 +226,29 @@ def test_shutdown_does_not_wait_for_a_wedged_device(gsb):
     gsb.arena_create(0, max_bytes=64 << 20)
     assert gsb.probe(0, _abi.GSB_OP_VERIFY, flags=3).mismatch_words == 0
     gsb.arena_destroy(0)
+
+
+def test_periodic_sweep_walks_everything_allocatable_and_gives_it_back(gsb):
+    """GSB_OPT_SWEEP_EVERY_CYCLES: with no standing arena, every Nth prober cycle is a transient window as large as
+    whatever is allocatable at that moment (minus the keep-free margin): all free HBM is walked — the coverage of the
+    start-up walk, at run time — and given back; the cycles in between stay one window."""
+    with pytest.raises(_abi.GsbError):
+        gsb.arena_bytes(0)
+    free0 = nvml_free()
+    gsb.set_option(_abi.GSB_OPT_SWEEP_EVERY_CYCLES, 4)
+    gsb.health_start(probe_period_ms=10, window_bytes=GiB)
+    try:
+        deadline = time.monotonic() + 20
+        while gsb.health_stats(0).sweeps < 2 and time.monotonic() < deadline:
+            time.sleep(0.1)
+        st = gsb.health_stats(0)
+        assert st.sweeps >= 2 and st.cycles >= 8 and st.faults == 0 and st.skipped == 0
+        assert st.last_sweep_bytes > 150 * GiB and st.last_sweep_bytes <= free0 - GiB + (64 << 20)  # all but the margin
+        assert st.last_sweep_ns < 5e9
+        assert gsb.health_wait(0) is None  # clean sweeps are silent
+    finally:
+        gsb.health_stop()
+        gsb.set_option(_abi.GSB_OPT_SWEEP_EVERY_CYCLES, 0)
+    assert abs(nvml_free() - free0) < 64 << 20  # nothing kept
+    with pytest.raises(_abi.GsbError):
+        gsb.arena_bytes(0)
