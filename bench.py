@@ -55,6 +55,23 @@ WORKLOAD = ("1xB200-per-rank inventory+health cycle: ListAndWatch inventory of 1
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
+def shared_config(n_gpus: int) -> dict:
+    """The `config` object BOTH arms print, key for key and value for value (the reference arm runs "on your arm's
+    config"); everything arm-specific is under `details`."""
+    return {"workload": WORKLOAD, "gpus": n_gpus, "memory_unit": "GiB",
+            "slices": "floor(floor(nvmlMemory_t.total / 2^20) / 1024) per GPU (179 on a B200), one fake device per slice",
+            "cycle": "one cycle of one device = inventory (identity + total -> slices -> fake devices -> ListAndWatchResponse "
+                     "bytes) + one health check; N devices: N such cycles per node cycle",
+            "l2_policy": "ours: inputs larger than L2 — the 1 GiB probe window rotates over an arena of all allocatable HBM, no "
+                         "flush needed; reference: touches no HBM",
+            "value_timing": "ours: `value` = CUDA events around each probe launch on the launching stream, the KERNEL ONLY (no "
+                            "inventory, encode or host cost: value / reference.value is not a speed-up), `e2e` = host wall time "
+                            "around the C-ABI calls, the like-for-like figure; reference: `value` = `e2e` = host monotonic clock "
+                            "around each cycle inside the C binary",
+            "setup": "once-per-plugin-start work (ours: gsb_init + arena map + FILL; reference: nvmlInit + first getDevices + "
+                     "event-set registration) is reported under `setup` on both arms and is in no timed cycle"}
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -433,20 +450,19 @@ def bench_reference(args) -> None:
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean_us * cps / 1e3,
         "ms_per_device_cycle": mean_us / 1e3 / max(n, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "reference_path": f"one cycle = getDevices over the first {n} GPU(s) (11 NVML getters each + fan-out + gogo "
-                                     "marshal, nvidia.go:53-89) + one WaitForEvent(0 ms) on the standing event set "
-                                     "(nvidia.go:126); sequential, 1 thread; the reference moves no HBM bytes. The event-set "
-                                     "registration (S*N RegisterEventForDevice, nvidia.go:104-117) is once per plugin start and "
-                                     "is reported under setup, outside the timed cycles — as our arm's arena set-up is",
-                   "devices_seen": n, "fake_devices": r["n_devices"], "lw_bytes": r["lw_len"],
-                   "cycles_per_step": cps, "cycles_timed": args.steps * cps,
-                   "step": f"one step = a bounded sample of {cps} node cycles (NVML latency on a shared host is too noisy for a "
-                           "20-cycle mean: 2.2 ms idle, 4-7 ms beside a polling nvidia-smi); ms_per_step is the whole sample",
-                   "value_timing": "host monotonic clock around each cycle inside the C binary",
-                   "phases": reference_phases(r),
-                   "pynvml_twin": pynvml_twin(min(args.steps, 50)),
-                   "host": f"{cpu_model()}, nproc={os.cpu_count()}"},
+        "config": shared_config(args.gpus),
+        "details": {"reference_path": f"one cycle = getDevices over the first {n} GPU(s) (11 NVML getters each + fan-out + gogo "
+                                      "marshal, nvidia.go:53-89) + one WaitForEvent(0 ms) on the standing event set "
+                                      "(nvidia.go:126); sequential, 1 thread; the reference moves no HBM bytes. The event-set "
+                                      "registration (S*N RegisterEventForDevice, nvidia.go:104-117) is once per plugin start and "
+                                      "is reported under setup, outside the timed cycles — as our arm's arena set-up is",
+                    "devices_seen": n, "fake_devices": r["n_devices"], "lw_bytes": r["lw_len"],
+                    "cycles_per_step": cps, "cycles_timed": args.steps * cps,
+                    "step": f"one step = a bounded sample of {cps} node cycles (NVML latency on a shared host is too noisy for a "
+                            "20-cycle mean: 2.2 ms idle, 4-7 ms beside a polling nvidia-smi); ms_per_step is the whole sample",
+                    "phases": reference_phases(r),
+                    "pynvml_twin": pynvml_twin(min(args.steps, 50)),
+                    "host": f"{cpu_model()}, nproc={os.cpu_count()}"},
         "setup": reference_phases(r)["setup_once_per_start_us"],
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
                          "sample": f"{args.steps * cps} cycles (+{args.warmup * cps} warm-up) of oracle/_ref/ref_inventory (reference's "
@@ -665,19 +681,14 @@ def bench_ours(args) -> None:
         "metric": METRIC, "value": units / kern_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": kern_s * 1e3 / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "ours_path": f"{last.slices} slices / {last.lw_len} B ListAndWatchResponse + VERIFY_REFILL HBM probe of a "
-                                f"rotating {args.window_gib} GiB window (one advertised slice) over the whole arena",
-                   "window_bytes": window, "arena_bytes": arena, "variant": _abi.VARIANT_NAMES[last.probe.variant],
-                   "grid_ctas": last.probe.grid_ctas, "block_threads": last.probe.block_threads,
-                   "inventory_policy": args.inventory,
-                   "l2_policy": "inputs larger than L2: the window rotates over the whole arena, no flush needed",
-                   "value_timing": "`value` = CUDA events around each probe launch on the launching stream (inside gsb_probe): the "
-                                   "KERNEL ONLY. It excludes the inventory step, the encode and every host cost, so value / "
-                                   "reference.value is not a speed-up; `e2e` (host wall time around the C-ABI call) is the "
-                                   "like-for-like figure",
-                   "replicas": "one independent replica per GPU, no collective (path does not shard)",
-                   "host": f"{cpu_model()}, nproc={os.cpu_count()}"},
+        "config": shared_config(world),
+        "details": {"ours_path": f"{last.slices} slices / {last.lw_len} B ListAndWatchResponse + VERIFY_REFILL HBM probe of a "
+                                 f"rotating {args.window_gib} GiB window (one advertised slice) over the whole arena",
+                    "window_bytes": window, "arena_bytes": arena, "variant": _abi.VARIANT_NAMES[last.probe.variant],
+                    "grid_ctas": last.probe.grid_ctas, "block_threads": last.probe.block_threads,
+                    "inventory_policy": args.inventory,
+                    "replicas": "one independent replica per GPU, no collective (path does not shard)",
+                    "host": f"{cpu_model()}, nproc={os.cpu_count()}"},
         "e2e": {"value": units / wall_s, "unit": UNIT, "ms_per_step": wall_s * 1e3 / args.steps,
                 "p50_value": world / p50_s, "p50_ms_per_step": p50_s * 1e3,
                 "value_incl_closing_barrier": units / wall_incl_s,

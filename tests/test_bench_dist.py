@@ -63,9 +63,12 @@ def test_reference_arm_runs_on_rank0_only():
                          {"LD_LIBRARY_PATH": fake, "FAKE_NVML_GPUS": "8"})  # an 8-GPU box: the arm must see only 2
     assert [p.returncode for p in procs] == [0, 0], outs
     line = json.loads(outs[0][0].strip().splitlines()[-1])
-    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["config"]["devices_seen"] == 2
-    assert line["config"]["fake_devices"] == 358 and line["setup"]["register_calls"] == 179 * 4 + 179 * 6
-    assert set(line["config"]["phases"]["cycle_us"]) >= {"inventory_p50", "health_poll_p50", "cycle_mean"}
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["details"]["devices_seen"] == 2
+    assert line["details"]["fake_devices"] == 358 and line["setup"]["register_calls"] == 179 * 4 + 179 * 6
+    assert set(line["details"]["phases"]["cycle_us"]) >= {"inventory_p50", "health_poll_p50", "cycle_mean"}
     assert line["metric"] == "inventory+health-probe cycles/sec" and line["cpu_baseline"]["kind"] == "reference"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
     assert outs[1][0].strip() == ""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.shared_config(2)  # the very object our own arm prints: same config, key for key
