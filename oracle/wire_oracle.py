@@ -5,12 +5,13 @@ inventory -> fake devices -> wire bytes, the XID filter, and Allocate. Only test
 __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import it; the
 product never does.
 
-Parity status: the reference has NO tests or golden vectors for this path (its only test,
+Parity status — PARITY UNPINNED: the reference has NO tests or golden vectors for this path (its only test,
 pkg/kubelet/client/client_test.go, asserts nothing — SURVEY.md §4), and its Go sources cannot be
 compiled here (no Go toolchain). The known-answer vectors in tests/golden/wire_kat.json are direct
 readings of the cited lines (SURVEY.md §8(c) ①-⑨); the byte-level encoders are additionally checked
 against google.protobuf's own encoder driven by a descriptor built from the reference's api.proto
-field numbers (tests/test_wire_oracle.py).
+field numbers (tests/test_wire.py). Since round 2 the answers are frozen in tests/golden/allocate_cases.json
+(oracle/make_wire_golden.py) so that drift shows up in review; DESIGN.md §4a maps every function to its Go lines.
 
 Every function cites the reference lines it follows (paths relative to /root/reference).
 """
