@@ -195,24 +195,15 @@ def dist_setup(n_gpus: int):
     return rank, world, local, dist
 
 
-_BARRIER_TOKEN = {}
-
-
 def barrier_sync(dist, local):
-    """A barrier across all ranks + torch.cuda.synchronize(). The barrier is an all-reduce of one element that lives on
-    this rank's GPU (allocated once): every rank leaves only after every rank has entered, like dist.barrier(), without
-    that call's per-invocation tensor allocation and device-wide bookkeeping (~0.85 ms per call at N = 8, measured in
-    profiles/bench_r02_8gpu_sampled.json, against a 6.8 ms timed region)."""
+    """dist.barrier() + torch.cuda.synchronize(): one bracket of a timed region. (At N = 8 the NCCL barrier itself takes
+    ~0.85 ms once the ranks arrive together — a one-element all-reduce on a resident tensor measured the same, so it is
+    NCCL's latency, not this call's overhead; 0.2 ms at N = 2. bench reports it per rank as closing_barrier_ms.)"""
     if dist is not None:
         import torch
+        dist.barrier()
         if torch.cuda.is_available():
-            t = _BARRIER_TOKEN.get(local)
-            if t is None:
-                t = _BARRIER_TOKEN[local] = torch.zeros(1, dtype=torch.int32, device=f"cuda:{local}")
-            dist.all_reduce(t)
             torch.cuda.synchronize(local)
-        else:
-            dist.barrier()
 
 
 def aligned_start(dist, local):
