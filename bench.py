@@ -232,8 +232,10 @@ def run_reference_cycles(iters: int, warmup: int, gpus: int = 0, setup_iters: in
     """oracle/_ref/ref_inventory bench over the first `gpus` GPUs (0 = all): health set-up once
     (RegisterEventForDevice per fake device), then `iters` timed cycles of inventory (11 NVML getters/GPU + fan-out +
     marshal) + one WaitForEvent(0 ms) on the standing event set, on 1 pinned host thread."""
-    if not os.access(REF_BIN, os.X_OK):
-        raise RuntimeError("oracle/_ref/ref_inventory missing: run build.sh where /root/reference exists")
+    if not os.access(REF_BIN, os.X_OK) or os.environ.get("GSB_BENCH_FORCE_PORT") == "1":
+        # oracle/_ref is built from the reference's own nvml_dl.c where /root/reference exists and travels with the repo;
+        # should it be missing, the arm does not die: the oracle PORT (pynvml + oracle/wire_oracle.py) runs the same phases
+        return run_reference_cycles_port(iters, warmup, gpus, setup_iters)
     cmd = [REF_BIN, "bench", "--iters", str(iters), "--warmup", str(warmup), "--wait-ms", "0",
            "--setup-iters", str(setup_iters)]
     if gpus:
@@ -242,6 +244,108 @@ def run_reference_cycles(iters: int, warmup: int, gpus: int = 0, setup_iters: in
         cmd = ["taskset", "-c", "0"] + cmd
     out = subprocess.run(cmd, check=True, capture_output=True, text=True, timeout=600)
     return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def run_reference_cycles_port(iters: int, warmup: int, gpus: int = 0, setup_iters: int = 3) -> dict:
+    """The same phases as oracle/ref_inventory.c, as the oracle PORT: NVML through pynvml (an independent binding of the
+    same libnvidia-ml calls), fan-out and gogo marshal through oracle/wire_oracle.py. Single thread. `kind` = "port"."""
+    import pynvml as nv
+    from oracle import wire_oracle as wo
+    t0 = time.perf_counter_ns()
+    nv.nvmlInit()
+    init_us = (time.perf_counter_ns() - t0) / 1e3
+
+    def soft(fn, *a):  # bindings.go: NOT_SUPPORTED => nil value, not an error
+        try:
+            return fn(*a)
+        except nv.NVMLError:
+            return None
+
+    def count():
+        n = nv.nvmlDeviceGetCount()
+        return min(n, gpus) if gpus else n
+
+    def get_devices():  # nvidia.go:53-89 over nvml.NewDevice (nvml.go:297-359)
+        inv = []
+        for i in range(count()):
+            h = nv.nvmlDeviceGetHandleByIndex(i)
+            soft(nv.nvmlDeviceGetName, h)
+            uuid = nv.nvmlDeviceGetUUID(h)
+            minor = nv.nvmlDeviceGetMinorNumber(h)
+            soft(nv.nvmlDeviceGetPowerManagementLimit, h)
+            mem = nv.nvmlDeviceGetMemoryInfo(h)
+            pci = soft(nv.nvmlDeviceGetPciInfo, h)
+            soft(nv.nvmlDeviceGetBAR1MemoryInfo, h)
+            soft(nv.nvmlDeviceGetMaxPcieLinkGeneration, h)
+            soft(nv.nvmlDeviceGetMaxPcieLinkWidth, h)
+            soft(nv.nvmlDeviceGetMaxClockInfo, h, nv.NVML_CLOCK_SM)
+            soft(nv.nvmlDeviceGetMaxClockInfo, h, nv.NVML_CLOCK_MEM)
+            if pci is not None:
+                bus = pci.busId.decode() if isinstance(pci.busId, bytes) else pci.busId
+                try:
+                    with open(f"/sys/bus/pci/devices/{bus.lower()[4:] if len(bus) > 12 else bus.lower()}/numa_node") as f:
+                        f.read()
+                except OSError:
+                    pass
+            uuid = uuid.decode() if isinstance(uuid, bytes) else uuid
+            inv.append({"uuid": uuid, "path": f"/dev/nvidia{minor}", "memory_mib": wo.mib_from_bytes(int(mem.total))})
+        devs, _, _ = wo.getDevices(inv)
+        return devs
+
+    def register_all(devs):  # nvidia.go:101-117 + bindings.go:97-128 (count + linear HandleByIndex/GetUUID scan)
+        es = nv.nvmlEventSetCreate()
+        calls = 0
+        for id_, _health in devs:
+            real = wo.extractRealDeviceID(id_)
+            n = count()
+            calls += 1
+            for i in range(n):
+                h = nv.nvmlDeviceGetHandleByIndex(i)
+                u = nv.nvmlDeviceGetUUID(h)
+                calls += 2
+                if (u.decode() if isinstance(u, bytes) else u) == real:
+                    nv.nvmlDeviceRegisterEvents(h, nv.nvmlEventTypeXidCriticalError, es)
+                    calls += 1
+                    break
+        return es, calls
+
+    t_reg, es, reg_calls, first_inv_us = [], None, 0, 0.0
+    for si in range(max(1, setup_iters)):
+        a = time.perf_counter_ns()
+        devs = get_devices()
+        if si == 0:
+            first_inv_us = (time.perf_counter_ns() - a) / 1e3
+        if es is not None:
+            nv.nvmlEventSetFree(es)
+        b = time.perf_counter_ns()
+        es, reg_calls = register_all(devs)
+        t_reg.append((time.perf_counter_ns() - b) / 1e3)
+    t_inv, t_wait, t_cyc, lw = [], [], [], b""
+    for it in range(-warmup, iters):
+        a = time.perf_counter_ns()
+        devs = get_devices()
+        lw = wo.marshal_ListAndWatchResponse(devs)
+        b = time.perf_counter_ns()
+        try:
+            nv.nvmlEventSetWait_v2(es, 0) if hasattr(nv, "nvmlEventSetWait_v2") else nv.nvmlEventSetWait(es, 0)
+        except nv.NVMLError:
+            pass  # timeout
+        c = time.perf_counter_ns()
+        if it >= 0:
+            t_inv.append((b - a) / 1e3)
+            t_wait.append((c - b) / 1e3)
+            t_cyc.append((c - a) / 1e3)
+    nv.nvmlEventSetFree(es)
+
+    def dist_of(v):
+        v = sorted(v)
+        q = lambda f: v[min(len(v) - 1, int(round(f * (len(v) - 1))))]  # noqa: E731
+        return {"p10": q(.1), "p50": q(.5), "p90": q(.9), "p99": q(.99), "mean": sum(v) / len(v)}
+    return {"mode": "bench", "kind": "port", "iters": iters, "setup_iters": setup_iters, "n_gpus": count(), "gpu_limit": gpus,
+            "n_devices": len(devs), "lw_len": len(lw), "wait_ms": 0, "nvml_init_us": init_us, "first_inventory_us": first_inv_us,
+            "register_calls_per_setup": reg_calls, "register_rc": 0, "wait_rc": 10,
+            "inventory_us": dist_of(t_inv), "health_setup_us": dist_of(t_reg), "health_poll_us": dist_of(t_wait),
+            "cycle_us": dist_of(t_cyc), "total_us": sum(t_cyc)}
 
 
 def reference_phases(r: dict) -> dict:
@@ -467,7 +571,7 @@ def bench_reference(args) -> None:
                     "pynvml_twin": pynvml_twin(min(args.steps, 50)),
                     "host": f"{cpu_model()}, nproc={os.cpu_count()}"},
         "setup": reference_phases(r)["setup_once_per_start_us"],
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": r.get("kind", "reference"),
                          "sample": f"{args.steps * cps} cycles (+{args.warmup * cps} warm-up) of oracle/_ref/ref_inventory (reference's "
                                    f"nvml_dl.c) over {n} GPU(s), taskset -c 0, {cpu_model()}, nproc={os.cpu_count()}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
@@ -584,7 +688,7 @@ def bench_ours(args) -> None:
         # `--impl reference --gpus 1`, so the two numbers agree within host noise
         try:
             r = run_reference_cycles(args.cpu_iters, 3, gpus=1)
-            line_cpu = {"value": r["n_gpus"] * 1e6 / r["cycle_us"]["mean"], "unit": UNIT, "cores": 1, "kind": "reference",
+            line_cpu = {"value": r["n_gpus"] * 1e6 / r["cycle_us"]["mean"], "unit": UNIT, "cores": 1, "kind": r.get("kind", "reference"),
                         "sample": f"{args.cpu_iters} cycles (+3 warm-up) of oracle/_ref/ref_inventory (built with the reference's "
                                   f"nvml_dl.c) over 1 GPU, before this process created a CUDA context: inventory p50 "
                                   f"{r['inventory_us']['p50']} us + poll p50 {r['health_poll_us']['p50']} us per cycle; "

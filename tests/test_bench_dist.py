@@ -72,3 +72,18 @@ def test_reference_arm_runs_on_rank0_only():
     sys.path.insert(0, ROOT)
     import bench
     assert line["config"] == bench.shared_config(2)  # the very object our own arm prints: same config, key for key
+
+
+def test_reference_arm_falls_back_to_the_oracle_port_when_the_built_reference_is_missing():
+    """`--impl reference` must not die if oracle/_ref (built from the reference's nvml_dl.c where /root/reference exists)
+    did not travel: the oracle port — pynvml + oracle/wire_oracle.py — runs the same phases; kind says which one ran."""
+    fake = os.path.join(ROOT, "oracle", "_fake")
+    env = dict(os.environ, LD_LIBRARY_PATH=fake, FAKE_NVML_GPUS="8", GSB_BENCH_FORCE_PORT="1")
+    out = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--gpus", "4", "--steps", "3", "--warmup", "3",
+                          "--no-allocate"], env=env, capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert out.returncode == 0, out.stderr[-800:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
+    d = line["details"]
+    assert (d["devices_seen"], d["fake_devices"], d["lw_bytes"]) == (4, 716, 41804)
+    assert line["setup"]["register_calls"] == sum(179 * (1 + 2 * (g + 1) + 1) for g in range(4))  # same quadratic scan
